@@ -1,0 +1,93 @@
+// Per-channel statistics plumbing shared by every producer kernel (pointwise GEMM, depthwise).
+//
+// A producer CTA accumulates per-channel partial sums in shared memory, publishes them to
+// partials[cta][stat][C], and the LAST CTA to finish (threadfence + counter) reduces over CTAs in a
+// fixed order and runs the BatchNorm bookkeeping of nn.BatchNorm2d
+// (reference: models/mobilenet_base.py:203,417 -> torch.nn.BatchNorm2d semantics):
+//   forward : mean / biased var -> scale, shift (what the consumer kernel applies), saved
+//             mean/invstd, running stats with UNBIASED var, momentum or cumulative (momentum<0).
+//   backward: sum(dz), sum(dz*xhat) -> dgamma, dbeta and the affine coefficients
+//             dh = ca*dz + cb*h + cc that the consumer kernel applies on load.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/yamb200.h"
+
+namespace yamb {
+
+// Publish this CTA's partials (s_part: [2][C] in shared memory) and return true in the last CTA.
+// Must be called by ALL threads of the CTA.
+__device__ __forceinline__ bool publish_partials(const float* s_part, int C, float* partials,
+                                                 uint32_t* counter) {
+  __shared__ uint32_t s_is_last;
+  float* mine = partials + (size_t)blockIdx.x * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) mine[i] = s_part[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t prev = atomicAdd(counter, 1u);
+    s_is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_is_last) __threadfence();
+  return s_is_last != 0;
+}
+
+__device__ __forceinline__ void bn_fwd_finalize(const yamb_bn_fwd& f, int C, int nparts) {
+  const double inv_count = 1.0 / (double)f.count;
+  float factor = f.momentum;
+  if (f.num_batches_tracked != nullptr) {
+    long long nbt = *f.num_batches_tracked + 1;
+    if (f.momentum < 0.f) factor = 1.0f / (float)nbt;  // momentum=None: cumulative average
+    __syncthreads();
+    if (threadIdx.x == 0) *f.num_batches_tracked = nbt;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      s += (double)f.partials[(size_t)p * 2 * C + c];
+      q += (double)f.partials[(size_t)p * 2 * C + C + c];
+    }
+    double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    float g = f.gamma ? f.gamma[c] : 1.f;
+    float b = f.beta ? f.beta[c] : 0.f;
+    float sc = g * invstd;
+    f.scale[c] = sc;
+    f.shift[c] = b - (float)mean * sc;
+    if (f.mean) f.mean[c] = (float)mean;
+    if (f.invstd) f.invstd[c] = invstd;
+    if (f.running_mean) {
+      double unbiased = f.count > 1 ? var * ((double)f.count / (double)(f.count - 1)) : var;
+      f.running_mean[c] = (1.f - factor) * f.running_mean[c] + factor * (float)mean;
+      f.running_var[c] = (1.f - factor) * f.running_var[c] + factor * (float)unbiased;
+    }
+  }
+}
+
+__device__ __forceinline__ void bn_bwd_finalize(const yamb_bn_bwd& f, int C, int nparts) {
+  const double inv_count = 1.0 / (double)f.count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int p = 0; p < nparts; ++p) {
+      s += (double)f.partials[(size_t)p * 2 * C + c];
+      q += (double)f.partials[(size_t)p * 2 * C + C + c];
+    }
+    // s = sum(dz), q = sum(dz * xhat)
+    if (f.dgamma) f.dgamma[c] += (float)q;
+    if (f.dbeta) f.dbeta[c] += (float)s;
+    float g = f.gamma ? f.gamma[c] : 1.f;
+    float r = f.invstd[c];
+    float mu = f.mean[c];
+    float sc = g * r;
+    float m1 = (float)(s * inv_count), m2 = (float)(q * inv_count);
+    f.ca[c] = sc;
+    f.cb[c] = -sc * r * m2;
+    f.cc[c] = sc * (mu * r * m2 - m1);
+  }
+}
+
+}  // namespace yamb

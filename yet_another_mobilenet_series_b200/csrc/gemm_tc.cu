@@ -1,0 +1,698 @@
+// Pointwise-convolution GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane, tcgen05.mma.cta_group::1.kind::f16, M=128)
+//   warp 2      TMEM allocator / deallocator
+//   warp 3      idle
+//   warps 4-7   epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store,
+//               per-column BatchNorm statistics
+//   warps 8-11  operand transform (BN-apply + activation, or BN-backward affine) applied in place
+//               on the TMA-landed tile before the MMA reads it (only launched when needed)
+//
+// Replaces, behind yamb_pointwise_gemm (include/yamb200.h), the nn.Conv2d(kernel_size=1) forward /
+// dgrad / wgrad library calls of the reference block (models/mobilenet_base.py:391-395, :413,
+// :253-257, :284-285) together with the BatchNorm statistics passes (:203, :417).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "bn_finalize.cuh"
+#include "host_util.h"
+#include "prims.cuh"
+
+namespace yamb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int kPanelBytes64 = 8192;  // 64 rows x 128 B
+constexpr int kABytes = 16384;       // 128 x 64 bf16
+constexpr int kStageOutBytes = 16384;  // 128 rows x 64 cols bf16 staging sub-tile
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // two accumulator stages of 256 columns
+
+struct GemmDev {
+  int M, N, K;
+  int block_n, m_blocks, n_blocks, num_k_blocks, ksplit, kb_per_split, num_work;
+  int a_mn, b_mn;
+  int num_stages;
+  int b_bytes;      // bytes of the B region of one stage
+  int a2_off;       // offset of A2 region inside a stage (0 = none)
+  int b2_off;
+  int stage_bytes;
+  int a_xform, a_act, b_xform, b_act;
+  const float *a_scale, *a_shift, *a_scale2;
+  const float *b_scale, *b_shift, *b_scale2;
+  int epi;
+  int has_residual;
+  void* D;
+  long long ldd;
+  yamb_bn_fwd bnf;
+  int has_bnf;
+  const float *h_scale, *h_shift;
+  int h_act;
+  yamb_bn_bwd bnb;
+  int has_bnb;
+  // smem offsets (bytes from the 1024-aligned base)
+  int off_out, off_side, off_coef, off_stats, off_bars;
+};
+
+struct Bars {
+  uint64_t full[kMaxStages];
+  uint64_t xdone[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t side[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// In-place transform of one panel (R rows x 128 B, SWIZZLE_128B) by 128 threads.
+//   mode 1: v = act(s[c]*v + b[c])        mode 2: v = s[c]*v + s2[c]*v2 + b[c]
+// `t` in [0,128).  Channel of (logical 16B chunk lc, element e) = cbase + lc*8 + e.
+__device__ __forceinline__ void xform_panel(uint8_t* panel, const uint8_t* panel2, int R, int t,
+                                            int mode, int act, const float* cs, const float* cb,
+                                            const float* cs2, int cbase, int C, int row_limit) {
+  const int row = t % R;
+  const int parts = 128 / R;  // threads per row
+  const int per = 8 / parts;
+  const int part = t / R;
+  if (row >= row_limit) return;
+#pragma unroll 1
+  for (int j = 0; j < per; ++j) {
+    const int lc = part * per + j;
+    const int c0 = cbase + lc * 8;
+    if (c0 >= C) continue;
+    const int off = row * 128 + ((lc ^ (row & 7)) << 4);
+    uint4 v = *reinterpret_cast<uint4*>(panel + off);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (mode == 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo = act_fwd(fmaf(cs[c0 + 2 * q], bf16lo(w[q]), cb[c0 + 2 * q]), act);
+        float hi = act_fwd(fmaf(cs[c0 + 2 * q + 1], bf16hi(w[q]), cb[c0 + 2 * q + 1]), act);
+        w[q] = pack_bf16(lo, hi);
+      }
+    } else {
+      uint4 v2 = *reinterpret_cast<const uint4*>(panel2 + off);
+      uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float lo = fmaf(cs[c0 + 2 * q], bf16lo(w[q]),
+                        fmaf(cs2[c0 + 2 * q], bf16lo(w2[q]), cb[c0 + 2 * q]));
+        float hi = fmaf(cs[c0 + 2 * q + 1], bf16hi(w[q]),
+                        fmaf(cs2[c0 + 2 * q + 1], bf16hi(w2[q]), cb[c0 + 2 * q + 1]));
+        w[q] = pack_bf16(lo, hi);
+      }
+    }
+    *reinterpret_cast<uint4*>(panel + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <bool kXform>
+__global__ void __launch_bounds__(kXform ? 384 : 256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmS,
+               const __grid_constant__ GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  Bars* bars = reinterpret_cast<Bars*>(smem + p.off_bars);
+  float* s_stats = reinterpret_cast<float*>(smem + p.off_stats);  // [2][N]
+  float* s_coef = reinterpret_cast<float*>(smem + p.off_coef);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int S = p.num_stages;
+
+  // ---- one-time setup ------------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.epi != 2) tma_prefetch_desc(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->xdone[i], 128);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 128);
+      mbar_init(&bars->side[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_base, kTmemCols);
+    tmem_relinquish();
+  }
+  // zero the per-CTA statistics accumulators
+  if (p.has_bnf || p.has_bnb) {
+    for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) s_stats[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const uint32_t a_tx = (uint32_t)kABytes;
+  const bool use_x = kXform && (p.a_xform != 0 || p.b_xform != 0);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const int mn = w / p.ksplit, slab = w % p.ksplit;
+        const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
+        const int kb0 = slab * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          // count the bytes first, then issue
+          uint32_t tx = 0;
+          const int a_panels = p.a_mn ? 2 : 1;
+          int a_issue[2] = {0, 0};
+          if (!p.a_mn) {
+            tx += a_tx;
+          } else {
+            for (int q = 0; q < 2; ++q)
+              if (m_blk * kBlockM + q * 64 < p.M) { a_issue[q] = 1; tx += kPanelBytes64; }
+          }
+          const int b_panels = (p.block_n + 63) / 64;
+          if (!p.b_mn) {
+            tx += (uint32_t)p.block_n * 128u;
+          } else {
+            for (int q = 0; q < b_panels; ++q)
+              if (n_blk * p.block_n + q * 64 < p.N) tx += kPanelBytes64;
+          }
+          if (p.a_xform == 2) tx += p.a_mn ? (a_issue[0] + a_issue[1]) * kPanelBytes64 : a_tx;
+          if (p.b_xform == 2) {
+            if (!p.b_mn) tx += (uint32_t)p.block_n * 128u;
+            else
+              for (int q = 0; q < b_panels; ++q)
+                if (n_blk * p.block_n + q * 64 < p.N) tx += kPanelBytes64;
+          }
+          mbar_arrive_expect_tx(&bars->full[stage], tx);
+          if (!p.a_mn) {
+            tma_load_2d(&tmA, &bars->full[stage], sA, kb * kBlockK, m_blk * kBlockM);
+            if (p.a_xform == 2)
+              tma_load_2d(&tmA2, &bars->full[stage], sA + p.a2_off, kb * kBlockK, m_blk * kBlockM);
+          } else {
+            for (int q = 0; q < a_panels; ++q)
+              if (a_issue[q]) {
+                tma_load_2d(&tmA, &bars->full[stage], sA + q * kPanelBytes64,
+                            m_blk * kBlockM + q * 64, kb * kBlockK);
+                if (p.a_xform == 2)
+                  tma_load_2d(&tmA2, &bars->full[stage], sA + p.a2_off + q * kPanelBytes64,
+                              m_blk * kBlockM + q * 64, kb * kBlockK);
+              }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(&tmB, &bars->full[stage], sB, kb * kBlockK, n_blk * p.block_n);
+            if (p.b_xform == 2)
+              tma_load_2d(&tmB2, &bars->full[stage], sA + p.b2_off, kb * kBlockK,
+                          n_blk * p.block_n);
+          } else {
+            for (int q = 0; q < b_panels; ++q)
+              if (n_blk * p.block_n + q * 64 < p.N) {
+                tma_load_2d(&tmB, &bars->full[stage], sB + q * kPanelBytes64,
+                            n_blk * p.block_n + q * 64, kb * kBlockK);
+                if (p.b_xform == 2)
+                  tma_load_2d(&tmB2, &bars->full[stage], sA + p.b2_off + q * kPanelBytes64,
+                              n_blk * p.block_n + q * 64, kb * kBlockK);
+              }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, p.a_mn, p.b_mn);
+    int stage = 0, phase = 0, it = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
+      const int slab = w % p.ksplit;
+      const int kb0 = slab * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      const int as = it & 1;
+      mbar_wait(&bars->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccStride);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(use_x ? &bars->xdone[stage] : &bars->full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sB = sA + kABytes;
+          const int krem = p.K - kb * kBlockK;
+          const int nk = krem >= kBlockK ? 4 : (krem + 15) / 16;
+          for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t ad = p.a_mn ? umma_smem_desc(sA + kk * 2048, kPanelBytes64, 1024)
+                                       : umma_smem_desc(sA + kk * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? umma_smem_desc(sB + kk * 2048, kPanelBytes64, 1024)
+                                       : umma_smem_desc(sB + kk * 32, 16, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (kb == kb1 - 1) umma_commit(&bars->tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ======================================= epilogue =======================================
+    const int et = threadIdx.x - 128;  // 0..127
+    const int q = warp & 3;            // TMEM lane quadrant
+    const int row = q * 32 + lane;     // row inside the 128-row tile
+    uint8_t* s_out = smem + p.off_out;
+    uint8_t* s_side = smem + p.off_side;
+    // per-column coefficient tables for epi 1:  [h_scale | h_shift | mean | invstd] x N
+    const float* cz_s = s_coef;
+    const float* cz_t = s_coef + p.N;
+    const float* cz_m = s_coef + 2 * p.N;
+    const float* cz_r = s_coef + 3 * p.N;
+    if (p.epi == 1) {
+      float* wr = s_coef;
+      for (int i = et; i < p.N; i += 128) {
+        wr[i] = p.h_scale[i];
+        wr[p.N + i] = p.h_shift[i];
+        wr[2 * p.N + i] = p.bnb.mean[i];
+        wr[3 * p.N + i] = p.bnb.invstd[i];
+      }
+      named_bar_sync(1, 128);
+    }
+    int it = 0;
+    uint32_t sub_count = 0;   // running sub-tile counter -> staging buffer parity
+    uint32_t side_count = 0;  // running side-load counter
+    const bool side_in = (p.epi == 1) || p.has_residual;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
+      const int mn = w / p.ksplit;
+      const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
+      const int as = it & 1;
+      // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
+      const int n_sub = min((p.block_n + 63) / 64, (p.N - n_blk * p.block_n + 63) / 64);
+      const int grow = m_blk * kBlockM + row;
+      // prefetch the first side sub-tile of this tile
+      if (side_in && et == 0) {
+        const uint32_t sb = side_count & 1;
+        mbar_arrive_expect_tx(&bars->side[sb], kStageOutBytes);
+        tma_load_2d(&tmS, &bars->side[sb], s_side + sb * kStageOutBytes, n_blk * p.block_n,
+                    m_blk * kBlockM);
+      }
+      mbar_wait(&bars->tmem_full[as], (it >> 1) & 1);
+      tc_fence_after();
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int col0 = n_blk * p.block_n + sub * 64;  // global column of this sub-tile
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + sub * 64);
+        uint32_t acc[2][32];
+        tmem_ld_32x32(taddr, acc[0]);
+        tmem_ld_32x32(taddr + 32, acc[1]);
+        tmem_ld_wait();
+        if (sub == n_sub - 1) {
+          // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&bars->tmem_empty[as]);
+        }
+        if (p.epi == 2) {
+          // split-K partial sums: fp32 atomic accumulate into D[M][ldd]
+          if (grow < p.M) {
+            float* drow = reinterpret_cast<float*>(p.D) + (size_t)grow * p.ldd;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = col0 + h * 32 + j;
+                if (c < p.N && (sub * 64 + h * 32 + j) < p.block_n)
+                  atomicAdd(drow + c, __uint_as_float(acc[h][j]));
+              }
+          }
+          continue;
+        }
+        const uint32_t ob = sub_count & 1;
+        uint8_t* sO = s_out + ob * kStageOutBytes;
+        // the TMA store that last read this staging buffer must have drained
+        if (et == 0) tma_store_wait_read<1>();
+        const uint8_t* sS = nullptr;
+        if (side_in) {
+          const uint32_t sb = side_count & 1;
+          sS = s_side + sb * kStageOutBytes;
+          mbar_wait(&bars->side[sb], (side_count >> 1) & 1);
+        }
+        named_bar_sync(1, 128);
+        // kick the next side sub-tile (its buffer was consumed two sub-tiles ago; all threads have
+        // passed the barrier above, which is after their last read of it)
+        if (side_in && et == 0 && sub + 1 < n_sub) {
+          const uint32_t sb = (side_count + 1) & 1;
+          mbar_arrive_expect_tx(&bars->side[sb], kStageOutBytes);
+          tma_load_2d(&tmS, &bars->side[sb], s_side + sb * kStageOutBytes, col0 + 64,
+                      m_blk * kBlockM);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 columns
+          const int pc = ch ^ (row & 7);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
+          if (side_in) {
+            const uint4 sv = *reinterpret_cast<const uint4*>(sS + row * 128 + (pc << 4));
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            if (p.epi == 0) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += bf16lo(sw[e]);
+                v[2 * e + 1] += bf16hi(sw[e]);
+              }
+            } else {
+              const int cb = col0 + ch * 8;
+              if (cb < p.N) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float h0 = bf16lo(sw[e]), h1 = bf16hi(sw[e]);
+                  const float z0 = fmaf(cz_s[cb + 2 * e], h0, cz_t[cb + 2 * e]);
+                  const float z1 = fmaf(cz_s[cb + 2 * e + 1], h1, cz_t[cb + 2 * e + 1]);
+                  v[2 * e] *= act_bwd(z0, p.h_act);
+                  v[2 * e + 1] *= act_bwd(z1, p.h_act);
+                }
+              }
+            }
+          }
+          uint4 o;
+          o.x = pack_bf16(v[0], v[1]);
+          o.y = pack_bf16(v[2], v[3]);
+          o.z = pack_bf16(v[4], v[5]);
+          o.w = pack_bf16(v[6], v[7]);
+          *reinterpret_cast<uint4*>(sO + row * 128 + (pc << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          tma_store_2d(&tmD, sO, col0, m_blk * kBlockM);
+          tma_store_commit();
+        }
+        // ---- per-column statistics of the bf16-rounded output tile ----
+        if (p.has_bnf || p.has_bnb) {
+          const int cp = et & 31;  // column pair
+          const int rg = et >> 5;  // row group of 32 rows
+          const int c = col0 + 2 * cp;
+          if (c < p.N && (sub * 64 + 2 * cp) < p.block_n) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const int rmax = min(32, p.M - (m_blk * kBlockM + rg * 32));
+            if (p.has_bnf) {
+              for (int r = 0; r < rmax; ++r) {
+                const int rr = rg * 32 + r;
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                    sO + rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+                const float a = bf16lo(u), b = bf16hi(u);
+                s0 += a; s1 += b;
+                q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+              }
+            } else {
+              const float m0 = cz_m[c], m1 = cz_m[c + 1], r0 = cz_r[c], r1 = cz_r[c + 1];
+              for (int r = 0; r < rmax; ++r) {
+                const int rr = rg * 32 + r;
+                const int off = rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2);
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + off);
+                const uint32_t hh = *reinterpret_cast<const uint32_t*>(sS + off);
+                const float a = bf16lo(u), b = bf16hi(u);
+                s0 += a; s1 += b;
+                q0 = fmaf(a, (bf16lo(hh) - m0) * r0, q0);
+                q1 = fmaf(b, (bf16hi(hh) - m1) * r1, q1);
+              }
+            }
+            atomicAdd(&s_stats[c], s0);
+            atomicAdd(&s_stats[c + 1], s1);
+            atomicAdd(&s_stats[p.N + c], q0);
+            atomicAdd(&s_stats[p.N + c + 1], q1);
+          }
+        }
+        ++sub_count;
+        if (side_in) ++side_count;
+      }
+    }
+    if (et == 0 && p.epi != 2) tma_store_wait_all<0>();
+  } else if (kXform && warp >= 8) {
+    // ================================== operand transform ==================================
+    if (use_x) {
+      const int t = threadIdx.x - 256;
+      // coefficient tables in smem: A: [scale|shift|scale2] x Ca, then B likewise
+      const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
+      const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
+      float* xa = s_coef + (p.epi == 1 ? 4 * p.N : 0);
+      float* xb = xa + 3 * Ca;
+      for (int i = t; i < Ca; i += 128) {
+        xa[i] = p.a_scale[i];
+        xa[Ca + i] = p.a_shift[i];
+        xa[2 * Ca + i] = p.a_xform == 2 ? p.a_scale2[i] : 0.f;
+      }
+      for (int i = t; i < Cb; i += 128) {
+        xb[i] = p.b_scale[i];
+        xb[Cb + i] = p.b_shift[i];
+        xb[2 * Cb + i] = p.b_xform == 2 ? p.b_scale2[i] : 0.f;
+      }
+      named_bar_sync(2, 128);
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+        const int mn = w / p.ksplit, slab = w % p.ksplit;
+        const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
+        const int kb0 = slab * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          if (p.a_xform) {
+            if (!p.a_mn) {
+              xform_panel(sA, sA + p.a2_off, 128, t, p.a_xform, p.a_act, xa, xa + Ca, xa + 2 * Ca,
+                          kb * kBlockK, p.K, p.M - m_blk * kBlockM);
+            } else {
+              for (int q = 0; q < 2; ++q)
+                if (m_blk * kBlockM + q * 64 < p.M)
+                  xform_panel(sA + q * kPanelBytes64, sA + p.a2_off + q * kPanelBytes64, 64, t,
+                              p.a_xform, p.a_act, xa, xa + Ca, xa + 2 * Ca,
+                              m_blk * kBlockM + q * 64, p.M, p.K - kb * kBlockK);
+            }
+          }
+          if (p.b_xform) {
+            if (!p.b_mn) {
+              // K-major B: rows are output channels; transform is along K
+              for (int r0 = 0; r0 < p.block_n; r0 += 128)
+                xform_panel(sB + r0 * 128, sA + p.b2_off + r0 * 128, 128, t, p.b_xform, p.b_act, xb,
+                            xb + Cb, xb + 2 * Cb, kb * kBlockK, p.K,
+                            min(128, p.block_n - r0));
+            } else {
+              const int b_panels = (p.block_n + 63) / 64;
+              for (int q = 0; q < b_panels; ++q)
+                if (n_blk * p.block_n + q * 64 < p.N)
+                  xform_panel(sB + q * kPanelBytes64, sA + p.b2_off + q * kPanelBytes64, 64, t,
+                              p.b_xform, p.b_act, xb, xb + Cb, xb + 2 * Cb,
+                              n_blk * p.block_n + q * 64, p.N, p.K - kb * kBlockK);
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&bars->xdone[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+  if (p.has_bnf) {
+    if (publish_partials(s_stats, p.N, p.bnf.partials, p.bnf.counter)) {
+      bn_fwd_finalize(p.bnf, p.N, gridDim.x);
+      __syncthreads();
+      if (threadIdx.x == 0) *p.bnf.counter = 0;
+    }
+  } else if (p.has_bnb) {
+    if (publish_partials(s_stats, p.N, p.bnb.partials, p.bnb.counter)) {
+      bn_bwd_finalize(p.bnb, p.N, gridDim.x);
+      __syncthreads();
+      if (threadIdx.x == 0) *p.bnb.counter = 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int make_map_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
+                       uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  static PFN_encodeTiled encode = get_encode_tiled();
+  if (!encode) return set_error(YAMB_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (strides[0] & 15))
+    return set_error(YAMB_EINVAL, "TMA operand must be 16-byte aligned with a 16-byte row pitch");
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(YAMB_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static int pick_block_n(int N) {
+  if (N <= 256) return (N + 15) / 16 * 16;
+  // multi-block: block_n must be a multiple of 64 so staging sub-tiles never straddle blocks
+  int best = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 128; bn -= 64) {
+    int blocks = (N + bn - 1) / bn;
+    int waste = blocks * bn - N;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
+  }
+  return best;
+}
+
+int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
+  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(YAMB_EINVAL, "bad GEMM shape");
+  if ((a->N % 8) || (a->a_mn_major ? (a->M % 8) : (a->K % 8)) || (a->b_mn_major ? 0 : (a->K % 8)))
+    return set_error(YAMB_EINVAL, "GEMM channel dims must be multiples of 8 (M=%d N=%d K=%d)",
+                     a->M, a->N, a->K);
+  if (a->epi < 0 || a->epi > 2) return set_error(YAMB_EINVAL, "bad epilogue");
+  int dev_ctas = max_ctas();
+  if (dev_ctas <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.block_n = pick_block_n(a->N);
+  p.m_blocks = (a->M + kBlockM - 1) / kBlockM;
+  p.n_blocks = (a->N + p.block_n - 1) / p.block_n;
+  p.num_k_blocks = (a->K + kBlockK - 1) / kBlockK;
+  p.epi = a->epi;
+  p.a_xform = a->a_xform; p.a_act = a->a_act;
+  p.b_xform = a->b_xform; p.b_act = a->b_act;
+  p.a_scale = a->a_scale; p.a_shift = a->a_shift; p.a_scale2 = a->a_scale2;
+  p.b_scale = a->b_scale; p.b_shift = a->b_shift; p.b_scale2 = a->b_scale2;
+  if ((p.a_xform && (!a->a_scale || !a->a_shift)) || (p.b_xform && (!a->b_scale || !a->b_shift)))
+    return set_error(YAMB_EINVAL, "operand transform without coefficients");
+  if ((p.a_xform == 2 && (!a->A2 || !a->a_scale2)) || (p.b_xform == 2 && (!a->B2 || !a->b_scale2)))
+    return set_error(YAMB_EINVAL, "two-source transform without second tensor");
+  p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
+  p.D = a->D; p.ldd = a->ldd;
+  if (a->epi == 0 && a->bn_fwd) { p.bnf = *a->bn_fwd; p.has_bnf = 1; }
+  if (a->epi == 1) {
+    if (!a->H || !a->h_scale || !a->h_shift || !a->bn_bwd)
+      return set_error(YAMB_EINVAL, "dz epilogue needs H, h_scale, h_shift, bn_bwd");
+    p.bnb = *a->bn_bwd; p.has_bnb = 1;
+    p.h_scale = a->h_scale; p.h_shift = a->h_shift; p.h_act = a->h_act;
+  }
+  // split-K only for the atomic epilogue
+  const int mn_tiles = p.m_blocks * p.n_blocks;
+  int ctas = dev_ctas;
+  if (a->max_ctas > 0 && a->max_ctas < ctas) ctas = a->max_ctas;
+  p.ksplit = 1;
+  if (a->epi == 2) {
+    int want = (2 * ctas + mn_tiles - 1) / mn_tiles;
+    int maxsplit = (p.num_k_blocks + 3) / 4;
+    p.ksplit = want < 1 ? 1 : (want > maxsplit ? maxsplit : want);
+    if (p.ksplit < 1) p.ksplit = 1;
+  }
+  p.kb_per_split = (p.num_k_blocks + p.ksplit - 1) / p.ksplit;
+  p.ksplit = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty slabs
+  p.num_work = mn_tiles * p.ksplit;
+
+  // ---- shared memory plan ----
+  const int b_panels = (p.block_n + 63) / 64;
+  p.b_bytes = p.b_mn ? b_panels * kPanelBytes64 : ((p.block_n * 128 + 1023) / 1024) * 1024;
+  int stage = kABytes + p.b_bytes;
+  if (p.a_xform == 2) { p.a2_off = stage; stage += kABytes; }
+  if (p.b_xform == 2) { p.b2_off = stage; stage += p.b_bytes; }
+  p.stage_bytes = stage;
+  const bool xf = p.a_xform || p.b_xform;
+  const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
+  const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
+  int fixed = 0;
+  int out_bytes = (a->epi == 2) ? 0 : 2 * kStageOutBytes;
+  int side_bytes = (a->epi == 1 || p.has_residual) ? 2 * kStageOutBytes : 0;
+  int coef_bytes = ((a->epi == 1 ? 4 * p.N : 0) + 3 * Ca + 3 * Cb) * 4;
+  int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * 4 : 0;
+  fixed = out_bytes + side_bytes + ((coef_bytes + 15) & ~15) + ((stats_bytes + 15) & ~15) +
+          (int)sizeof(Bars) + 64;
+  const int budget = 232448 - 1024;  // 227 KB minus alignment slack
+  int stages = (budget - fixed) / p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return set_error(YAMB_EINVAL, "GEMM tile does not fit shared memory");
+  p.num_stages = stages;
+  int off = stages * p.stage_bytes;
+  p.off_out = off; off += out_bytes;
+  p.off_side = off; off += side_bytes;
+  p.off_coef = off; off += (coef_bytes + 15) & ~15;
+  p.off_stats = off; off += (stats_bytes + 15) & ~15;
+  p.off_bars = (off + 15) & ~15; off = p.off_bars + (int)sizeof(Bars);
+  const int smem_total = off + 1024;
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmD, tmS;
+  memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB2, 0, sizeof(tmB2));
+  memset(&tmD, 0, sizeof(tmD)); memset(&tmS, 0, sizeof(tmS));
+  int rc;
+  if (!p.a_mn) rc = make_map_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128);
+  else rc = make_map_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_map_2d(&tmB, a->B, a->K, a->N, a->ldb, 64, p.block_n);
+  else rc = make_map_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, 64);
+  if (rc) return rc;
+  if (p.a_xform == 2) {
+    if (!p.a_mn) rc = make_map_2d(&tmA2, a->A2, a->K, a->M, a->lda2, 64, 128);
+    else rc = make_map_2d(&tmA2, a->A2, a->M, a->K, a->lda2, 64, 64);
+    if (rc) return rc;
+  }
+  if (p.b_xform == 2) {
+    if (!p.b_mn) rc = make_map_2d(&tmB2, a->B2, a->K, a->N, a->ldb2, 64, p.block_n);
+    else rc = make_map_2d(&tmB2, a->B2, a->N, a->K, a->ldb2, 64, 64);
+    if (rc) return rc;
+  }
+  if (a->epi != 2) {
+    rc = make_map_2d(&tmD, a->D, a->N, a->M, a->ldd, 64, 128);
+    if (rc) return rc;
+  }
+  if (a->epi == 1) rc = make_map_2d(&tmS, a->H, a->N, a->M, a->ldh, 64, 128);
+  else if (p.has_residual) rc = make_map_2d(&tmS, a->residual, a->N, a->M, a->ldr, 64, 128);
+  if (rc) return rc;
+
+  const int grid = p.num_work < ctas ? p.num_work : ctas;
+  cudaError_t e;
+  if (xf) {
+    e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_total);
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
+    gemm_tc_kernel<true><<<grid, 384, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, tmS, p);
+  } else {
+    e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_total);
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
+    gemm_tc_kernel<false><<<grid, 256, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, tmS, p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace yamb

@@ -1,0 +1,103 @@
+"""ctypes binding of libyamb200.so (the C ABI declared in include/yamb200.h).
+
+There is no fallback: if the shared library is missing or no CUDA device is present the compute
+entry points raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyamb200.so")
+
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SWISH, ACT_HSWISH = 0, 1, 2, 3, 4
+
+c_f32p = C.c_void_p  # device pointers are passed as integers
+
+
+class BnFwd(C.Structure):
+    _fields_ = [
+        ("partials", C.c_void_p), ("counter", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("eps", C.c_float), ("momentum", C.c_float),
+        ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+        ("num_batches_tracked", C.c_void_p),
+        ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p),
+        ("count", C.c_int64),
+    ]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [
+        ("partials", C.c_void_p), ("counter", C.c_void_p),
+        ("gamma", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("ca", C.c_void_p), ("cb", C.c_void_p), ("cc", C.c_void_p),
+        ("count", C.c_int64),
+    ]
+
+
+class Gemm(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64),
+        ("B", C.c_void_p), ("ldb", C.c_int64),
+        ("D", C.c_void_p), ("ldd", C.c_int64),
+        ("epi", C.c_int32),
+        ("a_xform", C.c_int32), ("a_act", C.c_int32),
+        ("a_scale", C.c_void_p), ("a_shift", C.c_void_p), ("a_scale2", C.c_void_p),
+        ("A2", C.c_void_p), ("lda2", C.c_int64),
+        ("b_xform", C.c_int32), ("b_act", C.c_int32),
+        ("b_scale", C.c_void_p), ("b_shift", C.c_void_p), ("b_scale2", C.c_void_p),
+        ("B2", C.c_void_p), ("ldb2", C.c_int64),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("bn_fwd", C.POINTER(BnFwd)),
+        ("H", C.c_void_p), ("ldh", C.c_int64),
+        ("h_scale", C.c_void_p), ("h_shift", C.c_void_p), ("h_act", C.c_int32),
+        ("bn_bwd", C.POINTER(BnBwd)),
+        ("max_ctas", C.c_int32),
+    ]
+
+
+_STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm}
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libyamb200.so (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                "libyamb200.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        l = C.CDLL(LIB_PATH)
+        l.yamb_last_error.restype = C.c_char_p
+        l.yamb_struct_size.argtypes = [C.c_int]
+        for which, st in _STRUCTS.items():
+            n = l.yamb_struct_size(which)
+            if n != C.sizeof(st):
+                raise NativeError("ABI mismatch for struct %d: C %d vs ctypes %d" %
+                                  (which, n, C.sizeof(st)))
+        l.yamb_pointwise_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError("yamb200 error %d: %s" % (rc, lib().yamb_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
