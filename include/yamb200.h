@@ -82,6 +82,7 @@ typedef struct yamb_bn_bwd {
   float* cb;           /* out [C] */
   float* cc;           /* out [C] */
   int64_t count;
+  int32_t use_batch_stats; /* 1: train-mode BN (batch statistics); 0: eval-mode BN => dh = ca*dz */
 } yamb_bn_bwd;
 
 /* ---- pointwise (1x1) convolution = GEMM on tcgen05 tensor cores ----------------------------------
@@ -126,10 +127,97 @@ typedef struct yamb_gemm {
 
 int yamb_pointwise_gemm(const yamb_gemm* args, yamb_stream_t stream);
 
-/* number of CTAs the persistent kernels launch at most (sizes the `partials` workspaces) */
+/* ---- depthwise k x k convolution (k in {3,5,7}, stride 1/2, pad (k-1)/2) -------------------------
+ * Replaces nn.Conv2d(groups=C)+BatchNorm2d+activation of ConvBNReLU
+ * (reference: models/mobilenet_base.py:405-411 unfused, :275-281 fused, :181-203 ConvBNReLU).
+ * Operates on a channel SLICE [c0, c0+C) of NHWC tensors whose row pitch is ldc channels: all
+ * pointers are pre-offset to the slice's first channel (multi-kernel-size branches of one hidden
+ * tensor are one call per branch; reference :266 Narrow, :332-336 cat).
+ *   forward : y = dwconv(act(in_scale*x + in_shift), w)   (in_scale NULL => y = dwconv(x, w))
+ *             + BatchNorm statistics of y (bn, optional)
+ *   backward: dh = ca*dz + cb*h + cc ;  da = dwconv^T(dh, w) ;  dw += sum dh * act(z) ;
+ *             dx = da * act'(z) (+ residual),  z = in_scale*x + in_shift ;
+ *             statistics sum(dx), sum(dx*xhat) for the preceding BatchNorm (bn, optional)
+ * w / dw: fp32 [C][k][k] (the reference's [C,1,k,k] parameter layout). */
+typedef struct yamb_dw_fwd {
+  int32_t N, H, W, C, ldc, k, stride;
+  const void* x;
+  const float* in_scale; const float* in_shift; int32_t in_act;
+  const float* w;
+  void* y;
+  const yamb_bn_fwd* bn;
+} yamb_dw_fwd;
+
+typedef struct yamb_dw_bwd {
+  int32_t N, H, W, C, ldc, k, stride;
+  const void* dz; const void* h;                     /* [N,Ho,Wo,ldc] */
+  const float* ca; const float* cb; const float* cc; /* dh = ca*dz + cb*h + cc */
+  const float* w; float* dw;
+  const void* x;                                     /* [N,H,W,ldc] pre-BN input of the stage */
+  const float* in_scale; const float* in_shift; int32_t in_act;
+  void* dx;
+  const void* residual;                              /* bf16 [N,H,W,ldc] added to dx, or NULL */
+  const yamb_bn_bwd* bn;
+} yamb_dw_bwd;
+
+int yamb_depthwise_fwd(const yamb_dw_fwd* args, yamb_stream_t stream);
+int yamb_depthwise_bwd(const yamb_dw_bwd* args, yamb_stream_t stream);
+
+/* ---- per-channel elementwise / reduction on [M, C] bf16 matrices ---------------------------------
+ * bn_apply : y = act(scale*h + shift) * gate[n][c] + residual     (pw_bn + skip connection,
+ *            reference models/mobilenet_base.py:448-450, :340-341; SE gating :113)
+ * bn_reduce: sum(dy), sum(dy*xhat) + BatchNorm-backward finalize  (autograd of :417 pw_bn) */
+typedef struct yamb_bn_apply {
+  int64_t M; int32_t C; int32_t ldh, ldr, ldy;
+  const void* h; const float* scale; const float* shift; int32_t act;
+  const void* residual; void* y;
+  const float* gate; int64_t rows_per_sample;   /* optional [N][C] fp32 gate */
+} yamb_bn_apply;
+
+typedef struct yamb_bn_reduce {
+  int64_t M; int32_t C; int32_t lddy, ldh;
+  const void* dy; const void* h;
+  const yamb_bn_bwd* bn;
+} yamb_bn_reduce;
+
+typedef struct yamb_se_pool {
+  int32_t N, HW, C, ldh;
+  const void* h; const float* scale; const float* shift; int32_t act;
+  float* pooled;
+} yamb_se_pool;
+
+int yamb_bn_apply_fwd(const yamb_bn_apply* args, yamb_stream_t stream);
+int yamb_bn_reduce_bwd(const yamb_bn_reduce* args, yamb_stream_t stream);
+int yamb_se_pool_fwd(const yamb_se_pool* args, yamb_stream_t stream);
+
+/* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
+ * Replaces RMSprop.step (reference utils/rmsprop.py:67-129), the gradient of cal_l2_loss
+ * (utils/optim.py:177-200; l2 * p added where wd_mask != 0), the division by world size of
+ * _allreduce_coalesced (utils/distributed.py:136; grad_scale) and ExponentialMovingAverage.forward
+ * (utils/optim.py:53-64; ema / ema_m) in ONE launch over flat fp32 arenas of n elements.
+ * hyper: optional device array [lr, ema_m] read instead of the host scalars (CUDA-graph replay). */
+typedef struct yamb_rmsprop {
+  int64_t n;
+  float* p; const float* g; float* sq; float* mom; float* grad_avg;
+  float* ema; void* p_bf16; const uint8_t* wd_mask;
+  const float* hyper;
+  float lr, alpha, eps, momentum, weight_decay, l2, grad_scale, ema_m;
+  int32_t eps_inside_sqrt, centered;
+} yamb_rmsprop;
+
+int yamb_rmsprop_step(const yamb_rmsprop* args, yamb_stream_t stream);
+/* shadow = m*shadow + (1-m)*x over n floats (BN running statistics; common.py:58-63) */
+int yamb_ema_update(float* shadow, const float* x, int64_t n, const float* hyper, float m,
+                    yamb_stream_t stream);
+/* dst(bf16) = src(fp32) */
+int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t stream);
+
+/* upper bound of CTAs any statistics-producing kernel launches (sizes `partials`: 2*C floats
+ * per CTA); 2 x SM count; <= 0 without a device */
 int yamb_max_ctas(void);
 
-/* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, ...) so bindings can self-check */
+/* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
+ * 6 bn_reduce, 7 se_pool, 8 rmsprop) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

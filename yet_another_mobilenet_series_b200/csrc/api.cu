@@ -49,18 +49,40 @@ extern "C" {
 
 const char* yamb_last_error(void) { return yamb::g_err; }
 int yamb_version(void) { return 100; }
-int yamb_max_ctas(void) { return yamb::max_ctas(); }
+int yamb_max_ctas(void) { int n = yamb::max_ctas(); return n > 0 ? 2 * n : n; }
 int yamb_struct_size(int which) {
   switch (which) {
     case 0: return (int)sizeof(yamb_bn_fwd);
     case 1: return (int)sizeof(yamb_bn_bwd);
     case 2: return (int)sizeof(yamb_gemm);
+    case 3: return (int)sizeof(yamb_dw_fwd);
+    case 4: return (int)sizeof(yamb_dw_bwd);
+    case 5: return (int)sizeof(yamb_bn_apply);
+    case 6: return (int)sizeof(yamb_bn_reduce);
+    case 7: return (int)sizeof(yamb_se_pool);
+    case 8: return (int)sizeof(yamb_rmsprop);
     default: return -1;
   }
 }
 
 int yamb_pointwise_gemm(const yamb_gemm* args, yamb_stream_t stream) {
   return yamb::gemm_launch(args, reinterpret_cast<cudaStream_t>(stream));
+}
+
+
+#define YAMB_ST(s) reinterpret_cast<cudaStream_t>(s)
+int yamb_depthwise_fwd(const yamb_dw_fwd* a, yamb_stream_t s) { return yamb::dw_fwd_launch(a, YAMB_ST(s)); }
+int yamb_depthwise_bwd(const yamb_dw_bwd* a, yamb_stream_t s) { return yamb::dw_bwd_launch(a, YAMB_ST(s)); }
+int yamb_bn_apply_fwd(const yamb_bn_apply* a, yamb_stream_t s) { return yamb::bn_apply_launch(a, YAMB_ST(s)); }
+int yamb_bn_reduce_bwd(const yamb_bn_reduce* a, yamb_stream_t s) { return yamb::bn_reduce_launch(a, YAMB_ST(s)); }
+int yamb_se_pool_fwd(const yamb_se_pool* a, yamb_stream_t s) { return yamb::se_pool_launch(a, YAMB_ST(s)); }
+int yamb_rmsprop_step(const yamb_rmsprop* a, yamb_stream_t s) { return yamb::rmsprop_launch(a, YAMB_ST(s)); }
+int yamb_ema_update(float* shadow, const float* x, int64_t n, const float* hyper, float m,
+                    yamb_stream_t s) {
+  return yamb::ema_launch(shadow, x, n, hyper, m, YAMB_ST(s));
+}
+int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t s) {
+  return yamb::cast_bf16_launch(src, dst, n, YAMB_ST(s));
 }
 
 }  // extern "C"

@@ -85,8 +85,8 @@ __device__ __forceinline__ void bn_bwd_finalize(const yamb_bn_bwd& f, int C, int
     float sc = g * r;
     float m1 = (float)(s * inv_count), m2 = (float)(q * inv_count);
     f.ca[c] = sc;
-    f.cb[c] = -sc * r * m2;
-    f.cc[c] = sc * (mu * r * m2 - m1);
+    f.cb[c] = f.use_batch_stats ? -sc * r * m2 : 0.f;
+    f.cc[c] = f.use_batch_stats ? sc * (mu * r * m2 - m1) : 0.f;
   }
 }
 

@@ -1,0 +1,218 @@
+// HBM-bound per-channel kernels on [pixels, channels] bf16 matrices, sm_100a:
+//   bn_apply   y = act(scale[c]*h + shift[c]) (+ residual)        — pw_bn + skip connection of
+//              the block (reference models/mobilenet_base.py:448-450, :340-341) and the
+//              ConvBNReLU tails (:203)
+//   bn_reduce  sum(dy), sum(dy*xhat) per channel + BatchNorm-backward finalize (last CTA)
+//   se_pool / se_gate / se_bwd: Squeeze-and-Excitation pieces (reference :110-113)
+// 16-byte vector accesses, consecutive threads -> consecutive channel groups, then pixels.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "bn_finalize.cuh"
+#include "host_util.h"
+#include "prims.cuh"
+
+namespace yamb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+  v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                    pack_bf16(v[6], v[7]));
+}
+
+struct BnApplyDev {
+  long long M;
+  int C, ldh, ldr, ldy;
+  const __nv_bfloat16* h;
+  const float *scale, *shift;
+  int act;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* y;
+  // optional per-(sample, channel) gate (SE): y *= gate[n][c], n = row / rows_per_sample
+  const float* gate;
+  long long rows_per_sample;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __grid_constant__ BnApplyDev p) {
+  const int CG = p.C / 8;
+  const long long total = p.M * CG;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CG;
+    const int c0 = (int)(i % CG) * 8;
+    float v[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = act_fwd(fmaf(sc[e], v[e], sh[e]), p.act);
+    if (p.gate) {
+      const float* g = p.gate + (row / p.rows_per_sample) * p.C + c0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= __ldg(g + e);
+    }
+    if (p.residual) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + c0)), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    *reinterpret_cast<uint4*>(p.y + row * p.ldy + c0) = pack8(v);
+  }
+}
+
+struct BnReduceDev {
+  long long M;
+  int C, lddy, ldh;
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* h;
+  yamb_bn_bwd bn;
+};
+
+// sum(dy), sum(dy * xhat) with xhat = (h - mean) * invstd; thread owns one 8-channel group.
+__global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ BnReduceDev p) {
+  extern __shared__ float s_part[];  // [2][C]
+  const int CG = p.C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  // channel groups beyond 256 are covered by looping cg
+  for (int cgb = 0; cgb < CG; cgb += 256) {
+    const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
+    const int px = CG >= 256 ? 0 : threadIdx.x / CG;
+    if (cg < CG && px < PX) {
+      const int c0 = cg * 8;
+      float mu[8], rs[8], s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        mu[e] = __ldg(p.bn.mean + c0 + e);
+        rs[e] = __ldg(p.bn.invstd + c0 + e);
+        s[e] = q[e] = 0.f;
+      }
+      for (long long row = (long long)blockIdx.x * PX + px; row < p.M;
+           row += (long long)gridDim.x * PX) {
+        float d[8], hv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.lddy + c0)), d);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e] += d[e];
+          q[e] = fmaf(d[e], (hv[e] - mu[e]) * rs[e], q[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_part[c0 + e], s[e]);
+        atomicAdd(&s_part[p.C + c0 + e], q[e]);
+      }
+    }
+  }
+  __syncthreads();
+  if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
+    bn_bwd_finalize(p.bn, p.C, gridDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) *p.bn.counter = 0;
+  }
+}
+
+// ---- Squeeze-and-Excitation ----------------------------------------------------------------------
+// pooled[n][c] = mean over HW of act(scale*h+shift)  (a2 is never materialised).
+struct SePoolDev {
+  int N, HW, C, ldh;
+  const __nv_bfloat16* h;
+  const float *scale, *shift;
+  int act;
+  float* pooled;  // [N][C]
+};
+__global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ SePoolDev p) {
+  // grid: (N, ceil(C/8/32)); block: 32 channel groups x 8 pixel lanes
+  const int n = blockIdx.x;
+  const int cg = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int pl = threadIdx.x >> 5;  // 0..7
+  __shared__ float red[8][32][8];
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  const bool ok = cg * 8 < p.C;
+  if (ok) {
+    const int c0 = cg * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+    for (int i = pl; i < p.HW; i += 8) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + ((size_t)n * p.HW + i) * p.ldh + c0)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += round_bf16(act_fwd(fmaf(sc[e], v[e], sh[e]), p.act));
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][threadIdx.x & 31][e] = s[e];
+  __syncthreads();
+  if (pl == 0 && ok) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x & 31][e];
+      p.pooled[(size_t)n * p.C + cg * 8 + e] = t / (float)p.HW;
+    }
+  }
+}
+
+int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t st) {
+  if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8)) return set_error(YAMB_EINVAL, "bn_apply shape");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  BnApplyDev p;
+  p.M = a->M; p.C = a->C; p.ldh = a->ldh; p.ldr = a->ldr; p.ldy = a->ldy;
+  p.h = (const __nv_bfloat16*)a->h; p.scale = a->scale; p.shift = a->shift; p.act = a->act;
+  p.residual = (const __nv_bfloat16*)a->residual; p.y = (__nv_bfloat16*)a->y;
+  p.gate = a->gate; p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
+  const long long total = a->M * (a->C / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)max_ctas() * 16;
+  bn_apply_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_apply: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t st) {
+  if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8) || !a->bn)
+    return set_error(YAMB_EINVAL, "bn_reduce shape");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  BnReduceDev p;
+  p.M = a->M; p.C = a->C; p.lddy = a->lddy; p.ldh = a->ldh;
+  p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h; p.bn = *a->bn;
+  const int CG = a->C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  long long want = (a->M + PX - 1) / PX;
+  int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
+  bn_reduce_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_reduce: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int se_pool_launch(const yamb_se_pool* a, cudaStream_t st) {
+  if (!a || a->N <= 0 || a->HW <= 0 || a->C <= 0 || (a->C % 8))
+    return set_error(YAMB_EINVAL, "se_pool shape");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  SePoolDev p;
+  p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldh = a->ldh;
+  p.h = (const __nv_bfloat16*)a->h; p.scale = a->scale; p.shift = a->shift; p.act = a->act;
+  p.pooled = a->pooled;
+  dim3 grid(a->N, (a->C / 8 + 31) / 32);
+  se_pool_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace yamb

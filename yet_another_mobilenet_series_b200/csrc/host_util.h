@@ -17,5 +17,14 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 
 int gemm_launch(const yamb_gemm* a, cudaStream_t stream);
+int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t stream);
+int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t stream);
+int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t stream);
+int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t stream);
+int se_pool_launch(const yamb_se_pool* a, cudaStream_t stream);
+int rmsprop_launch(const yamb_rmsprop* a, cudaStream_t stream);
+int ema_launch(float* shadow, const float* x, long long n, const float* hyper, float m,
+               cudaStream_t stream);
+int cast_bf16_launch(const float* src, void* dst, long long n, cudaStream_t stream);
 
 }  // namespace yamb

@@ -1,0 +1,636 @@
+"""Host-side sequencing of the sm_100a kernels for one inverted-residual block.
+
+A `BlockPlan` owns the HBM-resident intermediates of one block for one input shape
+(NHWC bf16 [pixels, channels] matrices) and the pre-built C-ABI argument structs; `block_apply`
+is the autograd entry the modules in `mobilenet_base.py` call.  Kernel order (train mode):
+
+  forward   expand GEMM (+BN1 stats) -> depthwise (BN1+act on load, +BN2 stats)
+            -> project GEMM (BN2+act operand transform, +BN3 stats) -> BN3 apply (+x)
+  backward  BN3 reduce -> project dgrad GEMM (BN3-bwd operand transform, act'/BN2-bwd epilogue)
+            + project wgrad GEMM -> depthwise bwd (BN2-bwd on load, fused wgrad, act'/BN1-bwd
+            epilogue) -> expand dgrad GEMM (+dy) + expand wgrad GEMM
+
+Reference semantics: models/mobilenet_base.py:446-451 (unfused), :330-342 (fused) and their
+torch.autograd backward.  No tensor between the 1x1 convs is ever normalised in HBM: BatchNorm +
+activation are applied by the consumer on load.
+"""
+import ctypes as C
+import threading
+
+import torch
+
+from . import native as nat
+
+_ACT_CODE = {"none": 0, "relu": 1, "relu6": 2, "swish": 3, "hswish": 4}
+_tls = threading.local()
+
+
+def act_code_of(active_fn):
+    """Activation code of the reference's zero-arg activation factory (get_active_fn)."""
+    m = active_fn() if callable(active_fn) and not isinstance(active_fn, torch.nn.Module) \
+        else active_fn
+    name = type(m).__name__
+    table = {"ReLU": 1, "ReLU6": 2, "Swish": 3, "HSwish": 4, "Identity": 0}
+    if name not in table:
+        raise ValueError("unsupported activation for the fused path: %s" % name)
+    return table[name]
+
+
+class Workspace:
+    """Per-device scratch shared by all kernels of a stream (they serialise on it)."""
+    _per_device = {}
+
+    def __init__(self, device):
+        lib = nat.lib()
+        self.max_ctas = lib.yamb_max_ctas()
+        if self.max_ctas <= 0:
+            raise nat.NativeError("no CUDA device visible to libyamb200 (there is no CPU path)")
+        self.max_c = 4096
+        self.partials = torch.zeros(self.max_ctas * 2 * self.max_c, device=device,
+                                    dtype=torch.float32)
+        self.counter = torch.zeros(4, device=device, dtype=torch.int32)
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index if device.index is not None
+               else torch.cuda.current_device())
+        ws = cls._per_device.get(key)
+        if ws is None:
+            ws = cls(device)
+            cls._per_device[key] = ws
+        return ws
+
+
+def to_nhwc_bf16(x):
+    """[N,C,H,W] any float dtype/layout -> channels_last bf16 (no copy if already so)."""
+    if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)
+    return x
+
+
+def _f32(n, dev):
+    return torch.zeros(n, device=dev, dtype=torch.float32)
+
+
+class _Bn:
+    """Device-side state of one BatchNorm stage (possibly several reference BN modules whose
+    channels are concatenated: per-branch BNs of the unfused block)."""
+
+    def __init__(self, mods, dev):
+        self.mods = list(mods)
+        self.C = sum(m.num_features for m in self.mods)
+        self.single = len(self.mods) == 1
+        for name in ("scale", "shift", "mean", "invstd", "ca", "cb", "cc"):
+            setattr(self, name, _f32(self.C, dev))
+        self.dev = dev
+        if not self.single:
+            self.gamma = _f32(self.C, dev)
+            self.beta = _f32(self.C, dev)
+            self.dgamma = _f32(self.C, dev)
+            self.dbeta = _f32(self.C, dev)
+        self.eps = self.mods[0].eps
+        self.slices = []
+        c0 = 0
+        for m in self.mods:
+            self.slices.append((c0, m.num_features))
+            c0 += m.num_features
+
+    @property
+    def batch_stats(self):
+        m = self.mods[0]
+        return m.training or not m.track_running_stats
+
+    def momentum_value(self):
+        m = self.mods[0].momentum
+        return -1.0 if m is None else float(m)
+
+    def gamma_beta(self):
+        if self.single:
+            return self.mods[0].weight, self.mods[0].bias
+        torch.cat([m.weight.detach() for m in self.mods], out=self.gamma)
+        torch.cat([m.bias.detach() for m in self.mods], out=self.beta)
+        return self.gamma, self.beta
+
+    def eval_coeffs(self):
+        """scale/shift from running statistics (eval mode)."""
+        rm = torch.cat([m.running_mean for m in self.mods]) if not self.single \
+            else self.mods[0].running_mean
+        rv = torch.cat([m.running_var for m in self.mods]) if not self.single \
+            else self.mods[0].running_var
+        g, b = self.gamma_beta()
+        torch.rsqrt(rv + self.eps, out=self.invstd)
+        torch.mul(g.detach(), self.invstd, out=self.scale)
+        self.mean.copy_(rm)
+        torch.addcmul(b.detach(), rm, self.scale, value=-1.0, out=self.shift)
+
+
+class BlockPlan:
+    def __init__(self, block, x):
+        dev = x.device
+        self.dev = dev
+        self.ws = Workspace.get(dev)
+        self.lib = nat.lib()
+        N, Cin, H, W = x.shape
+        self.N, self.H, self.W, self.Cin = N, H, W, Cin
+        self.stride = block.stride
+        # pad=(k-1)//2, odd k: out = floor((H-1)/s)+1
+        self.Ho = (H - 1) // self.stride + 1
+        self.Wo = (W - 1) // self.stride + 1
+        self.Cout = block.output_dim
+        self.channels = list(block.channels)
+        self.ks = list(block.kernel_sizes)
+        self.expand = bool(block.expand)
+        self.residual = bool(block.use_res_connect)
+        self.act = act_code_of(block.active_fn)
+        self.fused = hasattr(block, "expand_conv")
+        self.Chid = sum(self.channels)
+        if self.Cin % 8 or self.Cout % 8 or any(c % 8 for c in self.channels):
+            raise nat.NativeError(
+                "channel counts must be multiples of 8 for the sm_100a path "
+                "(inp=%d oup=%d hidden=%s)" % (self.Cin, self.Cout, self.channels))
+        if not self.expand and not self.fused and len(self.channels) > 1:
+            raise nat.NativeError("expand=False with several branches is not supported")
+        self.M_in = N * H * W
+        self.M_out = N * self.Ho * self.Wo
+        bf = torch.bfloat16
+        Chid, Cout = self.Chid, self.Cout
+        # ---- intermediates (raw, pre-BatchNorm) ----
+        self.h1 = torch.empty(self.M_in, Chid, device=dev, dtype=bf) if self.expand else None
+        self.h2 = torch.empty(self.M_out, Chid, device=dev, dtype=bf)
+        self.h3 = torch.empty(self.M_out, Cout, device=dev, dtype=bf)
+        self.dz2 = None
+        self.dz1 = None
+        # ---- modules ----
+        if self.fused:
+            self.conv_exp = [block.expand_conv[0]] if self.expand else []
+            bn1 = [block.expand_conv[1]] if self.expand else []
+            dws = [list(op.children())[-1] for op in block.depth_ops]
+            self.conv_proj = [block.project_conv[0]]
+            bn3 = block.project_conv[1]
+            if type(block.se_op).__name__ != "Identity":
+                raise nat.NativeError("Squeeze-and-Excitation is not yet on the sm_100a path")
+            if type(block.nl_op).__name__ != "Identity":
+                raise nat.NativeError("Nonlocal is not yet on the sm_100a path")
+        else:
+            if self.expand:
+                self.conv_exp = [op[0][0] for op in block.ops]
+                bn1 = [op[0][1] for op in block.ops]
+                dws = [op[1] for op in block.ops]
+                self.conv_proj = [op[2] for op in block.ops]
+            else:
+                self.conv_exp, bn1 = [], []
+                dws = [op[0] for op in block.ops]
+                self.conv_proj = [op[1] for op in block.ops]
+            bn3 = block.pw_bn
+        self.conv_dw = [d[0] for d in dws]
+        self.bn1 = _Bn(bn1, dev) if self.expand else None
+        self.bn2 = _Bn([d[1] for d in dws], dev)
+        self.bn3 = _Bn([bn3], dev)
+        # ---- bf16 tensor-core operands + fp32 gradient accumulators ----
+        self.w_exp_bf = torch.empty(Chid, Cin, device=dev, dtype=bf) if self.expand else None
+        self.w_proj_bf = torch.empty(Cout, Chid, device=dev, dtype=bf)
+        self.g_exp = _f32(Chid * Cin, dev).view(Chid, Cin) if self.expand else None
+        self.g_proj = _f32(Cout * Chid, dev).view(Cout, Chid)
+        self.g_dw = [torch.zeros_like(c.weight, dtype=torch.float32) for c in self.conv_dw]
+        self.generation = 0
+        self._keep = []
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _bn_fwd_struct(self, bn, count, c0=0, C=None):
+        """yamb_bn_fwd for channels [c0, c0+C) of stage `bn` (per-branch slice for depthwise)."""
+        C = bn.C if C is None else C
+        s = nat.BnFwd()
+        s.partials = self.ws.partials.data_ptr()
+        s.counter = self.ws.counter.data_ptr()
+        if bn.single:
+            m = bn.mods[0]
+            g, b = m.weight, m.bias
+            rm, rv, nbt = m.running_mean, m.running_var, m.num_batches_tracked
+            off = c0
+        else:
+            # slice == exactly one reference BN module
+            idx = [i for i, (s0, n) in enumerate(bn.slices) if s0 == c0 and n == C]
+            if len(idx) != 1:
+                raise nat.NativeError("BatchNorm slice does not match a reference module")
+            m = bn.mods[idx[0]]
+            g, b = m.weight, m.bias
+            rm, rv, nbt = m.running_mean, m.running_var, m.num_batches_tracked
+            off = 0
+        f4 = 4
+        s.gamma = g.data_ptr() + off * f4 if g is not None else None
+        s.beta = b.data_ptr() + off * f4 if b is not None else None
+        s.eps = bn.eps
+        s.momentum = bn.momentum_value()
+        if m.track_running_stats and rm is not None:
+            s.running_mean = rm.data_ptr() + off * f4
+            s.running_var = rv.data_ptr() + off * f4
+            s.num_batches_tracked = nbt.data_ptr() if nbt is not None else None
+        s.scale = bn.scale.data_ptr() + c0 * f4
+        s.shift = bn.shift.data_ptr() + c0 * f4
+        s.mean = bn.mean.data_ptr() + c0 * f4
+        s.invstd = bn.invstd.data_ptr() + c0 * f4
+        s.count = count
+        self._keep.append(s)
+        return s
+
+    def _bn_bwd_struct(self, bn, count, grads, c0=0, C=None):
+        C = bn.C if C is None else C
+        s = nat.BnBwd()
+        s.partials = self.ws.partials.data_ptr()
+        s.counter = self.ws.counter.data_ptr()
+        f4 = 4
+        if bn.single:
+            mi, off = 0, c0
+        else:
+            mi = [i for i, (s0, n) in enumerate(bn.slices) if s0 == c0 and n == C][0]
+            off = 0
+        m = bn.mods[mi]
+        s.gamma = m.weight.data_ptr() + off * f4 if m.weight is not None else None
+        s.mean = bn.mean.data_ptr() + c0 * f4
+        s.invstd = bn.invstd.data_ptr() + c0 * f4
+        dg, db = grads[mi]
+        s.dgamma = dg.data_ptr() + off * f4 if dg is not None else None
+        s.dbeta = db.data_ptr() + off * f4 if db is not None else None
+        s.ca = bn.ca.data_ptr() + c0 * f4
+        s.cb = bn.cb.data_ptr() + c0 * f4
+        s.cc = bn.cc.data_ptr() + c0 * f4
+        s.count = count
+        s.use_batch_stats = 1 if bn.batch_stats else 0
+        self._keep.append(s)
+        return s
+
+    def _refresh_weights(self):
+        """fp32 master -> bf16 tensor-core operands (merged over branches)."""
+        with torch.no_grad():
+            if self.expand:
+                if len(self.conv_exp) == 1:
+                    w = self.conv_exp[0].weight
+                    mirror = getattr(w, "_yamb_bf16", None)  # kept fresh by the fused optimizer
+                    if mirror is not None:
+                        self.w_exp_bf = mirror.view(self.Chid, self.Cin)
+                    else:
+                        self.w_exp_bf.copy_(w.view(self.Chid, self.Cin))
+                else:
+                    self.w_exp_bf.copy_(torch.cat([c.weight.flatten(1) for c in self.conv_exp]))
+            if len(self.conv_proj) == 1:
+                w = self.conv_proj[0].weight
+                mirror = getattr(w, "_yamb_bf16", None)
+                if mirror is not None:
+                    self.w_proj_bf = mirror.view(self.Cout, self.Chid)
+                else:
+                    self.w_proj_bf.copy_(w.view(self.Cout, self.Chid))
+            else:
+                self.w_proj_bf.copy_(torch.cat([c.weight.flatten(1) for c in self.conv_proj], 1))
+
+    def _call(self, fn, st):
+        nat.check(fn(C.byref(st), nat.stream_handle()))
+
+    # -- forward ---------------------------------------------------------------------------------
+    def forward(self, x):
+        """x: channels_last bf16 [N,Cin,H,W]; returns channels_last bf16 [N,Cout,Ho,Wo]."""
+        lib = self.lib
+        self._keep = []
+        self.generation += 1
+        self._refresh_weights()
+        xm = x.permute(0, 2, 3, 1).reshape(self.M_in, self.Cin)  # view, NHWC matrix
+        y = torch.empty((self.N, self.Cout, self.Ho, self.Wo), device=self.dev,
+                        dtype=torch.bfloat16, memory_format=torch.channels_last)
+        # 1. expand 1x1 + BN1 statistics
+        if self.expand:
+            g = nat.Gemm()
+            g.M, g.N, g.K = self.M_in, self.Chid, self.Cin
+            g.A, g.lda = xm.data_ptr(), self.Cin
+            g.B, g.ldb = self.w_exp_bf.data_ptr(), self.Cin
+            g.D, g.ldd = self.h1.data_ptr(), self.Chid
+            if self.bn1.batch_stats:
+                if self.bn1.single:
+                    g.bn_fwd = C.pointer(self._bn_fwd_struct(self.bn1, self.M_in))
+                    self._call(lib.yamb_pointwise_gemm, g)
+                else:
+                    # per-branch BN modules: one finalize per branch slice is done by the GEMM only
+                    # for a single module; otherwise run the statistics per slice via N-slices
+                    self._gemm_sliced_stats(g, self.bn1, self.M_in)
+            else:
+                self.bn1.eval_coeffs()
+                self._call(lib.yamb_pointwise_gemm, g)
+        # 2. depthwise per branch (BN1+act applied on load) + BN2 statistics
+        if not self.bn2.batch_stats:
+            self.bn2.eval_coeffs()
+        c0 = 0
+        for b, (cb, k) in enumerate(zip(self.channels, self.ks)):
+            d = nat.DwFwd()
+            # hidden pitch; when not expanding hidden == inp, so x has the same pitch
+            d.N, d.H, d.W, d.C, d.ldc, d.k, d.stride = self.N, self.H, self.W, cb, self.Chid, k, \
+                self.stride
+            if self.expand:
+                d.x = self.h1.data_ptr() + c0 * 2
+                d.in_scale = self.bn1.scale.data_ptr() + c0 * 4
+                d.in_shift = self.bn1.shift.data_ptr() + c0 * 4
+                d.in_act = self.act
+            else:
+                d.x = xm.data_ptr()
+            d.w = self.conv_dw[b].weight.data_ptr()
+            d.y = self.h2.data_ptr() + c0 * 2
+            if self.bn2.batch_stats:
+                d.bn = C.pointer(self._bn_fwd_struct(self.bn2, self.M_out, c0, cb))
+            self._call(lib.yamb_depthwise_fwd, d)
+            c0 += cb
+        # 3. project 1x1 (BN2+act as operand transform) + BN3 statistics
+        g = nat.Gemm()
+        g.M, g.N, g.K = self.M_out, self.Cout, self.Chid
+        g.A, g.lda = self.h2.data_ptr(), self.Chid
+        g.B, g.ldb = self.w_proj_bf.data_ptr(), self.Chid
+        g.D, g.ldd = self.h3.data_ptr(), self.Cout
+        g.a_xform, g.a_act = 1, self.act
+        g.a_scale, g.a_shift = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr()
+        if self.bn3.batch_stats:
+            g.bn_fwd = C.pointer(self._bn_fwd_struct(self.bn3, self.M_out))
+        else:
+            self.bn3.eval_coeffs()
+        self._call(lib.yamb_pointwise_gemm, g)
+        # 4. BN3 apply (+ skip connection)
+        a = nat.BnApply()
+        a.M, a.C = self.M_out, self.Cout
+        a.ldh = a.ldr = a.ldy = self.Cout
+        a.h, a.scale, a.shift = self.h3.data_ptr(), self.bn3.scale.data_ptr(), \
+            self.bn3.shift.data_ptr()
+        a.act = 0
+        a.residual = xm.data_ptr() if self.residual else None
+        a.y = y.data_ptr()
+        self._call(lib.yamb_bn_apply_fwd, a)
+        return y
+
+    def _gemm_sliced_stats(self, g, bn, count):
+        """Expand GEMM whose output channels belong to several BN modules: one GEMM per module
+        slice (N-slices of the weight), each finalising its own BatchNorm."""
+        lib = self.lib
+        for (c0, cb) in bn.slices:
+            gs = nat.Gemm()
+            C.memmove(C.byref(gs), C.byref(g), C.sizeof(nat.Gemm))
+            gs.N = cb
+            gs.B = g.B + c0 * g.ldb * 2
+            gs.D = g.D + c0 * 2
+            gs.bn_fwd = C.pointer(self._bn_fwd_struct(bn, count, c0, cb))
+            self._call(lib.yamb_pointwise_gemm, gs)
+
+    # -- backward --------------------------------------------------------------------------------
+    def backward(self, x, dy, grads):
+        """grads: dict with fp32 accumulation targets:
+           'exp' [Chid,Cin], 'proj' [Cout,Chid], 'dw' list[[C,1,k,k]], 'bn1'/'bn2'/'bn3' lists of
+           (dgamma, dbeta) per reference BN module.  Returns dx (channels_last bf16)."""
+        lib = self.lib
+        self._keep = []
+        bf = torch.bfloat16
+        if self.dz2 is None:
+            self.dz2 = torch.empty(self.M_out, self.Chid, device=self.dev, dtype=bf)
+            if self.expand:
+                self.dz1 = torch.empty(self.M_in, self.Chid, device=self.dev, dtype=bf)
+        xm = x.permute(0, 2, 3, 1).reshape(self.M_in, self.Cin)
+        dym = dy.permute(0, 2, 3, 1).reshape(self.M_out, self.Cout)
+        dx = torch.empty((self.N, self.Cin, self.H, self.W), device=self.dev, dtype=bf,
+                         memory_format=torch.channels_last)
+        # 1. BN3 backward reduction -> ca3, cb3, cc3, dgamma3, dbeta3
+        r = nat.BnReduce()
+        r.M, r.C, r.lddy, r.ldh = self.M_out, self.Cout, self.Cout, self.Cout
+        r.dy, r.h = dym.data_ptr(), self.h3.data_ptr()
+        r.bn = C.pointer(self._bn_bwd_struct(self.bn3, self.M_out, grads["bn3"]))
+        self._call(lib.yamb_bn_reduce_bwd, r)
+        # 2. project dgrad: da2 = dh3 * W3, dz2 = da2 * act'(z2), BN2-backward statistics
+        g = nat.Gemm()
+        g.M, g.N, g.K = self.M_out, self.Chid, self.Cout
+        g.A, g.lda = dym.data_ptr(), self.Cout
+        g.a_xform = 2
+        g.a_scale, g.a_scale2, g.a_shift = self.bn3.ca.data_ptr(), self.bn3.cb.data_ptr(), \
+            self.bn3.cc.data_ptr()
+        g.A2, g.lda2 = self.h3.data_ptr(), self.Cout
+        g.B, g.ldb, g.b_mn_major = self.w_proj_bf.data_ptr(), self.Chid, 1
+        g.D, g.ldd = self.dz2.data_ptr(), self.Chid
+        g.epi = 1
+        g.H, g.ldh = self.h2.data_ptr(), self.Chid
+        g.h_scale, g.h_shift, g.h_act = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr(), \
+            self.act
+        if len(self.bn2.mods) == 1:
+            g.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"]))
+            self._call(lib.yamb_pointwise_gemm, g)
+        else:
+            for (c0, cb) in self.bn2.slices:
+                gs = nat.Gemm()
+                C.memmove(C.byref(gs), C.byref(g), C.sizeof(nat.Gemm))
+                gs.N = cb
+                gs.B = g.B + c0 * 2
+                gs.D = g.D + c0 * 2
+                gs.H = g.H + c0 * 2
+                gs.h_scale = g.h_scale + c0 * 4
+                gs.h_shift = g.h_shift + c0 * 4
+                gs.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"], c0,
+                                                          cb))
+                self._call(lib.yamb_pointwise_gemm, gs)
+        # 3. project wgrad: dW3[Cout,Chid] += dh3^T * a2
+        g = nat.Gemm()
+        g.M, g.N, g.K = self.Cout, self.Chid, self.M_out
+        g.a_mn_major = g.b_mn_major = 1
+        g.A, g.lda = dym.data_ptr(), self.Cout
+        g.a_xform = 2
+        g.a_scale, g.a_scale2, g.a_shift = self.bn3.ca.data_ptr(), self.bn3.cb.data_ptr(), \
+            self.bn3.cc.data_ptr()
+        g.A2, g.lda2 = self.h3.data_ptr(), self.Cout
+        g.B, g.ldb = self.h2.data_ptr(), self.Chid
+        g.b_xform, g.b_act = 1, self.act
+        g.b_scale, g.b_shift = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr()
+        g.D, g.ldd = grads["proj"].data_ptr(), self.Chid
+        g.epi = 2
+        self._call(lib.yamb_pointwise_gemm, g)
+        # 4. depthwise backward per branch
+        c0 = 0
+        for b, (cb, k) in enumerate(zip(self.channels, self.ks)):
+            d = nat.DwBwd()
+            d.N, d.H, d.W, d.C, d.ldc, d.k, d.stride = self.N, self.H, self.W, cb, self.Chid, k, \
+                self.stride
+            d.dz = self.dz2.data_ptr() + c0 * 2
+            d.h = self.h2.data_ptr() + c0 * 2
+            d.ca = self.bn2.ca.data_ptr() + c0 * 4
+            d.cb = self.bn2.cb.data_ptr() + c0 * 4
+            d.cc = self.bn2.cc.data_ptr() + c0 * 4
+            d.w = self.conv_dw[b].weight.data_ptr()
+            d.dw = grads["dw"][b].data_ptr()
+            if self.expand:
+                d.x = self.h1.data_ptr() + c0 * 2
+                d.in_scale = self.bn1.scale.data_ptr() + c0 * 4
+                d.in_shift = self.bn1.shift.data_ptr() + c0 * 4
+                d.in_act = self.act
+                d.dx = self.dz1.data_ptr() + c0 * 2
+                d.bn = C.pointer(self._bn_bwd_struct(self.bn1, self.M_in, grads["bn1"], c0, cb))
+            else:
+                d.x = xm.data_ptr()
+                d.dx = dx.data_ptr()
+                d.residual = dym.data_ptr() if self.residual else None
+            self._call(lib.yamb_depthwise_bwd, d)
+            c0 += cb
+        if not self.expand:
+            return dx
+        # 5. expand dgrad: dx = dh1 * W1 (+ dy)
+        g = nat.Gemm()
+        g.M, g.N, g.K = self.M_in, self.Cin, self.Chid
+        g.A, g.lda = self.dz1.data_ptr(), self.Chid
+        g.a_xform = 2
+        g.a_scale, g.a_scale2, g.a_shift = self.bn1.ca.data_ptr(), self.bn1.cb.data_ptr(), \
+            self.bn1.cc.data_ptr()
+        g.A2, g.lda2 = self.h1.data_ptr(), self.Chid
+        g.B, g.ldb, g.b_mn_major = self.w_exp_bf.data_ptr(), self.Cin, 1
+        g.D, g.ldd = dx.data_ptr(), self.Cin
+        if self.residual:
+            g.residual, g.ldr = dym.data_ptr(), self.Cout
+        self._call(lib.yamb_pointwise_gemm, g)
+        # 6. expand wgrad: dW1[Chid,Cin] += dh1^T * x
+        g = nat.Gemm()
+        g.M, g.N, g.K = self.Chid, self.Cin, self.M_in
+        g.a_mn_major = g.b_mn_major = 1
+        g.A, g.lda = self.dz1.data_ptr(), self.Chid
+        g.a_xform = 2
+        g.a_scale, g.a_scale2, g.a_shift = self.bn1.ca.data_ptr(), self.bn1.cb.data_ptr(), \
+            self.bn1.cc.data_ptr()
+        g.A2, g.lda2 = self.h1.data_ptr(), self.Chid
+        g.B, g.ldb = xm.data_ptr(), self.Cin
+        g.D, g.ldd = grads["exp"].data_ptr(), self.Cin
+        g.epi = 2
+        self._call(lib.yamb_pointwise_gemm, g)
+        return dx
+
+
+def _plan_for(block, x):
+    plans = block.__dict__.setdefault("_yamb_plans", {})
+    key = (tuple(x.shape), x.device.index)
+    p = plans.get(key)
+    if p is None:
+        p = BlockPlan(block, x)
+        plans[key] = p
+    return p
+
+
+def block_params(block):
+    """Parameters of a block in the fixed order the autograd Function receives them."""
+    return [p for p in block.parameters()]
+
+
+class _BlockFn(torch.autograd.Function):
+    """autograd boundary of the fused block: forward/backward run the sm_100a kernel sequences.
+
+    Parameter gradients: when a parameter carries a pre-allocated fp32 `.grad` that the flat-arena
+    optimizer marked with `_yamb_direct` the kernels accumulate straight into it and autograd gets
+    None; otherwise gradients are produced into plan-owned buffers and returned to autograd."""
+
+    @staticmethod
+    def forward(ctx, x, block, *params):
+        plan = _plan_for(block, x)
+        y = plan.forward(x)
+        ctx.block = block
+        ctx.plan = plan
+        ctx.generation = plan.generation
+        ctx.save_for_backward(x)
+        ctx.nparams = len(params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan, block = ctx.plan, ctx.block
+        if plan.generation != ctx.generation:
+            raise RuntimeError(
+                "yamb: this block ran another forward before backward of the previous one; the "
+                "saved intermediates were overwritten (one forward/backward in flight per block)")
+        (x,) = ctx.saved_tensors
+        dy = to_nhwc_bf16(dy)
+        params = list(block.parameters())
+        direct = all(getattr(p, "_yamb_direct", False) and p.grad is not None for p in params)
+        out = {}
+
+        def target(p, zero_buf):
+            if direct:
+                return p.grad
+            zero_buf.zero_()
+            return zero_buf
+
+        def bn_targets(bn, key):
+            res = []
+            if bn is None:
+                return res
+            for i, m in enumerate(bn.mods):
+                if direct:
+                    res.append((m.weight.grad, m.bias.grad))
+                else:
+                    bufs = plan.__dict__.setdefault("_bn_gbuf", {})
+                    k2 = (key, i)
+                    if k2 not in bufs:
+                        bufs[k2] = (torch.zeros_like(m.weight), torch.zeros_like(m.bias))
+                    bufs[k2][0].zero_()
+                    bufs[k2][1].zero_()
+                    res.append(bufs[k2])
+            return res
+
+        single_exp = plan.expand and len(plan.conv_exp) == 1
+        single_proj = len(plan.conv_proj) == 1
+        g = {}
+        if plan.expand:
+            if single_exp and direct:
+                g["exp"] = plan.conv_exp[0].weight.grad.view(plan.Chid, plan.Cin)
+            else:
+                plan.g_exp.zero_()
+                g["exp"] = plan.g_exp
+        if single_proj and direct:
+            g["proj"] = plan.conv_proj[0].weight.grad.view(plan.Cout, plan.Chid)
+        else:
+            plan.g_proj.zero_()
+            g["proj"] = plan.g_proj
+        g["dw"] = [target(c.weight, plan.g_dw[i]) for i, c in enumerate(plan.conv_dw)]
+        g["bn1"] = bn_targets(plan.bn1, "bn1")
+        g["bn2"] = bn_targets(plan.bn2, "bn2")
+        g["bn3"] = bn_targets(plan.bn3, "bn3")
+        dx = plan.backward(x, dy, g)
+        # ---- hand gradients to autograd ----
+        gmap = {}
+        if plan.expand:
+            if not (single_exp and direct):
+                c0 = 0
+                for conv in plan.conv_exp:
+                    n = conv.weight.shape[0]
+                    piece = plan.g_exp[c0:c0 + n].reshape(conv.weight.shape)
+                    if direct:
+                        conv.weight.grad.add_(piece)
+                    else:
+                        gmap[id(conv.weight)] = piece
+                    c0 += n
+        if not (single_proj and direct):
+            c0 = 0
+            for conv in plan.conv_proj:
+                n = conv.weight.shape[1]
+                piece = plan.g_proj[:, c0:c0 + n].reshape(conv.weight.shape)
+                if direct:
+                    conv.weight.grad.add_(piece)
+                else:
+                    gmap[id(conv.weight)] = piece
+                c0 += n
+        if not direct:
+            for i, c in enumerate(plan.conv_dw):
+                gmap[id(c.weight)] = plan.g_dw[i]
+            for key, bn in (("bn1", plan.bn1), ("bn2", plan.bn2), ("bn3", plan.bn3)):
+                if bn is None:
+                    continue
+                for i, m in enumerate(bn.mods):
+                    dg, db = g[key][i]
+                    gmap[id(m.weight)] = dg
+                    gmap[id(m.bias)] = db
+        pgrads = []
+        for p in params:
+            t = gmap.get(id(p))
+            pgrads.append(t.clone() if t is not None else None)
+        return (dx, None) + tuple(pgrads)
+
+
+def block_apply(block, x):
+    """Forward of a reference-compatible block module through the sm_100a path."""
+    if not x.is_cuda:
+        raise nat.NativeError(
+            "the inverted-residual block runs only on CUDA sm_100a (no CPU fallback); got a %s "
+            "tensor" % x.device)
+    x = to_nhwc_bf16(x)
+    params = list(block.parameters())
+    return _BlockFn.apply(x, block, *params)

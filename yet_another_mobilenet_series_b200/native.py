@@ -34,6 +34,7 @@ class BnBwd(C.Structure):
         ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
         ("ca", C.c_void_p), ("cb", C.c_void_p), ("cc", C.c_void_p),
         ("count", C.c_int64),
+        ("use_batch_stats", C.c_int32),
     ]
 
 
@@ -60,7 +61,79 @@ class Gemm(C.Structure):
     ]
 
 
-_STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm}
+class DwFwd(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("ldc", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+        ("x", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_act", C.c_int32),
+        ("w", C.c_void_p), ("y", C.c_void_p),
+        ("bn", C.POINTER(BnFwd)),
+    ]
+
+
+class DwBwd(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+        ("ldc", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+        ("dz", C.c_void_p), ("h", C.c_void_p),
+        ("ca", C.c_void_p), ("cb", C.c_void_p), ("cc", C.c_void_p),
+        ("w", C.c_void_p), ("dw", C.c_void_p),
+        ("x", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_act", C.c_int32),
+        ("dx", C.c_void_p), ("residual", C.c_void_p),
+        ("bn", C.POINTER(BnBwd)),
+    ]
+
+
+class BnApply(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("C", C.c_int32), ("ldh", C.c_int32), ("ldr", C.c_int32),
+        ("ldy", C.c_int32),
+        ("h", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int32),
+        ("residual", C.c_void_p), ("y", C.c_void_p),
+        ("gate", C.c_void_p), ("rows_per_sample", C.c_int64),
+    ]
+
+
+class BnReduce(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("C", C.c_int32), ("lddy", C.c_int32), ("ldh", C.c_int32),
+        ("dy", C.c_void_p), ("h", C.c_void_p),
+        ("bn", C.POINTER(BnBwd)),
+    ]
+
+
+class SePool(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32), ("ldh", C.c_int32),
+        ("h", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int32),
+        ("pooled", C.c_void_p),
+    ]
+
+
+class Rmsprop(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("p", C.c_void_p), ("g", C.c_void_p), ("sq", C.c_void_p), ("mom", C.c_void_p),
+        ("grad_avg", C.c_void_p),
+        ("ema", C.c_void_p), ("p_bf16", C.c_void_p), ("wd_mask", C.c_void_p),
+        ("hyper", C.c_void_p),
+        ("lr", C.c_float), ("alpha", C.c_float), ("eps", C.c_float), ("momentum", C.c_float),
+        ("weight_decay", C.c_float), ("l2", C.c_float), ("grad_scale", C.c_float),
+        ("ema_m", C.c_float),
+        ("eps_inside_sqrt", C.c_int32), ("centered", C.c_int32),
+    ]
+
+
+_STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
+            8: Rmsprop}
+
+# every symbol include/yamb200.h declares
+SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
+           "yamb_bn_reduce_bwd", "yamb_se_pool_fwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
+           "yamb_version"]
 _lib = None
 
 
@@ -84,6 +157,15 @@ def lib():
                 raise NativeError("ABI mismatch for struct %d: C %d vs ctypes %d" %
                                   (which, n, C.sizeof(st)))
         l.yamb_pointwise_gemm.argtypes = [C.POINTER(Gemm), C.c_void_p]
+        l.yamb_depthwise_fwd.argtypes = [C.POINTER(DwFwd), C.c_void_p]
+        l.yamb_depthwise_bwd.argtypes = [C.POINTER(DwBwd), C.c_void_p]
+        l.yamb_bn_apply_fwd.argtypes = [C.POINTER(BnApply), C.c_void_p]
+        l.yamb_bn_reduce_bwd.argtypes = [C.POINTER(BnReduce), C.c_void_p]
+        l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
+        l.yamb_rmsprop_step.argtypes = [C.POINTER(Rmsprop), C.c_void_p]
+        l.yamb_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
+                                      C.c_void_p]
+        l.yamb_cast_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = l
     return _lib
 
