@@ -4,8 +4,12 @@ Two references, both on the same seeded inputs:
   * the committed golden fixtures produced by the LIVE reference modules in fp32
     (tests/golden/blocks.pt, oracle/make_golden.py).  The CUDA path computes in bf16 with fp32
     accumulation, so the bound is the reference's own bf16 error budget (SURVEY.md §8c measured
-    3.6e-3..5.6e-3 rel-L2 forward for the reference under autocast-bf16): forward 1e-2,
-    gradients 5e-2 rel-L2.
+    3.6e-3..5.6e-3 rel-L2 forward, 3e-2 dgrad / 4e-2 wgrad for ReLU blocks for the reference under
+    autocast-bf16; ReLU-mask flips of near-zero pre-activations dominate): forward 1e-2,
+    gradients 1e-1 rel-L2.  (oracle quant=True vs the same fixtures measures 3.8e-3..5.8e-3
+    forward, 1.4e-2..7.0e-2 dx and up to 2.6e-1 on a BN-gamma gradient of the 288-sample
+    multi-branch case: the bound is the bf16 budget of these tiny batches, not kernel error; the
+    kernels are held to the quant oracle below.)
   * the oracle in `quant=True` mode, which rounds to bf16 at exactly the points where the CUDA
     path materialises bf16 tensors: forward 3e-3, gradients 1.5e-2 rel-L2 (north-star "1e-3 rel"
     is met per element up to bf16 output rounding, 2^-9 = 2e-3).
@@ -55,13 +59,19 @@ def test_block_vs_golden_and_oracle(built_lib, name, mode):
     y.backward(dy.to(y.dtype))
     torch.cuda.synchronize()
     gold = rec[mode]
-    # ---- vs the live reference (fp32) ----
+    # ---- the oracle with the same bf16 rounding points ----
+    blk_cpu = _build(rec, "cpu")
+    cfg, P = ob.extract(blk_cpu)
+    yo, S = ob.forward(rec["x"], cfg, P, training=(mode == "train"), quant=True)
+    dxo, G = ob.backward(dy.cpu(), cfg, P, S, training=(mode == "train"), quant=True)
+    # ---- vs the live reference (fp32): no further away than the bf16 rounding explains ----
     assert _rel(y, gold["y"]) < 1e-2
-    assert _rel(x.grad, gold["dx"]) < 5e-2
+    assert _rel(x.grad, gold["dx"]) < 1.2 * _rel(dxo, gold["dx"]) + 1e-2
+    worst = 0.0
     for k, p in blk.named_parameters():
         assert p.grad is not None, k
-        e = _rel(p.grad, gold["grads"][k])
-        assert e < 6e-2, (k, e)
+        worst = max(worst, _rel(p.grad, gold["grads"][k]))
+    assert worst < 0.35, worst  # small-sample bf16 budget (see module docstring); tight check below
     if mode == "train":
         for k, v in blk.state_dict().items():
             ref = gold["state_after"][k]
@@ -69,11 +79,6 @@ def test_block_vs_golden_and_oracle(built_lib, name, mode):
                 assert torch.allclose(v.cpu(), ref, rtol=5e-3, atol=2e-3), k
             elif "num_batches_tracked" in k:
                 assert int(v) == int(ref), k
-    # ---- vs the oracle with the same bf16 rounding points ----
-    blk_cpu = _build(rec, "cpu")
-    cfg, P = ob.extract(blk_cpu)
-    yo, S = ob.forward(rec["x"], cfg, P, training=(mode == "train"), quant=True)
-    dxo, G = ob.backward(dy.cpu(), cfg, P, S, training=(mode == "train"), quant=True)
     assert _rel(y, yo) < 3e-3
     assert _rel(x.grad, dxo) < 1.5e-2
     # merged-layout gradients of the CUDA path

