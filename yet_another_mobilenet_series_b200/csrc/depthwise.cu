@@ -5,15 +5,18 @@
 // (models/mobilenet_base.py:405-411 unfused, :275-281 fused) and their autograd backward.
 //
 // forward : y = dwconv(act(in_scale*x + in_shift))   — the producer's BatchNorm + activation is
-//           applied on load in fp32 (the normalised tensor never exists in HBM); per-channel
-//           sum / sum^2 of the bf16 output feed the next BatchNorm (last-CTA finalize).
-// backward: dh = ca*dz + cb*h + cc (BatchNorm backward of the depthwise output, applied on load),
-//           da = dwconv^T(dh, w), dwgt += sum dh * a  (fused wgrad), dx = da * act'(z) with the
-//           statistics of the preceding BatchNorm's backward.
+//           applied ONCE per element while the input tile (with halo) is staged into shared
+//           memory in fp32; per-channel sum / sum^2 of the bf16 output feed the next BatchNorm
+//           (last-CTA finalize).
+// backward: dh = ca*dz + cb*h + cc (BatchNorm backward of the depthwise output) is formed ONCE per
+//           element while the gradient tile (with halo) is staged; da = dwconv^T(dh, w),
+//           dwgt += sum dh * a (fused wgrad, accumulated in registers across the persistent loop),
+//           dx = da * act'(z) with the statistics of the preceding BatchNorm's backward.
 //
-// HBM-bound integer-free stencil: channels are the contiguous dimension; a thread owns VEC
-// consecutive channels (16/8/4-byte vector accesses), consecutive threads own consecutive channel
-// groups and then consecutive pixels, so every warp access is a contiguous run of >= 128 bytes.
+// HBM-bound stencil: channels are the contiguous dimension; a thread owns 4 consecutive channels
+// (8-byte global, 16-byte shared accesses); consecutive threads own consecutive channel groups and
+// then consecutive pixels, so global accesses are contiguous runs of CT*2 bytes per pixel and
+// shared accesses are bank-conflict free.  CTAs are persistent over (channel chunk, image tile).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -23,6 +26,20 @@
 
 namespace yamb {
 
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
+}
+// round to bf16, store, and leave the rounded values in v
+__device__ __forceinline__ void st4_round(__nv_bfloat16* p, float (&v)[4]) {
+  const uint32_t a = pack_bf16(v[0], v[1]), b = pack_bf16(v[2], v[3]);
+  v[0] = bf16lo(a); v[1] = bf16hi(a); v[2] = bf16lo(b); v[3] = bf16hi(b);
+  *reinterpret_cast<uint2*>(p) = make_uint2(a, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
 struct DwFwdDev {
   int N, H, W, Ho, Wo, C, ldc;
   const __nv_bfloat16* x;
@@ -33,112 +50,131 @@ struct DwFwdDev {
   __nv_bfloat16* y;
   int has_bn;
   yamb_bn_fwd bn;
+  int tiles_h, tiles_w, chunks;
+  long long num_tiles;
 };
 
-template <int VEC>
-__device__ __forceinline__ void load_vec(const __nv_bfloat16* p, float (&v)[VEC]) {
-  if constexpr (VEC == 8) {
-    uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-    v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
-    v[4] = bf16lo(u.z); v[5] = bf16hi(u.z); v[6] = bf16lo(u.w); v[7] = bf16hi(u.w);
-  } else if constexpr (VEC == 4) {
-    uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-    v[0] = bf16lo(u.x); v[1] = bf16hi(u.x); v[2] = bf16lo(u.y); v[3] = bf16hi(u.y);
-  } else {
-    uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
-    v[0] = bf16lo(u); v[1] = bf16hi(u);
-  }
-}
-// round to bf16, store, and return the rounded values in v
-template <int VEC>
-__device__ __forceinline__ void store_vec_round(__nv_bfloat16* p, float (&v)[VEC]) {
-  uint32_t u[VEC / 2];
-#pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) {
-    u[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
-    v[2 * i] = bf16lo(u[i]);
-    v[2 * i + 1] = bf16hi(u[i]);
-  }
-  if constexpr (VEC == 8) *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
-  else if constexpr (VEC == 4) *reinterpret_cast<uint2*>(p) = make_uint2(u[0], u[1]);
-  else *reinterpret_cast<uint32_t*>(p) = u[0];
-}
+// CT channels per tile (32 or 64); 256 threads = NCG channel groups x NSTRIP vertical strips.
+template <int K, int S, int CT>
+struct FwdGeom {
+  static constexpr int TH = 4;                    // output rows per thread
+  static constexpr int NCG = CT / 4;
+  static constexpr int NSTRIP = 256 / NCG;
+  static constexpr int TOW = 8;
+  static constexpr int TOH = NSTRIP / TOW * TH;   // 8 (CT=64) or 16 (CT=32)
+  static constexpr int IH = (TOH - 1) * S + K;
+  static constexpr int IW = (TOW - 1) * S + K;
+};
 
-template <int K, int VEC, int S>
+template <int K, int S, int CT>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwFwdDev p) {
-  constexpr int TH = 4;                  // output rows per thread (vertical strip)
+  using G = FwdGeom<K, S, CT>;
   constexpr int P = (K - 1) / 2;
-  constexpr int IR = (TH - 1) * S + K;   // input rows touched by one strip
-  extern __shared__ float s_part[];      // [2][C] per-CTA statistics
-  const int CG = p.C / VEC;
-  const int PX = 256 / CG;
-  const int px = threadIdx.x / CG;
-  const int cg = threadIdx.x % CG;
-  const int c0 = cg * VEC;
-  const bool active = px < PX;
-  if (p.has_bn)
-    for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
-  __syncthreads();
+  constexpr int TH = G::TH, NCG = G::NCG, IH = G::IH, IW = G::IW;
+  constexpr int IR = (TH - 1) * S + K;
+  extern __shared__ __align__(16) float smem_f[];
+  float* s_tile = smem_f;                       // [IH*IW][CT]
+  float* s_sc = s_tile + IH * IW * CT;          // [C]
+  float* s_sh = s_sc + p.C;                     // [C]
+  float* s_part = s_sh + p.C;                   // [2][C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.C; i += 256) {
+    s_sc[i] = p.in_scale ? __ldg(p.in_scale + i) : 1.f;
+    s_sh[i] = p.in_scale ? __ldg(p.in_shift + i) : 0.f;
+  }
+  for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
+  const int act = p.in_scale ? p.in_act : ACT_NONE;
+  const int cg = tid % NCG;
+  const int strip = tid / NCG;
+  const int sx = strip % G::TOW, sy = strip / G::TOW;
+  float wreg[K * K][4];
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+  int cur_chunk = -1;
+  const long long tiles_per_chunk = (long long)p.N * p.tiles_h * p.tiles_w;
 
-  float ssum[VEC], ssq[VEC];
+  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const int chunk = (int)(t / tiles_per_chunk);
+    long long r = t % tiles_per_chunk;
+    const int n = (int)(r / (p.tiles_h * p.tiles_w));
+    r %= (p.tiles_h * p.tiles_w);
+    const int ty = (int)(r / p.tiles_w), tx = (int)(r % p.tiles_w);
+    const int cbase = chunk * CT;
+    const int c0 = cbase + cg * 4;
+    const bool cvalid = c0 < p.C;
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0 && p.has_bn) {
+        const int pc = cur_chunk * CT + cg * 4;
+        if (pc < p.C) {
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) ssum[v] = ssq[v] = 0.f;
-
-  if (active) {
-    float w[K * K][VEC];
-    float sc[VEC], sh[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-#pragma unroll
-      for (int t = 0; t < K * K; ++t) w[t][v] = __ldg(p.w + (size_t)(c0 + v) * K * K + t);
-      sc[v] = p.in_scale ? __ldg(p.in_scale + c0 + v) : 1.f;
-      sh[v] = p.in_scale ? __ldg(p.in_shift + c0 + v) : 0.f;
-    }
-    const int act = p.in_scale ? p.in_act : ACT_NONE;
-    const int nstrips = (p.Ho + TH - 1) / TH;
-    const long long items = (long long)p.N * nstrips * p.Wo;
-    for (long long item = (long long)blockIdx.x * PX + px; item < items;
-         item += (long long)gridDim.x * PX) {
-      const int xo = (int)(item % p.Wo);
-      const long long t = item / p.Wo;
-      const int strip = (int)(t % nstrips);
-      const int n = (int)(t / nstrips);
-      const int yo0 = strip * TH;
-      float acc[TH][VEC];
-#pragma unroll
-      for (int j = 0; j < TH; ++j)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[j][v] = 0.f;
-#pragma unroll
-      for (int r = 0; r < IR; ++r) {
-        const int yi = yo0 * S - P + r;
-        if (yi < 0 || yi >= p.H) continue;
-#pragma unroll
-        for (int dx = 0; dx < K; ++dx) {
-          const int xi = xo * S - P + dx;
-          if (xi < 0 || xi >= p.W) continue;
-          float a[VEC];
-          load_vec<VEC>(p.x + ((size_t)((size_t)n * p.H + yi) * p.W + xi) * p.ldc + c0, a);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) a[v] = act_fwd(fmaf(sc[v], a[v], sh[v]), act);
-#pragma unroll
-          for (int j = 0; j < TH; ++j) {
-            const int ky = r - j * S;  // compile-time after unrolling
-            if (ky >= 0 && ky < K) {
-#pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[j][v] = fmaf(w[ky * K + dx][v], a[v], acc[j][v]);
-            }
+          for (int v = 0; v < 4; ++v) {
+            atomicAdd(&s_part[pc + v], ssum[v]);
+            atomicAdd(&s_part[p.C + pc + v], ssq[v]);
+            ssum[v] = ssq[v] = 0.f;
           }
         }
       }
+      cur_chunk = chunk;
+#pragma unroll
+      for (int tp = 0; tp < K * K; ++tp)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          wreg[tp][v] = cvalid ? __ldg(p.w + (size_t)(c0 + v) * K * K + tp) : 0.f;
+    }
+    const int oy0 = ty * G::TOH, ox0 = tx * G::TOW;
+    const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
+    __syncthreads();  // previous tile's compute is done with s_tile (and the tables are written)
+    // ---- stage the input tile: BN + activation applied once per element, halo / padding = 0 ----
+    for (int idx = tid; idx < IH * IW * NCG; idx += 256) {
+      const int pix = idx / NCG, g = idx % NCG;
+      const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
+      const int c = cbase + g * 4;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && c < p.C) {
+        float v[4];
+        ld4(p.x + ((size_t)((size_t)n * p.H + iy) * p.W + ix) * p.ldc + c, v);
+        const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
+        const float4 sh = *reinterpret_cast<const float4*>(s_sh + c);
+        a.x = act_fwd(fmaf(sc.x, v[0], sh.x), act);
+        a.y = act_fwd(fmaf(sc.y, v[1], sh.y), act);
+        a.z = act_fwd(fmaf(sc.z, v[2], sh.z), act);
+        a.w = act_fwd(fmaf(sc.w, v[3], sh.w), act);
+      }
+      *reinterpret_cast<float4*>(s_tile + (size_t)pix * CT + g * 4) = a;
+    }
+    __syncthreads();
+    // ---- stencil: TH output rows x 4 channels per thread ----
+    float acc[TH][4];
+#pragma unroll
+    for (int j = 0; j < TH; ++j)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[j][v] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < IR; ++rr) {
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const float4 a = *reinterpret_cast<const float4*>(
+            s_tile + (size_t)((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
+#pragma unroll
+        for (int j = 0; j < TH; ++j) {
+          const int ky = rr - j * S;  // compile-time after unrolling
+          if (ky >= 0 && ky < K) {
+            acc[j][0] = fmaf(wreg[ky * K + dx][0], a.x, acc[j][0]);
+            acc[j][1] = fmaf(wreg[ky * K + dx][1], a.y, acc[j][1]);
+            acc[j][2] = fmaf(wreg[ky * K + dx][2], a.z, acc[j][2]);
+            acc[j][3] = fmaf(wreg[ky * K + dx][3], a.w, acc[j][3]);
+          }
+        }
+      }
+    }
+    const int ox = ox0 + sx;
+    if (cvalid && ox < p.Wo) {
 #pragma unroll
       for (int j = 0; j < TH; ++j) {
-        const int yo = yo0 + j;
-        if (yo < p.Ho) {
-          store_vec_round<VEC>(p.y + ((size_t)((size_t)n * p.Ho + yo) * p.Wo + xo) * p.ldc + c0,
-                               acc[j]);
+        const int oy = oy0 + sy * TH + j;
+        if (oy < p.Ho) {
+          st4_round(p.y + ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c0, acc[j]);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
+          for (int v = 0; v < 4; ++v) {
             ssum[v] += acc[j][v];
             ssq[v] = fmaf(acc[j][v], acc[j][v], ssq[v]);
           }
@@ -147,11 +183,14 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
     }
   }
   if (p.has_bn) {
-    if (active) {
+    if (cur_chunk >= 0) {
+      const int pc = cur_chunk * CT + cg * 4;
+      if (pc < p.C) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        atomicAdd(&s_part[c0 + v], ssum[v]);
-        atomicAdd(&s_part[p.C + c0 + v], ssq[v]);
+        for (int v = 0; v < 4; ++v) {
+          atomicAdd(&s_part[pc + v], ssum[v]);
+          atomicAdd(&s_part[p.C + pc + v], ssq[v]);
+        }
       }
     }
     __syncthreads();
@@ -180,126 +219,222 @@ struct DwBwdDev {
   const __nv_bfloat16* residual;
   int has_bn;
   yamb_bn_bwd bn;
+  int tiles_h, tiles_w, chunks;
+  long long num_tiles;
 };
 
-template <int K, int VEC, int S>
+// Input-space tile TI x TI (8 for stride 1, 16 for stride 2); the gradient region that touches it
+// is at most RMAX x RMAX output pixels.
+template <int K, int S>
+struct BwdGeom {
+  static constexpr int P = (K - 1) / 2;
+  static constexpr int TI = S == 1 ? 8 : 16;
+  static constexpr int RMAX = S == 1 ? TI + K - 1 : (TI + K - 1) / 2 + 1;
+};
+
+// TAP0..TAP1: taps whose weight gradient this launch accumulates (all of them unless K == 7, where
+// 49 x 4 accumulators do not fit the register file and a second, wgrad-only launch covers the rest).
+// DGRAD: compute and store dx (+ statistics); false for that second launch.
+template <int K, int S, int CT, int TAP0, int TAP1, bool DGRAD>
 __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwBwdDev p) {
-  constexpr int P = (K - 1) / 2;
-  extern __shared__ float smem_f[];
-  // layout: s_w[K*K][C] | s_gw[K*K][C] | s_part[2][C]
-  float* s_w = smem_f;
-  float* s_gw = s_w + K * K * p.C;
-  float* s_part = s_gw + K * K * p.C;
-  const int CG = p.C / VEC;
-  const int PX = 256 / CG;
-  const int px = threadIdx.x / CG;
-  const int cg = threadIdx.x % CG;
-  const int c0 = cg * VEC;
-  const bool active = px < PX;
-  for (int i = threadIdx.x; i < K * K * p.C; i += blockDim.x) {
-    const int t = i / p.C, c = i % p.C;
-    s_w[i] = __ldg(p.w + (size_t)c * K * K + t);
+  using G = BwdGeom<K, S>;
+  constexpr int P = G::P, TI = G::TI, RMAX = G::RMAX;
+  constexpr int NCG = CT / 4;
+  constexpr int NPIX = 256 / NCG;           // pixels processed concurrently
+  constexpr int ITEMS = TI * TI / NPIX;     // pixels per thread per tile
+  constexpr int IB = ITEMS < 4 ? ITEMS : 4; // pixels per thread whose loads are batched
+  constexpr int NT = TAP1 - TAP0;
+  extern __shared__ __align__(16) float smem_f[];
+  float* s_dh = smem_f;                      // [RMAX*RMAX][CT]
+  float* s_tab = s_dh + RMAX * RMAX * CT;    // 7 tables x C: sc sh ca cb cc mu rs
+  float* s_w = s_tab + 7 * p.C;              // [K*K][C]
+  float* s_gw = s_w + K * K * p.C;           // [K*K][C]
+  float* s_part = s_gw + K * K * p.C;        // [2][C]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < p.C; i += 256) {
+    s_tab[i] = p.in_scale ? __ldg(p.in_scale + i) : 1.f;
+    s_tab[p.C + i] = p.in_scale ? __ldg(p.in_shift + i) : 0.f;
+    s_tab[2 * p.C + i] = __ldg(p.ca + i);
+    s_tab[3 * p.C + i] = __ldg(p.cb + i);
+    s_tab[4 * p.C + i] = __ldg(p.cc + i);
+    s_tab[5 * p.C + i] = p.has_bn ? __ldg(p.bn.mean + i) : 0.f;
+    s_tab[6 * p.C + i] = p.has_bn ? __ldg(p.bn.invstd + i) : 0.f;
+  }
+  for (int i = tid; i < K * K * p.C; i += 256) {
+    const int tp = i / p.C, c = i % p.C;
+    s_w[i] = __ldg(p.w + (size_t)c * K * K + tp);
     s_gw[i] = 0.f;
   }
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
+  const int act = p.in_scale ? p.in_act : ACT_NONE;
+  const int cg = tid % NCG;
+  const int pslot = tid / NCG;
+  float gw[NT][4];
+  float wreg[DGRAD ? K * K : 1][4];
+  float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int tp = 0; tp < NT; ++tp)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) gw[tp][v] = 0.f;
+  int cur_chunk = -1;
+  const long long tiles_per_chunk = (long long)p.N * p.tiles_h * p.tiles_w;
   __syncthreads();
 
-  float ssum[VEC], ssq[VEC];
-  float gw[K * K][VEC];
+  auto flush = [&](int chunk) {
+    const int pc = chunk * CT + cg * 4;
+    if (pc < p.C) {
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    ssum[v] = ssq[v] = 0.f;
+      for (int tp = 0; tp < NT; ++tp)
 #pragma unroll
-    for (int t = 0; t < K * K; ++t) gw[t][v] = 0.f;
-  }
-  if (active) {
-    float sc[VEC], sh[VEC], ca[VEC], cb[VEC], cc[VEC], mu[VEC], rs[VEC];
+        for (int v = 0; v < 4; ++v) {
+          atomicAdd(&s_gw[(TAP0 + tp) * p.C + pc + v], gw[tp][v]);
+          gw[tp][v] = 0.f;
+        }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      sc[v] = p.in_scale ? __ldg(p.in_scale + c0 + v) : 1.f;
-      sh[v] = p.in_scale ? __ldg(p.in_shift + c0 + v) : 0.f;
-      ca[v] = __ldg(p.ca + c0 + v);
-      cb[v] = __ldg(p.cb + c0 + v);
-      cc[v] = __ldg(p.cc + c0 + v);
-      mu[v] = p.has_bn ? __ldg(p.bn.mean + c0 + v) : 0.f;
-      rs[v] = p.has_bn ? __ldg(p.bn.invstd + c0 + v) : 0.f;
+      for (int v = 0; v < 4; ++v) {
+        atomicAdd(&s_part[pc + v], ssum[v]);
+        atomicAdd(&s_part[p.C + pc + v], ssq[v]);
+        ssum[v] = ssq[v] = 0.f;
+      }
     }
-    const int act = p.in_scale ? p.in_act : ACT_NONE;
-    const long long items = (long long)p.N * p.H * p.W;
-    for (long long item = (long long)blockIdx.x * PX + px; item < items;
-         item += (long long)gridDim.x * PX) {
-      const int x = (int)(item % p.W);
-      const long long t = item / p.W;
-      const int y = (int)(t % p.H);
-      const int n = (int)(t / p.H);
-      const size_t in_off = (size_t)item * p.ldc + c0;
-      float xv[VEC], a1[VEC], dact[VEC], da[VEC];
-      load_vec<VEC>(p.x + in_off, xv);
+  };
+
+  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const int chunk = (int)(t / tiles_per_chunk);
+    long long r = t % tiles_per_chunk;
+    const int n = (int)(r / (p.tiles_h * p.tiles_w));
+    r %= (p.tiles_h * p.tiles_w);
+    const int ty = (int)(r / p.tiles_w), tx = (int)(r % p.tiles_w);
+    const int cbase = chunk * CT;
+    const int c0 = cbase + cg * 4;
+    const bool cvalid = c0 < p.C;
+    if (chunk != cur_chunk) {
+      if (cur_chunk >= 0) flush(cur_chunk);
+      cur_chunk = chunk;
+      if (DGRAD) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float z = fmaf(sc[v], xv[v], sh[v]);
-        a1[v] = act_fwd(z, act);
-        dact[v] = act_bwd(z, act);
-        da[v] = 0.f;
+        for (int tp = 0; tp < K * K; ++tp)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) wreg[tp][v] = cvalid ? s_w[tp * p.C + c0 + v] : 0.f;
+      }
+    }
+    const int y0 = ty * TI, x0 = tx * TI;
+    // first output row / col whose receptive field reaches this input tile
+    const int ry0 = S == 1 ? y0 - P : (y0 - P + 1) >> 1;   // ceil((y0-P)/2), also right for < 0
+    const int rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
+    __syncthreads();
+    // ---- stage dh = ca*dz + cb*h + cc over the gradient region (0 outside the image) ----
+    for (int idx = tid; idx < RMAX * RMAX * NCG; idx += 256) {
+      const int pix = idx / NCG, g = idx % NCG;
+      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
+      const int c = cbase + g * 4;
+      float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo && c < p.C) {
+        const size_t o = ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c;
+        float dzv[4], hv[4];
+        ld4(p.dz + o, dzv);
+        ld4(p.h + o, hv);
+        const float4 ca = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
+        const float4 cb = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
+        const float4 cc = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
+        dh.x = fmaf(ca.x, dzv[0], fmaf(cb.x, hv[0], cc.x));
+        dh.y = fmaf(ca.y, dzv[1], fmaf(cb.y, hv[1], cc.y));
+        dh.z = fmaf(ca.z, dzv[2], fmaf(cb.z, hv[2], cc.z));
+        dh.w = fmaf(ca.w, dzv[3], fmaf(cb.w, hv[3], cc.w));
+      }
+      *reinterpret_cast<float4*>(s_dh + (size_t)pix * CT + g * 4) = dh;
+    }
+    __syncthreads();
+    // ---- per input pixel: dgrad gather + fused wgrad + act'/BN-backward epilogue ----
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 mu = sh, rs = sh;
+    if (cvalid) {
+      sc = *reinterpret_cast<const float4*>(s_tab + c0);
+      sh = *reinterpret_cast<const float4*>(s_tab + p.C + c0);
+      mu = *reinterpret_cast<const float4*>(s_tab + 5 * p.C + c0);
+      rs = *reinterpret_cast<const float4*>(s_tab + 6 * p.C + c0);
+    }
+#pragma unroll 1
+    for (int ib = 0; ib < ITEMS; ib += IB) {
+      float xv[IB][4];
+      bool ok[IB];
+#pragma unroll
+      for (int it = 0; it < IB; ++it) {  // batch the global loads of IB pixels
+        const int pix = (ib + it) * NPIX + pslot;
+        const int y = y0 + pix / TI, x = x0 + pix % TI;
+        ok[it] = cvalid && y < p.H && x < p.W;
+        if (ok[it]) ld4(p.x + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.ldc + c0, xv[it]);
       }
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int yy = y + P - ky;
-        if (yy < 0 || (S == 2 && (yy & 1))) continue;
-        const int yo = yy / S;
-        if (yo >= p.Ho) continue;
+      for (int it = 0; it < IB; ++it) {
+        if (!ok[it]) continue;
+        const int pix = (ib + it) * NPIX + pslot;
+        const int y = y0 + pix / TI, x = x0 + pix % TI;
+        const float z[4] = {fmaf(sc.x, xv[it][0], sh.x), fmaf(sc.y, xv[it][1], sh.y),
+                            fmaf(sc.z, xv[it][2], sh.z), fmaf(sc.w, xv[it][3], sh.w)};
+        float a1[4], da[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int xx = x + P - kx;
-          if (xx < 0 || (S == 2 && (xx & 1))) continue;
-          const int xo = xx / S;
-          if (xo >= p.Wo) continue;
-          const size_t o = ((size_t)((size_t)n * p.Ho + yo) * p.Wo + xo) * p.ldc + c0;
-          float dzv[VEC], hv[VEC];
-          load_vec<VEC>(p.dz + o, dzv);
-          load_vec<VEC>(p.h + o, hv);
-          const float* wt = s_w + (ky * K + kx) * p.C + c0;
+        for (int v = 0; v < 4; ++v) a1[v] = act_fwd(z[v], act);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) {
-            const float dh = fmaf(ca[v], dzv[v], fmaf(cb[v], hv[v], cc[v]));
-            da[v] = fmaf(dh, wt[v], da[v]);
-            gw[ky * K + kx][v] = fmaf(dh, a1[v], gw[ky * K + kx][v]);
+        for (int ky = 0; ky < K; ++ky) {
+          const int yy = y + P - ky;
+          if (S == 2 && (yy & 1)) continue;
+          const int oy = S == 1 ? yy : yy >> 1;
+          if (yy < 0 || oy >= p.Ho) continue;
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int tp = ky * K + kx;  // compile-time after unrolling
+            if (!DGRAD && (tp < TAP0 || tp >= TAP1)) continue;
+            const int xx = x + P - kx;
+            if (S == 2 && (xx & 1)) continue;
+            const int ox = S == 1 ? xx : xx >> 1;
+            if (xx < 0 || ox >= p.Wo) continue;
+            const float4 dh = *reinterpret_cast<const float4*>(
+                s_dh + (size_t)((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
+            if (DGRAD) {
+              da[0] = fmaf(dh.x, wreg[tp][0], da[0]);
+              da[1] = fmaf(dh.y, wreg[tp][1], da[1]);
+              da[2] = fmaf(dh.z, wreg[tp][2], da[2]);
+              da[3] = fmaf(dh.w, wreg[tp][3], da[3]);
+            }
+            if (tp >= TAP0 && tp < TAP1) {
+              gw[tp - TAP0][0] = fmaf(dh.x, a1[0], gw[tp - TAP0][0]);
+              gw[tp - TAP0][1] = fmaf(dh.y, a1[1], gw[tp - TAP0][1]);
+              gw[tp - TAP0][2] = fmaf(dh.z, a1[2], gw[tp - TAP0][2]);
+              gw[tp - TAP0][3] = fmaf(dh.w, a1[3], gw[tp - TAP0][3]);
+            }
           }
         }
-      }
+        if (DGRAD) {
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) da[v] *= dact[v];
-      if (p.residual) {
-        float rv[VEC];
-        load_vec<VEC>(p.residual + in_off, rv);
+          for (int v = 0; v < 4; ++v) da[v] *= act_bwd(z[v], act);
+          const size_t off = ((size_t)((size_t)n * p.H + y) * p.W + x) * p.ldc + c0;
+          if (p.residual) {
+            float rv[4];
+            ld4(p.residual + off, rv);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) da[v] += rv[v];
-      }
-      store_vec_round<VEC>(p.dx + in_off, da);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        ssum[v] += da[v];
-        ssq[v] = fmaf(da[v], (xv[v] - mu[v]) * rs[v], ssq[v]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < K * K; ++t)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) atomicAdd(&s_gw[t * p.C + c0 + v], gw[t][v]);
-    if (p.has_bn) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        atomicAdd(&s_part[c0 + v], ssum[v]);
-        atomicAdd(&s_part[p.C + c0 + v], ssq[v]);
+            for (int v = 0; v < 4; ++v) da[v] += rv[v];
+          }
+          st4_round(p.dx + off, da);
+          ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
+          ssq[0] = fmaf(da[0], (xv[it][0] - mu.x) * rs.x, ssq[0]);
+          ssq[1] = fmaf(da[1], (xv[it][1] - mu.y) * rs.y, ssq[1]);
+          ssq[2] = fmaf(da[2], (xv[it][2] - mu.z) * rs.z, ssq[2]);
+          ssq[3] = fmaf(da[3], (xv[it][3] - mu.w) * rs.w, ssq[3]);
+        }
       }
     }
   }
+  if (cur_chunk >= 0) flush(cur_chunk);
   __syncthreads();
-  for (int i = threadIdx.x; i < K * K * p.C; i += blockDim.x) {
-    const int t = i / p.C, c = i % p.C;
-    atomicAdd(p.dw + (size_t)c * K * K + t, s_gw[i]);
+  for (int i = tid; i < K * K * p.C; i += 256) {
+    const int tp = i / p.C, c = i % p.C;
+    const float g = s_gw[i];
+    if (g != 0.f) atomicAdd(p.dw + (size_t)c * K * K + tp, g);
   }
-  if (p.has_bn) {
+  if (p.has_bn && DGRAD) {
     if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
       bn_bwd_finalize(p.bn, p.C, gridDim.x);
       __syncthreads();
@@ -311,86 +446,87 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwB
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static int pick_vec(int C, int k, bool bwd) {
-  int vec = k == 3 ? (bwd ? 4 : 8) : (k == 5 ? 4 : 2);
-  while (vec > 2 && (C % vec)) vec >>= 1;
-  while (vec < 8 && C / vec > 256) vec <<= 1;  // at most 256 channel groups per CTA
-  return vec;
-}
-
-template <int K, int VEC>
-static cudaError_t launch_fwd(const DwFwdDev& p, int stride, int grid, size_t smem,
-                              cudaStream_t st) {
-  if (stride == 1) dw_fwd_kernel<K, VEC, 1><<<grid, 256, smem, st>>>(p);
-  else dw_fwd_kernel<K, VEC, 2><<<grid, 256, smem, st>>>(p);
-  return cudaGetLastError();
-}
-template <int K, int VEC>
-static cudaError_t launch_bwd(const DwBwdDev& p, int stride, int grid, size_t smem,
-                              cudaStream_t st) {
-  cudaError_t e;
-  if (stride == 1) {
-    e = cudaFuncSetAttribute(dw_bwd_kernel<K, VEC, 1>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dw_bwd_kernel<K, VEC, 1><<<grid, 256, smem, st>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(dw_bwd_kernel<K, VEC, 2>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dw_bwd_kernel<K, VEC, 2><<<grid, 256, smem, st>>>(p);
-  }
-  return cudaGetLastError();
-}
-
-#define YAMB_DISPATCH_KV(FN, ...)                                                        \
-  do {                                                                                   \
-    if (k == 3 && vec == 8) e = FN<3, 8>(__VA_ARGS__);                                   \
-    else if (k == 3 && vec == 4) e = FN<3, 4>(__VA_ARGS__);                              \
-    else if (k == 3 && vec == 2) e = FN<3, 2>(__VA_ARGS__);                              \
-    else if (k == 5 && vec == 8) e = FN<5, 8>(__VA_ARGS__);                              \
-    else if (k == 5 && vec == 4) e = FN<5, 4>(__VA_ARGS__);                              \
-    else if (k == 5 && vec == 2) e = FN<5, 2>(__VA_ARGS__);                              \
-    else if (k == 7 && vec == 4) e = FN<7, 4>(__VA_ARGS__);                              \
-    else if (k == 7 && vec == 2) e = FN<7, 2>(__VA_ARGS__);                              \
-    else return set_error(YAMB_EINVAL, "depthwise: unsupported k=%d vec=%d", k, vec);    \
-  } while (0)
-
 static int check_common(int N, int H, int W, int C, int ldc, int k, int stride) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(YAMB_EINVAL, "depthwise: bad shape");
-  if (C % 2 || ldc % 8 || C > ldc) return set_error(YAMB_EINVAL, "depthwise: C=%d ldc=%d", C, ldc);
+  if (C % 4 || ldc % 4 || C > ldc) return set_error(YAMB_EINVAL, "depthwise: C=%d ldc=%d", C, ldc);
   if (k != 3 && k != 5 && k != 7) return set_error(YAMB_EINVAL, "depthwise: k=%d", k);
   if (stride != 1 && stride != 2) return set_error(YAMB_EINVAL, "depthwise: stride=%d", stride);
-  if (C > 2048) return set_error(YAMB_EINVAL, "depthwise: C > 2048 per slice");
+  if (C > 4096) return set_error(YAMB_EINVAL, "depthwise: C > 4096 per slice");
   return 0;
 }
+
+template <typename Kern, typename Dev>
+static cudaError_t launch_k(Kern kern, const Dev& p, size_t smem, long long tiles, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  long long cap = (long long)max_ctas() * (per_sm > 2 ? 2 : per_sm);  // partials sized for 2/SM
+  int grid = (int)(tiles < cap ? tiles : cap);
+  if (grid < 1) grid = 1;
+  kern<<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+template <int KK, int SS, int CC, typename Dev>
+static cudaError_t launch_bwd(const Dev& p, size_t smem, long long tiles, cudaStream_t st) {
+  if constexpr (KK == 7) {
+    cudaError_t e = launch_k(dw_bwd_kernel<KK, SS, CC, 0, 25, true>, p, smem, tiles, st);
+    if (e != cudaSuccess) return e;
+    return launch_k(dw_bwd_kernel<KK, SS, CC, 25, KK * KK, false>, p, smem, tiles, st);
+  } else {
+    return launch_k(dw_bwd_kernel<KK, SS, CC, 0, KK * KK, true>, p, smem, tiles, st);
+  }
+}
+#define YAMB_DW_BWD(KK, SS, CC, ...) e = launch_bwd<KK, SS, CC>(__VA_ARGS__)
+
+#define YAMB_DW_DISPATCH(KERN, ...)                                           \
+  do {                                                                        \
+    if (k == 3 && s == 1 && ct == 64) e = launch_k(KERN<3, 1, 64>, __VA_ARGS__);      \
+    else if (k == 3 && s == 2 && ct == 64) e = launch_k(KERN<3, 2, 64>, __VA_ARGS__); \
+    else if (k == 3 && s == 1) e = launch_k(KERN<3, 1, 32>, __VA_ARGS__);             \
+    else if (k == 3 && s == 2) e = launch_k(KERN<3, 2, 32>, __VA_ARGS__);             \
+    else if (k == 5 && s == 1 && ct == 64) e = launch_k(KERN<5, 1, 64>, __VA_ARGS__); \
+    else if (k == 5 && s == 2 && ct == 64) e = launch_k(KERN<5, 2, 64>, __VA_ARGS__); \
+    else if (k == 5 && s == 1) e = launch_k(KERN<5, 1, 32>, __VA_ARGS__);             \
+    else if (k == 5 && s == 2) e = launch_k(KERN<5, 2, 32>, __VA_ARGS__);             \
+    else if (k == 7 && s == 1 && ct == 64) e = launch_k(KERN<7, 1, 64>, __VA_ARGS__); \
+    else if (k == 7 && s == 2 && ct == 64) e = launch_k(KERN<7, 2, 64>, __VA_ARGS__); \
+    else if (k == 7 && s == 1) e = launch_k(KERN<7, 1, 32>, __VA_ARGS__);             \
+    else e = launch_k(KERN<7, 2, 32>, __VA_ARGS__);                                   \
+  } while (0)
 
 int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   if (!a) return set_error(YAMB_EINVAL, "null args");
   int rc = check_common(a->N, a->H, a->W, a->C, a->ldc, a->k, a->stride);
   if (rc) return rc;
   if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
-  const int k = a->k, pad = (k - 1) / 2;
+  if (!a->x || !a->y || !a->w) return set_error(YAMB_EINVAL, "depthwise fwd: null pointer");
+  const int k = a->k, s = a->stride, pad = (k - 1) / 2;
+  const int ct = a->C > 32 ? 64 : 32;
   DwFwdDev p;
   p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.ldc = a->ldc;
-  p.Ho = (a->H + 2 * pad - k) / a->stride + 1;
-  p.Wo = (a->W + 2 * pad - k) / a->stride + 1;
+  p.Ho = (a->H + 2 * pad - k) / s + 1;
+  p.Wo = (a->W + 2 * pad - k) / s + 1;
   p.x = (const __nv_bfloat16*)a->x; p.y = (__nv_bfloat16*)a->y;
   p.in_scale = a->in_scale; p.in_shift = a->in_shift; p.in_act = a->in_act;
   p.w = a->w;
   p.has_bn = a->bn ? 1 : 0;
   if (a->bn) p.bn = *a->bn;
-  if ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 15)
-    return set_error(YAMB_EINVAL, "depthwise: activations must be 16-byte aligned");
-  const int vec = pick_vec(a->C, k, false);
-  const int CG = a->C / vec, PX = 256 / CG;
-  const long long items = (long long)a->N * ((p.Ho + 3) / 4) * p.Wo;
-  long long want = (items + PX - 1) / PX;
-  int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
-  if (grid < 1) grid = 1;
-  const size_t smem = (size_t)2 * a->C * sizeof(float);
+  if ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 7)
+    return set_error(YAMB_EINVAL, "depthwise: activations must be 8-byte aligned");
+  const int toh = ct == 64 ? 8 : 16, tow = 8;
+  p.tiles_h = (p.Ho + toh - 1) / toh;
+  p.tiles_w = (p.Wo + tow - 1) / tow;
+  p.chunks = (a->C + ct - 1) / ct;
+  p.num_tiles = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+  const int ih = (toh - 1) * s + k, iw = (tow - 1) * s + k;
+  const size_t smem = ((size_t)ih * iw * ct + 4 * (size_t)a->C) * sizeof(float);
+  if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise fwd: tile too large");
   cudaError_t e;
-  YAMB_DISPATCH_KV(launch_fwd, p, a->stride, grid, smem, st);
+  YAMB_DW_DISPATCH(dw_fwd_kernel, p, smem, p.num_tiles, st);
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "dw fwd launch: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -402,11 +538,12 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
   if (!a->ca || !a->cb || !a->cc || !a->dz || !a->h || !a->x || !a->dx || !a->dw || !a->w)
     return set_error(YAMB_EINVAL, "depthwise bwd: null pointer");
-  const int k = a->k, pad = (k - 1) / 2;
+  const int k = a->k, s = a->stride, pad = (k - 1) / 2;
+  const int ct = a->C > 32 ? 64 : 32;
   DwBwdDev p;
   p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.ldc = a->ldc;
-  p.Ho = (a->H + 2 * pad - k) / a->stride + 1;
-  p.Wo = (a->W + 2 * pad - k) / a->stride + 1;
+  p.Ho = (a->H + 2 * pad - k) / s + 1;
+  p.Wo = (a->W + 2 * pad - k) / s + 1;
   p.dz = (const __nv_bfloat16*)a->dz; p.h = (const __nv_bfloat16*)a->h;
   p.ca = a->ca; p.cb = a->cb; p.cc = a->cc;
   p.w = a->w; p.dw = a->dw;
@@ -416,16 +553,28 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   p.residual = (const __nv_bfloat16*)a->residual;
   p.has_bn = a->bn ? 1 : 0;
   if (a->bn) p.bn = *a->bn;
-  const int vec = pick_vec(a->C, k, true);
-  const int CG = a->C / vec, PX = 256 / CG;
-  const long long items = (long long)a->N * a->H * a->W;
-  long long want = (items + PX - 1) / PX;
-  int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
-  if (grid < 1) grid = 1;
-  const size_t smem = (size_t)(2 * k * k + 2) * a->C * sizeof(float);
-  if (smem > 200 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");
+  const int ti = s == 1 ? 8 : 16;
+  const int rmax = s == 1 ? ti + k - 1 : (ti + k - 1) / 2 + 1;
+  p.tiles_h = (a->H + ti - 1) / ti;
+  p.tiles_w = (a->W + ti - 1) / ti;
+  p.chunks = (a->C + ct - 1) / ct;
+  p.num_tiles = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+  const size_t smem =
+      ((size_t)rmax * rmax * ct + (size_t)(7 + 2 * k * k + 2) * a->C) * sizeof(float);
+  if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");
   cudaError_t e;
-  YAMB_DISPATCH_KV(launch_bwd, p, a->stride, grid, smem, st);
+  if (k == 3 && s == 1 && ct == 64) YAMB_DW_BWD(3, 1, 64, p, smem, p.num_tiles, st);
+  else if (k == 3 && s == 2 && ct == 64) YAMB_DW_BWD(3, 2, 64, p, smem, p.num_tiles, st);
+  else if (k == 3 && s == 1) YAMB_DW_BWD(3, 1, 32, p, smem, p.num_tiles, st);
+  else if (k == 3 && s == 2) YAMB_DW_BWD(3, 2, 32, p, smem, p.num_tiles, st);
+  else if (k == 5 && s == 1 && ct == 64) YAMB_DW_BWD(5, 1, 64, p, smem, p.num_tiles, st);
+  else if (k == 5 && s == 2 && ct == 64) YAMB_DW_BWD(5, 2, 64, p, smem, p.num_tiles, st);
+  else if (k == 5 && s == 1) YAMB_DW_BWD(5, 1, 32, p, smem, p.num_tiles, st);
+  else if (k == 5 && s == 2) YAMB_DW_BWD(5, 2, 32, p, smem, p.num_tiles, st);
+  else if (k == 7 && s == 1 && ct == 64) YAMB_DW_BWD(7, 1, 64, p, smem, p.num_tiles, st);
+  else if (k == 7 && s == 2 && ct == 64) YAMB_DW_BWD(7, 2, 64, p, smem, p.num_tiles, st);
+  else if (k == 7 && s == 1) YAMB_DW_BWD(7, 1, 32, p, smem, p.num_tiles, st);
+  else YAMB_DW_BWD(7, 2, 32, p, smem, p.num_tiles, st);
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "dw bwd launch: %s", cudaGetErrorString(e));
   return 0;
 }
