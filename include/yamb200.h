@@ -213,7 +213,7 @@ int yamb_ema_update(float* shadow, const float* x, int64_t n, const float* hyper
 int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t stream);
 
 /* upper bound of CTAs any statistics-producing kernel launches (sizes `partials`: 2*C floats
- * per CTA); 2 x SM count; <= 0 without a device */
+ * per CTA); 4 x SM count; <= 0 without a device */
 int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,

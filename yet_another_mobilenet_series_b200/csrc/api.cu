@@ -49,7 +49,7 @@ extern "C" {
 
 const char* yamb_last_error(void) { return yamb::g_err; }
 int yamb_version(void) { return 100; }
-int yamb_max_ctas(void) { int n = yamb::max_ctas(); return n > 0 ? 2 * n : n; }
+int yamb_max_ctas(void) { int n = yamb::max_ctas(); return n > 0 ? 4 * n : n; }
 int yamb_struct_size(int which) {
   switch (which) {
     case 0: return (int)sizeof(yamb_bn_fwd);

@@ -124,22 +124,41 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
     __syncthreads();  // previous tile's compute is done with s_tile (and the tables are written)
     // ---- stage the input tile: BN + activation applied once per element, halo / padding = 0 ----
-    for (int idx = tid; idx < IH * IW * NCG; idx += 256) {
-      const int pix = idx / NCG, g = idx % NCG;
-      const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
-      const int c = cbase + g * 4;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && c < p.C) {
-        float v[4];
-        ld4(p.x + ((size_t)((size_t)n * p.H + iy) * p.W + ix) * p.ldc + c, v);
-        const float4 sc = *reinterpret_cast<const float4*>(s_sc + c);
-        const float4 sh = *reinterpret_cast<const float4*>(s_sh + c);
-        a.x = act_fwd(fmaf(sc.x, v[0], sh.x), act);
-        a.y = act_fwd(fmaf(sc.y, v[1], sh.y), act);
-        a.z = act_fwd(fmaf(sc.z, v[2], sh.z), act);
-        a.w = act_fwd(fmaf(sc.w, v[3], sh.w), act);
+    // (4 independent global loads in flight per thread before the first use)
+    constexpr int NV = IH * IW * NCG;
+#pragma unroll 1
+    for (int base = tid; base < NV; base += 4 * 256) {
+      uint2 raw[4];
+      int cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * 256;
+        const int pix = idx / NCG, g = idx % NCG;
+        const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
+        const int c = cbase + g * 4;
+        cc[u] = -1;
+        raw[u] = make_uint2(0u, 0u);
+        if (idx < NV && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && c < p.C) {
+          cc[u] = c;
+          raw[u] = __ldg(reinterpret_cast<const uint2*>(
+              p.x + ((size_t)((size_t)n * p.H + iy) * p.W + ix) * p.ldc + c));
+        }
       }
-      *reinterpret_cast<float4*>(s_tile + (size_t)pix * CT + g * 4) = a;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int idx = base + u * 256;
+        if (idx >= NV) break;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc[u] >= 0) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc[u]);
+          const float4 sh = *reinterpret_cast<const float4*>(s_sh + cc[u]);
+          a.x = act_fwd(fmaf(sc.x, bf16lo(raw[u].x), sh.x), act);
+          a.y = act_fwd(fmaf(sc.y, bf16hi(raw[u].x), sh.y), act);
+          a.z = act_fwd(fmaf(sc.z, bf16lo(raw[u].y), sh.z), act);
+          a.w = act_fwd(fmaf(sc.w, bf16hi(raw[u].y), sh.w), act);
+        }
+        *reinterpret_cast<float4*>(s_tile + (size_t)(idx / NCG) * CT + (idx % NCG) * 4) = a;
+      }
     }
     __syncthreads();
     // ---- stencil: TH output rows x 4 channels per thread ----
@@ -236,7 +255,7 @@ struct BwdGeom {
 // 49 x 4 accumulators do not fit the register file and a second, wgrad-only launch covers the rest).
 // DGRAD: compute and store dx (+ statistics); false for that second launch.
 template <int K, int S, int CT, int TAP0, int TAP1, bool DGRAD>
-__global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwBwdDev p) {
+__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __grid_constant__ DwBwdDev p) {
   using G = BwdGeom<K, S>;
   constexpr int P = G::P, TI = G::TI, RMAX = G::RMAX;
   constexpr int NCG = CT / 4;
@@ -270,7 +289,6 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwB
   const int cg = tid % NCG;
   const int pslot = tid / NCG;
   float gw[NT][4];
-  float wreg[DGRAD ? K * K : 1][4];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int tp = 0; tp < NT; ++tp)
@@ -311,12 +329,6 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwB
     if (chunk != cur_chunk) {
       if (cur_chunk >= 0) flush(cur_chunk);
       cur_chunk = chunk;
-      if (DGRAD) {
-#pragma unroll
-        for (int tp = 0; tp < K * K; ++tp)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) wreg[tp][v] = cvalid ? s_w[tp * p.C + c0 + v] : 0.f;
-      }
     }
     const int y0 = ty * TI, x0 = tx * TI;
     // first output row / col whose receptive field reaches this input tile
@@ -324,25 +336,43 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwB
     const int rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
     __syncthreads();
     // ---- stage dh = ca*dz + cb*h + cc over the gradient region (0 outside the image) ----
-    for (int idx = tid; idx < RMAX * RMAX * NCG; idx += 256) {
-      const int pix = idx / NCG, g = idx % NCG;
-      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
-      const int c = cbase + g * 4;
-      float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo && c < p.C) {
-        const size_t o = ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c;
-        float dzv[4], hv[4];
-        ld4(p.dz + o, dzv);
-        ld4(p.h + o, hv);
-        const float4 ca = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
-        const float4 cb = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
-        const float4 cc = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
-        dh.x = fmaf(ca.x, dzv[0], fmaf(cb.x, hv[0], cc.x));
-        dh.y = fmaf(ca.y, dzv[1], fmaf(cb.y, hv[1], cc.y));
-        dh.z = fmaf(ca.z, dzv[2], fmaf(cb.z, hv[2], cc.z));
-        dh.w = fmaf(ca.w, dzv[3], fmaf(cb.w, hv[3], cc.w));
+    constexpr int NV = RMAX * RMAX * NCG;
+#pragma unroll 1
+    for (int base = tid; base < NV; base += 2 * 256) {
+      uint2 rdz[2], rh[2];
+      int cc2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = base + u * 256;
+        const int pix = idx / NCG, g = idx % NCG;
+        const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
+        const int c = cbase + g * 4;
+        cc2[u] = -1;
+        rdz[u] = rh[u] = make_uint2(0u, 0u);
+        if (idx < NV && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo && c < p.C) {
+          const size_t o = ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c;
+          cc2[u] = c;
+          rdz[u] = __ldg(reinterpret_cast<const uint2*>(p.dz + o));
+          rh[u] = __ldg(reinterpret_cast<const uint2*>(p.h + o));
+        }
       }
-      *reinterpret_cast<float4*>(s_dh + (size_t)pix * CT + g * 4) = dh;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = base + u * 256;
+        if (idx >= NV) break;
+        float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc2[u] >= 0) {
+          const int c = cc2[u];
+          const float4 ca = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
+          const float4 cb = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
+          const float4 cc = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
+          dh.x = fmaf(ca.x, bf16lo(rdz[u].x), fmaf(cb.x, bf16lo(rh[u].x), cc.x));
+          dh.y = fmaf(ca.y, bf16hi(rdz[u].x), fmaf(cb.y, bf16hi(rh[u].x), cc.y));
+          dh.z = fmaf(ca.z, bf16lo(rdz[u].y), fmaf(cb.z, bf16lo(rh[u].y), cc.z));
+          dh.w = fmaf(ca.w, bf16hi(rdz[u].y), fmaf(cb.w, bf16hi(rh[u].y), cc.w));
+        }
+        *reinterpret_cast<float4*>(s_dh + (size_t)(idx / NCG) * CT + (idx % NCG) * 4) = dh;
+      }
     }
     __syncthreads();
     // ---- per input pixel: dgrad gather + fused wgrad + act'/BN-backward epilogue ----
@@ -394,10 +424,11 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const __grid_constant__ DwB
             const float4 dh = *reinterpret_cast<const float4*>(
                 s_dh + (size_t)((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
             if (DGRAD) {
-              da[0] = fmaf(dh.x, wreg[tp][0], da[0]);
-              da[1] = fmaf(dh.y, wreg[tp][1], da[1]);
-              da[2] = fmaf(dh.z, wreg[tp][2], da[2]);
-              da[3] = fmaf(dh.w, wreg[tp][3], da[3]);
+              const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
+              da[0] = fmaf(dh.x, wv.x, da[0]);
+              da[1] = fmaf(dh.y, wv.y, da[1]);
+              da[2] = fmaf(dh.z, wv.z, da[2]);
+              da[3] = fmaf(dh.w, wv.w, da[3]);
             }
             if (tp >= TAP0 && tp < TAP1) {
               gw[tp - TAP0][0] = fmaf(dh.x, a1[0], gw[tp - TAP0][0]);
@@ -463,7 +494,7 @@ static cudaError_t launch_k(Kern kern, const Dev& p, size_t smem, long long tile
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-  long long cap = (long long)max_ctas() * (per_sm > 2 ? 2 : per_sm);  // partials sized for 2/SM
+  long long cap = (long long)max_ctas() * (per_sm > 4 ? 4 : per_sm);  // partials sized for 4/SM
   int grid = (int)(tiles < cap ? tiles : cap);
   if (grid < 1) grid = 1;
   kern<<<grid, 256, smem, st>>>(p);

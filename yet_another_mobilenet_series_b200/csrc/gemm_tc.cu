@@ -5,9 +5,12 @@
 //   warp 1      MMA issuer   (one elected lane, tcgen05.mma.cta_group::1.kind::f16, M=128)
 //   warp 2      TMEM allocator / deallocator
 //   warp 3      idle
-//   warps 4-7   epilogue: tcgen05.ld -> registers -> fused math -> swizzled smem -> TMA store,
-//               per-column BatchNorm statistics
-//   warps 8-11  operand transform (BN-apply + activation, or BN-backward affine) applied in place
+//   warps 4-11  epilogue, two warpgroups that alternate tiles (one per TMEM accumulator stage) so
+//               the latency chain of one tile hides behind the other; every WARP is independent:
+//               tcgen05.ld (its 32 TMEM lanes) -> registers -> fused math -> warp-private swizzled
+//               smem -> its own TMA store (box 64 x 32) -> per-column BatchNorm statistics read back
+//               from the staged tile.  No CTA-wide barrier in the steady state.
+//   warps 12-15 operand transform (BN-apply + activation, or BN-backward affine) applied in place
 //               on the TMA-landed tile before the MMA reads it (only launched when needed)
 //
 // Replaces, behind yamb_pointwise_gemm (include/yamb200.h), the nn.Conv2d(kernel_size=1) forward /
@@ -29,7 +32,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kPanelBytes64 = 8192;  // 64 rows x 128 B
 constexpr int kABytes = 16384;       // 128 x 64 bf16
-constexpr int kStageOutBytes = 16384;  // 128 rows x 64 cols bf16 staging sub-tile
+constexpr int kWarpOutBytes = 4096;  // 32 rows x 64 cols bf16: one warp's staging sub-tile
+constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // two accumulator stages of 256 columns
@@ -50,6 +54,9 @@ struct GemmDev {
   int has_residual;
   void* D;
   long long ldd;
+  const __nv_bfloat16* side;  // residual (epi 0) or H (epi 1), row-major [M][lds]
+  long long lds;
+  int out_bufs;               // staging buffers per epilogue warp (1 or 2)
   yamb_bn_fwd bnf;
   int has_bnf;
   const float *h_scale, *h_shift;
@@ -57,7 +64,7 @@ struct GemmDev {
   yamb_bn_bwd bnb;
   int has_bnb;
   // smem offsets (bytes from the 1024-aligned base)
-  int off_out, off_side, off_coef, off_stats, off_bars;
+  int off_out, off_hside, off_coef, off_stats, off_bars;
 };
 
 struct Bars {
@@ -66,7 +73,6 @@ struct Bars {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t side[2];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -118,11 +124,10 @@ __device__ __forceinline__ void xform_panel(uint8_t* panel, const uint8_t* panel
 }
 
 template <bool kXform>
-__global__ void __launch_bounds__(kXform ? 384 : 256, 1)
+__global__ void __launch_bounds__(kXform ? 512 : 384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmS,
-               const __grid_constant__ GemmDev p) {
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -149,7 +154,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], 128);
-      mbar_init(&bars->side[i], 1);
     }
     fence_barrier_init();
   }
@@ -274,13 +278,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
     // ======================================= epilogue =======================================
-    const int et = threadIdx.x - 128;  // 0..127
-    const int q = warp & 3;            // TMEM lane quadrant
+    const int ew = warp - 4;           // 0..7
+    const int wg = ew >> 2;            // epilogue warpgroup = TMEM accumulator stage it serves
+    const int q = warp & 3;            // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;     // row inside the 128-row tile
-    uint8_t* s_out = smem + p.off_out;
-    uint8_t* s_side = smem + p.off_side;
+    uint8_t* s_out = smem + p.off_out + (size_t)ew * p.out_bufs * kWarpOutBytes;
+    uint8_t* s_h = smem + p.off_hside + (size_t)ew * kWarpOutBytes;  // epi 1: raw H rows
     // per-column coefficient tables for epi 1:  [h_scale | h_shift | mean | invstd] x N
     const float* cz_s = s_coef;
     const float* cz_t = s_coef + p.N;
@@ -288,36 +293,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* cz_r = s_coef + 3 * p.N;
     if (p.epi == 1) {
       float* wr = s_coef;
-      for (int i = et; i < p.N; i += 128) {
+      for (int i = threadIdx.x - 128; i < p.N; i += 32 * kEpiWarps) {
         wr[i] = p.h_scale[i];
         wr[p.N + i] = p.h_shift[i];
         wr[2 * p.N + i] = p.bnb.mean[i];
         wr[3 * p.N + i] = p.bnb.invstd[i];
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 32 * kEpiWarps);
     }
-    int it = 0;
-    uint32_t sub_count = 0;   // running sub-tile counter -> staging buffer parity
-    uint32_t side_count = 0;  // running side-load counter
+    uint32_t sub_count = 0;   // running sub-tile counter of this warp -> staging buffer parity
     const bool side_in = (p.epi == 1) || p.has_residual;
+    // Column statistics: with a single n-block every lane owns the same 2 columns of sub-tile j in
+    // every tile, so the sums live in registers for the whole kernel (shared-memory float atomics
+    // are CAS loops and serialise the 8 epilogue warps); flushed once at the end.
+    const bool reg_stats = (p.has_bnf || p.has_bnb) && p.n_blocks == 1;
+    float racc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) racc[j][e] = 0.f;
+    int it = 0;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
+      if ((it & 1) != wg) continue;    // the other warpgroup owns this tile
       const int mn = w / p.ksplit;
       const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
-      const int as = it & 1;
+      const int as = wg;
+      const int grow = m_blk * kBlockM + row;
+      const bool row_ok = grow < p.M;
       // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
       const int n_sub = min((p.block_n + 63) / 64, (p.N - n_blk * p.block_n + 63) / 64);
-      const int grow = m_blk * kBlockM + row;
-      // prefetch the first side sub-tile of this tile
-      if (side_in && et == 0) {
-        const uint32_t sb = side_count & 1;
-        mbar_arrive_expect_tx(&bars->side[sb], kStageOutBytes);
-        tma_load_2d(&tmS, &bars->side[sb], s_side + sb * kStageOutBytes, n_blk * p.block_n,
-                    m_blk * kBlockM);
-      }
       mbar_wait(&bars->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
-      for (int sub = 0; sub < n_sub; ++sub) {
+#pragma unroll
+      for (int sub = 0; sub < 4; ++sub) {
+        if (sub >= n_sub) break;
         const int col0 = n_blk * p.block_n + sub * 64;  // global column of this sub-tile
+        // side operand rows straight from global (each thread owns one row: 8 x 16 B)
+        uint4 sv[8];
+        if (side_in) {
+          const __nv_bfloat16* srow = p.side + (size_t)grow * p.lds + col0;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            sv[ch] = make_uint4(0u, 0u, 0u, 0u);
+            if (row_ok && col0 + ch * 8 < p.N)
+              sv[ch] = __ldg(reinterpret_cast<const uint4*>(srow + ch * 8));
+          }
+        }
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + sub * 64);
         uint32_t acc[2][32];
@@ -331,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (p.epi == 2) {
           // split-K partial sums: fp32 atomic accumulate into D[M][ldd]
-          if (grow < p.M) {
+          if (row_ok) {
             float* drow = reinterpret_cast<float*>(p.D) + (size_t)grow * p.ldd;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -339,39 +360,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) {
                 const int c = col0 + h * 32 + j;
                 if (c < p.N && (sub * 64 + h * 32 + j) < p.block_n)
-                  atomicAdd(drow + c, __uint_as_float(acc[h][j]));
+                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(drow + c),
+                               "f"(__uint_as_float(acc[h][j]))
+                               : "memory");
               }
           }
           continue;
         }
-        const uint32_t ob = sub_count & 1;
-        uint8_t* sO = s_out + ob * kStageOutBytes;
+        uint8_t* sO = s_out + (p.out_bufs == 2 ? (sub_count & 1) : 0) * kWarpOutBytes;
         // the TMA store that last read this staging buffer must have drained
-        if (et == 0) tma_store_wait_read<1>();
-        const uint8_t* sS = nullptr;
-        if (side_in) {
-          const uint32_t sb = side_count & 1;
-          sS = s_side + sb * kStageOutBytes;
-          mbar_wait(&bars->side[sb], (side_count >> 1) & 1);
+        if (lane == 0) {
+          if (p.out_bufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
         }
-        named_bar_sync(1, 128);
-        // kick the next side sub-tile (its buffer was consumed two sub-tiles ago; all threads have
-        // passed the barrier above, which is after their last read of it)
-        if (side_in && et == 0 && sub + 1 < n_sub) {
-          const uint32_t sb = (side_count + 1) & 1;
-          mbar_arrive_expect_tx(&bars->side[sb], kStageOutBytes);
-          tma_load_2d(&tmS, &bars->side[sb], s_side + sb * kStageOutBytes, col0 + 64,
-                      m_blk * kBlockM);
-        }
+        __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 columns
-          const int pc = ch ^ (row & 7);
+          const int pc = ch ^ (lane & 7);
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
           if (side_in) {
-            const uint4 sv = *reinterpret_cast<const uint4*>(sS + row * 128 + (pc << 4));
-            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            const uint32_t sw[4] = {sv[ch].x, sv[ch].y, sv[ch].z, sv[ch].w};
             if (p.epi == 0) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -390,6 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   v[2 * e + 1] *= act_bwd(z1, p.h_act);
                 }
               }
+              *reinterpret_cast<uint4*>(s_h + lane * 128 + (pc << 4)) = sv[ch];
             }
           }
           uint4 o;
@@ -397,27 +408,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           o.y = pack_bf16(v[2], v[3]);
           o.z = pack_bf16(v[4], v[5]);
           o.w = pack_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(sO + row * 128 + (pc << 4)) = o;
+          *reinterpret_cast<uint4*>(sO + lane * 128 + (pc << 4)) = o;
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (et == 0) {
-          tma_store_2d(&tmD, sO, col0, m_blk * kBlockM);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmD, sO, col0, m_blk * kBlockM + q * 32);
           tma_store_commit();
         }
-        // ---- per-column statistics of the bf16-rounded output tile ----
+        // ---- per-column statistics of this warp's 32 rows of the bf16-rounded output ----
         if (p.has_bnf || p.has_bnb) {
-          const int cp = et & 31;  // column pair
-          const int rg = et >> 5;  // row group of 32 rows
-          const int c = col0 + 2 * cp;
-          if (c < p.N && (sub * 64 + 2 * cp) < p.block_n) {
+          const int c = col0 + 2 * lane;  // column pair owned by this lane
+          if (c < p.N && (sub * 64 + 2 * lane) < p.block_n) {
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const int rmax = min(32, p.M - (m_blk * kBlockM + rg * 32));
+            const int rmax = min(32, p.M - (m_blk * kBlockM + q * 32));
             if (p.has_bnf) {
               for (int r = 0; r < rmax; ++r) {
-                const int rr = rg * 32 + r;
                 const uint32_t u = *reinterpret_cast<const uint32_t*>(
-                    sO + rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+                    sO + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
                 const float a = bf16lo(u), b = bf16hi(u);
                 s0 += a; s1 += b;
                 q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
@@ -425,31 +433,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               const float m0 = cz_m[c], m1 = cz_m[c + 1], r0 = cz_r[c], r1 = cz_r[c + 1];
               for (int r = 0; r < rmax; ++r) {
-                const int rr = rg * 32 + r;
-                const int off = rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2);
+                const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
                 const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + off);
-                const uint32_t hh = *reinterpret_cast<const uint32_t*>(sS + off);
+                const uint32_t hh = *reinterpret_cast<const uint32_t*>(s_h + off);
                 const float a = bf16lo(u), b = bf16hi(u);
                 s0 += a; s1 += b;
                 q0 = fmaf(a, (bf16lo(hh) - m0) * r0, q0);
                 q1 = fmaf(b, (bf16hi(hh) - m1) * r1, q1);
               }
             }
-            atomicAdd(&s_stats[c], s0);
-            atomicAdd(&s_stats[c + 1], s1);
-            atomicAdd(&s_stats[p.N + c], q0);
-            atomicAdd(&s_stats[p.N + c + 1], q1);
+            if (reg_stats) {
+              racc[sub][0] += s0; racc[sub][1] += s1; racc[sub][2] += q0; racc[sub][3] += q1;
+            } else {
+              atomicAdd(&s_stats[c], s0);
+              atomicAdd(&s_stats[c + 1], s1);
+              atomicAdd(&s_stats[p.N + c], q0);
+              atomicAdd(&s_stats[p.N + c + 1], q1);
+            }
           }
+          __syncwarp();  // s_h / sO reads done before the next sub-tile overwrites them
         }
         ++sub_count;
-        if (side_in) ++side_count;
       }
     }
-    if (et == 0 && p.epi != 2) tma_store_wait_all<0>();
-  } else if (kXform && warp >= 8) {
+    if (reg_stats) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = j * 64 + 2 * lane;
+        if (c < p.N) {
+          atomicAdd(&s_stats[c], racc[j][0]);
+          atomicAdd(&s_stats[c + 1], racc[j][1]);
+          atomicAdd(&s_stats[p.N + c], racc[j][2]);
+          atomicAdd(&s_stats[p.N + c + 1], racc[j][3]);
+        }
+      }
+    }
+    if (lane == 0 && p.epi != 2) tma_store_wait_all<0>();
+  } else if (kXform && warp >= 4 + kEpiWarps) {
     // ================================== operand transform ==================================
     if (use_x) {
-      const int t = threadIdx.x - 256;
+      const int t = threadIdx.x - 32 * (4 + kEpiWarps);
       // coefficient tables in smem: A: [scale|shift|scale2] x Ca, then B likewise
       const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
       const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
@@ -629,29 +652,34 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
   const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
   int fixed = 0;
-  int out_bytes = (a->epi == 2) ? 0 : 2 * kStageOutBytes;
-  int side_bytes = (a->epi == 1 || p.has_residual) ? 2 * kStageOutBytes : 0;
-  int coef_bytes = ((a->epi == 1 ? 4 * p.N : 0) + 3 * Ca + 3 * Cb) * 4;
-  int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * 4 : 0;
-  fixed = out_bytes + side_bytes + ((coef_bytes + 15) & ~15) + ((stats_bytes + 15) & ~15) +
-          (int)sizeof(Bars) + 64;
+  // every epilogue warp stages its own 32 x 64 sub-tile: 2 buffers each unless smem is short
+  const int side_bytes = (a->epi == 1) ? kEpiWarps * kWarpOutBytes : 0;  // raw H rows (epi 1)
+  const int coef_bytes = ((a->epi == 1 ? 4 * p.N : 0) + 3 * Ca + 3 * Cb) * 4;
+  const int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * 4 : 0;
   const int budget = 232448 - 1024;  // 227 KB minus alignment slack
-  int stages = (budget - fixed) / p.stage_bytes;
+  int stages = 0, out_bytes = 0;
+  for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
+    out_bytes = (a->epi == 2) ? 0 : p.out_bufs * kEpiWarps * kWarpOutBytes;
+    fixed = out_bytes + side_bytes + ((coef_bytes + 15) & ~15) + ((stats_bytes + 15) & ~15) +
+            (int)sizeof(Bars) + 64;
+    stages = (budget - fixed) / p.stage_bytes;
+    if (stages >= 3 || p.out_bufs == 1) break;
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(YAMB_EINVAL, "GEMM tile does not fit shared memory");
   p.num_stages = stages;
   int off = stages * p.stage_bytes;
   p.off_out = off; off += out_bytes;
-  p.off_side = off; off += side_bytes;
+  p.off_hside = off; off += side_bytes;
   p.off_coef = off; off += (coef_bytes + 15) & ~15;
   p.off_stats = off; off += (stats_bytes + 15) & ~15;
   p.off_bars = (off + 15) & ~15; off = p.off_bars + (int)sizeof(Bars);
   const int smem_total = off + 1024;
 
   // ---- tensor maps ----
-  CUtensorMap tmA, tmB, tmA2, tmB2, tmD, tmS;
+  CUtensorMap tmA, tmB, tmA2, tmB2, tmD;
   memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB2, 0, sizeof(tmB2));
-  memset(&tmD, 0, sizeof(tmD)); memset(&tmS, 0, sizeof(tmS));
+  memset(&tmD, 0, sizeof(tmD));
   int rc;
   if (!p.a_mn) rc = make_map_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128);
   else rc = make_map_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64);
@@ -670,12 +698,13 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   if (a->epi != 2) {
-    rc = make_map_2d(&tmD, a->D, a->N, a->M, a->ldd, 64, 128);
+    rc = make_map_2d(&tmD, a->D, a->N, a->M, a->ldd, 64, 32);  // one epilogue warp's rows
     if (rc) return rc;
   }
-  if (a->epi == 1) rc = make_map_2d(&tmS, a->H, a->N, a->M, a->ldh, 64, 128);
-  else if (p.has_residual) rc = make_map_2d(&tmS, a->residual, a->N, a->M, a->ldr, 64, 128);
-  if (rc) return rc;
+  if (a->epi == 1) { p.side = (const __nv_bfloat16*)a->H; p.lds = a->ldh; }
+  else if (p.has_residual) { p.side = (const __nv_bfloat16*)a->residual; p.lds = a->ldr; }
+  if (p.side && ((reinterpret_cast<uintptr_t>(p.side) & 15) || (p.lds % 8)))
+    return set_error(YAMB_EINVAL, "side operand must be 16-byte aligned with lds % 8 == 0");
 
   const int grid = p.num_work < ctas ? p.num_work : ctas;
   cudaError_t e;
@@ -683,12 +712,12 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_total);
     if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
-    gemm_tc_kernel<true><<<grid, 384, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, tmS, p);
+    gemm_tc_kernel<true><<<grid, 512, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p);
   } else {
     e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_total);
     if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
-    gemm_tc_kernel<false><<<grid, 256, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, tmS, p);
+    gemm_tc_kernel<false><<<grid, 384, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
