@@ -178,6 +178,7 @@ def run_case(name):
         bwd.dgamma, bwd.dbeta = dg.data_ptr(), db.data_ptr()
         bwd.ca, bwd.cb, bwd.cc = [o.data_ptr() for o in co]
         bwd.count = M
+        bwd.use_batch_stats = 1
         g.H, g.ldh = H.data_ptr(), N
         g.h_scale, g.h_shift, g.h_act = hs.data_ptr(), ht.data_ptr(), act
         g.bn_bwd = C.pointer(bwd)

@@ -81,46 +81,138 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- explicit shared-space vector accesses (32-bit shared addresses, never generic) ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w) : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_c(float z) {
+  if (ACT == ACT_RELU) return fmaxf(z, 0.f);
+  if (ACT == ACT_RELU6) return fminf(fmaxf(z, 0.f), 6.f);
+  if (ACT == ACT_SWISH) return z / (1.f + __expf(-z));
+  if (ACT == ACT_HSWISH) return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return z;
+}
+
+// One 16-byte chunk (8 channels) of one row of a panel: loads first, math later.
+struct XChunk {
+  uint4 v, v2;
+  float4 sa, sb, ba, bb, ta, tb;
+  uint32_t addr;
+  bool ok;
+};
+template <int MODE>
+__device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t rbase2, int row,
+                                            int lc, uint32_t tab_s, uint32_t tab_b,
+                                            uint32_t tab_s2, int cbase, int C) {
+  const int c0 = cbase + lc * 8;
+  k.ok = c0 < C;
+  const uint32_t off = (uint32_t)((lc ^ (row & 7)) << 4);
+  k.addr = rbase + off;
+  if (k.ok) {
+    k.v = lds128(rbase + off);
+    if (MODE == 2) k.v2 = lds128(rbase2 + off);
+    k.sa = lds128f(tab_s + c0 * 4);
+    k.sb = lds128f(tab_s + c0 * 4 + 16);
+    k.ba = lds128f(tab_b + c0 * 4);
+    k.bb = lds128f(tab_b + c0 * 4 + 16);
+    if (MODE == 2) {
+      k.ta = lds128f(tab_s2 + c0 * 4);
+      k.tb = lds128f(tab_s2 + c0 * 4 + 16);
+    }
+  }
+}
+// Activation as data: relu / relu6 / none are clamp(z, lo, hi); swish / h-swish take the uniform
+// slow branch.  Keeps ONE copy of the transform per (R, MODE) instead of one per activation.
+struct ActParam {
+  float lo, hi;
+  int kind;  // 0: clamp only, ACT_SWISH, ACT_HSWISH
+};
+__device__ __forceinline__ ActParam make_act(int act) {
+  ActParam a;
+  a.lo = (act == ACT_RELU || act == ACT_RELU6) ? 0.f : -3.0e38f;
+  a.hi = (act == ACT_RELU6) ? 6.f : 3.0e38f;
+  a.kind = (act == ACT_SWISH || act == ACT_HSWISH) ? act : 0;
+  return a;
+}
+__device__ __forceinline__ float act_rt(float z, const ActParam& a) {
+  if (a.kind == 0) return fminf(fmaxf(z, a.lo), a.hi);
+  if (a.kind == ACT_SWISH) return z / (1.f + __expf(-z));
+  return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+}
+
+template <int MODE>
+__device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap) {
+  if (!k.ok) return;
+  float x0 = bf16lo(k.v.x), x1 = bf16hi(k.v.x), x2 = bf16lo(k.v.y), x3 = bf16hi(k.v.y);
+  float x4 = bf16lo(k.v.z), x5 = bf16hi(k.v.z), x6 = bf16lo(k.v.w), x7 = bf16hi(k.v.w);
+  if (MODE == 1) {
+    x0 = act_rt(fmaf(k.sa.x, x0, k.ba.x), ap); x1 = act_rt(fmaf(k.sa.y, x1, k.ba.y), ap);
+    x2 = act_rt(fmaf(k.sa.z, x2, k.ba.z), ap); x3 = act_rt(fmaf(k.sa.w, x3, k.ba.w), ap);
+    x4 = act_rt(fmaf(k.sb.x, x4, k.bb.x), ap); x5 = act_rt(fmaf(k.sb.y, x5, k.bb.y), ap);
+    x6 = act_rt(fmaf(k.sb.z, x6, k.bb.z), ap); x7 = act_rt(fmaf(k.sb.w, x7, k.bb.w), ap);
+  } else {
+    x0 = fmaf(k.sa.x, x0, fmaf(k.ta.x, bf16lo(k.v2.x), k.ba.x));
+    x1 = fmaf(k.sa.y, x1, fmaf(k.ta.y, bf16hi(k.v2.x), k.ba.y));
+    x2 = fmaf(k.sa.z, x2, fmaf(k.ta.z, bf16lo(k.v2.y), k.ba.z));
+    x3 = fmaf(k.sa.w, x3, fmaf(k.ta.w, bf16hi(k.v2.y), k.ba.w));
+    x4 = fmaf(k.sb.x, x4, fmaf(k.tb.x, bf16lo(k.v2.z), k.bb.x));
+    x5 = fmaf(k.sb.y, x5, fmaf(k.tb.y, bf16hi(k.v2.z), k.bb.y));
+    x6 = fmaf(k.sb.z, x6, fmaf(k.tb.z, bf16lo(k.v2.w), k.bb.z));
+    x7 = fmaf(k.sb.w, x7, fmaf(k.tb.w, bf16hi(k.v2.w), k.bb.w));
+  }
+  sts128(k.addr, make_uint4(pack_bf16(x0, x1), pack_bf16(x2, x3), pack_bf16(x4, x5),
+                            pack_bf16(x6, x7)));
+}
+
 // In-place transform of one panel (R rows x 128 B, SWIZZLE_128B) by 128 threads.
-//   mode 1: v = act(s[c]*v + b[c])        mode 2: v = s[c]*v + s2[c]*v2 + b[c]
+//   MODE 1: v = act(s[c]*v + b[c])        MODE 2: v = s[c]*v + s2[c]*v2 + b[c]
 // `t` in [0,128).  Channel of (logical 16B chunk lc, element e) = cbase + lc*8 + e.
-__device__ __forceinline__ void xform_panel(uint8_t* panel, const uint8_t* panel2, int R, int t,
-                                            int mode, int act, const float* cs, const float* cb,
-                                            const float* cs2, int cbase, int C, int row_limit) {
+// All addresses are 32-bit shared-window addresses; tab_* point at fp32 tables indexed by channel.
+// Two chunks' loads are in flight before the first use.
+template <int R, int MODE>
+__device__ __forceinline__ void xform_panel_t(uint32_t panel, uint32_t panel2, int t,
+                                              const ActParam& ap, uint32_t tab_s, uint32_t tab_b,
+                                              uint32_t tab_s2, int cbase, int C, int row_limit) {
+  constexpr int PARTS = 128 / R;   // threads per row
+  constexpr int PER = 8 / PARTS;   // chunks per thread (8 or 4)
   const int row = t % R;
-  const int parts = 128 / R;  // threads per row
-  const int per = 8 / parts;
   const int part = t / R;
   if (row >= row_limit) return;
+  const uint32_t rbase = panel + row * 128;
+  const uint32_t rbase2 = panel2 + row * 128;
 #pragma unroll 1
-  for (int j = 0; j < per; ++j) {
-    const int lc = part * per + j;
-    const int c0 = cbase + lc * 8;
-    if (c0 >= C) continue;
-    const int off = row * 128 + ((lc ^ (row & 7)) << 4);
-    uint4 v = *reinterpret_cast<uint4*>(panel + off);
-    uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    if (mode == 1) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float lo = act_fwd(fmaf(cs[c0 + 2 * q], bf16lo(w[q]), cb[c0 + 2 * q]), act);
-        float hi = act_fwd(fmaf(cs[c0 + 2 * q + 1], bf16hi(w[q]), cb[c0 + 2 * q + 1]), act);
-        w[q] = pack_bf16(lo, hi);
-      }
-    } else {
-      uint4 v2 = *reinterpret_cast<const uint4*>(panel2 + off);
-      uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float lo = fmaf(cs[c0 + 2 * q], bf16lo(w[q]),
-                        fmaf(cs2[c0 + 2 * q], bf16lo(w2[q]), cb[c0 + 2 * q]));
-        float hi = fmaf(cs[c0 + 2 * q + 1], bf16hi(w[q]),
-                        fmaf(cs2[c0 + 2 * q + 1], bf16hi(w2[q]), cb[c0 + 2 * q + 1]));
-        w[q] = pack_bf16(lo, hi);
-      }
-    }
-    *reinterpret_cast<uint4*>(panel + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int j0 = 0; j0 < PER; j0 += 2) {
+    XChunk a, b;
+    xchunk_load<MODE>(a, rbase, rbase2, row, part * PER + j0, tab_s, tab_b, tab_s2, cbase, C);
+    xchunk_load<MODE>(b, rbase, rbase2, row, part * PER + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
+    xchunk_apply<MODE>(a, ap);
+    xchunk_apply<MODE>(b, ap);
   }
+}
+
+// Runtime mode -> compile-time specialisation; the branch is uniform per kernel.
+template <int R>
+__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int t, int mode,
+                                            int act, uint32_t tab_s, uint32_t tab_b,
+                                            uint32_t tab_s2, int cbase, int C, int row_limit) {
+  const ActParam ap = make_act(act);
+  if (mode == 2) xform_panel_t<R, 2>(panel, panel2, t, ap, tab_s, tab_b, tab_s2, cbase, C, row_limit);
+  else xform_panel_t<R, 1>(panel, panel2, t, ap, tab_s, tab_b, tab_s2, cbase, C, row_limit);
 }
 
 template <bool kXform>
@@ -173,7 +265,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_tx = (uint32_t)kABytes;
   const bool use_x = kXform && (p.a_xform != 0 || p.b_xform != 0);
 
-  if (warp == 0) {
+  // 512-thread variant: every thread starts with 128 registers; the control warpgroup hands its
+  // surplus to the two epilogue warpgroups (64*4 + 160*8 + 128*4 warps x 32 lanes = 64 Ki regs).
+  if (warp < 4) {
+   if (kXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0, phase = 0;
@@ -244,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, p.a_mn, p.b_mn);
     int stage = 0, phase = 0, it = 0;
@@ -278,8 +374,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+   }
+  } else if (warp < 4 + kEpiWarps) {
     // ======================================= epilogue =======================================
+    if (kXform) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     const int ew = warp - 4;           // 0..7
     const int wg = ew >> 2;            // epilogue warpgroup = TMEM accumulator stage it serves
     const int q = warp & 3;            // TMEM lane quadrant of this warp
@@ -497,34 +595,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->full[stage], phase);
-          uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
-          uint8_t* sB = sA + kABytes;
+          const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sB = sA + kABytes;
+          const uint32_t ta_s = smem_u32(xa), ta_b = smem_u32(xa + Ca), ta_s2 = smem_u32(xa + 2 * Ca);
+          const uint32_t tb_s = smem_u32(xb), tb_b = smem_u32(xb + Cb), tb_s2 = smem_u32(xb + 2 * Cb);
           if (p.a_xform) {
             if (!p.a_mn) {
-              xform_panel(sA, sA + p.a2_off, 128, t, p.a_xform, p.a_act, xa, xa + Ca, xa + 2 * Ca,
-                          kb * kBlockK, p.K, p.M - m_blk * kBlockM);
+              xform_panel<128>(sA, sA + p.a2_off, t, p.a_xform, p.a_act, ta_s, ta_b, ta_s2,
+                               kb * kBlockK, p.K, p.M - m_blk * kBlockM);
             } else {
               for (int q = 0; q < 2; ++q)
                 if (m_blk * kBlockM + q * 64 < p.M)
-                  xform_panel(sA + q * kPanelBytes64, sA + p.a2_off + q * kPanelBytes64, 64, t,
-                              p.a_xform, p.a_act, xa, xa + Ca, xa + 2 * Ca,
-                              m_blk * kBlockM + q * 64, p.M, p.K - kb * kBlockK);
+                  xform_panel<64>(sA + q * kPanelBytes64, sA + p.a2_off + q * kPanelBytes64, t,
+                                  p.a_xform, p.a_act, ta_s, ta_b, ta_s2, m_blk * kBlockM + q * 64,
+                                  p.M, p.K - kb * kBlockK);
             }
           }
           if (p.b_xform) {
             if (!p.b_mn) {
               // K-major B: rows are output channels; transform is along K
               for (int r0 = 0; r0 < p.block_n; r0 += 128)
-                xform_panel(sB + r0 * 128, sA + p.b2_off + r0 * 128, 128, t, p.b_xform, p.b_act, xb,
-                            xb + Cb, xb + 2 * Cb, kb * kBlockK, p.K,
-                            min(128, p.block_n - r0));
+                xform_panel<128>(sB + r0 * 128, sA + p.b2_off + r0 * 128, t, p.b_xform, p.b_act,
+                                 tb_s, tb_b, tb_s2, kb * kBlockK, p.K, min(128, p.block_n - r0));
             } else {
               const int b_panels = (p.block_n + 63) / 64;
               for (int q = 0; q < b_panels; ++q)
                 if (n_blk * p.block_n + q * 64 < p.N)
-                  xform_panel(sB + q * kPanelBytes64, sA + p.b2_off + q * kPanelBytes64, 64, t,
-                              p.b_xform, p.b_act, xb, xb + Cb, xb + 2 * Cb,
-                              n_blk * p.block_n + q * 64, p.N, p.K - kb * kBlockK);
+                  xform_panel<64>(sB + q * kPanelBytes64, sA + p.b2_off + q * kPanelBytes64, t,
+                                  p.b_xform, p.b_act, tb_s, tb_b, tb_s2,
+                                  n_blk * p.block_n + q * 64, p.N, p.K - kb * kBlockK);
             }
           }
           fence_proxy_async_smem();
