@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
     s_sh[i] = p.in_scale ? __ldg(p.in_shift + i) : 0.f;
   }
   for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
-  const int act = p.in_scale ? p.in_act : ACT_NONE;
+  const ActParam ap = make_act(p.in_scale ? p.in_act : ACT_NONE);
   const int cg = tid % NCG;
   const int strip = tid / NCG;
   const int sx = strip % G::TOW, sy = strip / G::TOW;
@@ -124,40 +124,49 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
     __syncthreads();  // previous tile's compute is done with s_tile (and the tables are written)
     // ---- stage the input tile: BN + activation applied once per element, halo / padding = 0 ----
-    // (4 independent global loads in flight per thread before the first use)
-    constexpr int NV = IH * IW * NCG;
+    // 16-byte (8-channel) vectors, two independent global loads in flight per thread
+    constexpr int V8 = CT / 8;              // vectors per pixel
+    constexpr int NV = IH * IW * V8;
+    const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc;
 #pragma unroll 1
-    for (int base = tid; base < NV; base += 4 * 256) {
-      uint2 raw[4];
-      int cc[4];
+    for (int base = tid; base < NV; base += 2 * 256) {
+      uint4 raw[2];
+      int cc[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int idx = base + u * 256;
-        const int pix = idx / NCG, g = idx % NCG;
+        const int pix = idx / V8, g = idx % V8;
         const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
-        const int c = cbase + g * 4;
+        const int c = cbase + g * 8;
         cc[u] = -1;
-        raw[u] = make_uint2(0u, 0u);
-        if (idx < NV && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W && c < p.C) {
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (idx < NV && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C) {
           cc[u] = c;
-          raw[u] = __ldg(reinterpret_cast<const uint2*>(
-              p.x + ((size_t)((size_t)n * p.H + iy) * p.W + ix) * p.ldc + c));
+          raw[u] = __ldg(reinterpret_cast<const uint4*>(img + (unsigned)((iy * p.W + ix) * p.ldc + c)));
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int idx = base + u * 256;
         if (idx >= NV) break;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
         if (cc[u] >= 0) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_sc + cc[u]);
-          const float4 sh = *reinterpret_cast<const float4*>(s_sh + cc[u]);
-          a.x = act_fwd(fmaf(sc.x, bf16lo(raw[u].x), sh.x), act);
-          a.y = act_fwd(fmaf(sc.y, bf16hi(raw[u].x), sh.y), act);
-          a.z = act_fwd(fmaf(sc.z, bf16lo(raw[u].y), sh.z), act);
-          a.w = act_fwd(fmaf(sc.w, bf16hi(raw[u].y), sh.w), act);
+          const float4 s0 = *reinterpret_cast<const float4*>(s_sc + cc[u]);
+          const float4 s1 = *reinterpret_cast<const float4*>(s_sc + cc[u] + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(s_sh + cc[u]);
+          const float4 h1 = *reinterpret_cast<const float4*>(s_sh + cc[u] + 4);
+          a0.x = act_rt(fmaf(s0.x, bf16lo(raw[u].x), h0.x), ap);
+          a0.y = act_rt(fmaf(s0.y, bf16hi(raw[u].x), h0.y), ap);
+          a0.z = act_rt(fmaf(s0.z, bf16lo(raw[u].y), h0.z), ap);
+          a0.w = act_rt(fmaf(s0.w, bf16hi(raw[u].y), h0.w), ap);
+          a1.x = act_rt(fmaf(s1.x, bf16lo(raw[u].z), h1.x), ap);
+          a1.y = act_rt(fmaf(s1.y, bf16hi(raw[u].z), h1.y), ap);
+          a1.z = act_rt(fmaf(s1.z, bf16lo(raw[u].w), h1.z), ap);
+          a1.w = act_rt(fmaf(s1.w, bf16hi(raw[u].w), h1.w), ap);
         }
-        *reinterpret_cast<float4*>(s_tile + (size_t)(idx / NCG) * CT + (idx % NCG) * 4) = a;
+        float* dst = s_tile + (idx / V8) * CT + (idx % V8) * 8;
+        *reinterpret_cast<float4*>(dst) = a0;
+        *reinterpret_cast<float4*>(dst + 4) = a1;
       }
     }
     __syncthreads();
@@ -286,6 +295,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
   }
   for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
   const int act = p.in_scale ? p.in_act : ACT_NONE;
+  const ActParam ap = make_act(act);
   const int cg = tid % NCG;
   const int pslot = tid / NCG;
   float gw[NT][4];
@@ -336,42 +346,54 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
     const int rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
     __syncthreads();
     // ---- stage dh = ca*dz + cb*h + cc over the gradient region (0 outside the image) ----
-    constexpr int NV = RMAX * RMAX * NCG;
+    // 16-byte (8-channel) vectors; 2 x 2 independent global loads in flight per thread
+    constexpr int V8 = CT / 8;
+    constexpr int NV = RMAX * RMAX * V8;
+    const size_t img_o = (size_t)n * p.Ho * p.Wo * p.ldc;
 #pragma unroll 1
     for (int base = tid; base < NV; base += 2 * 256) {
-      uint2 rdz[2], rh[2];
+      uint4 rdz[2], rh[2];
       int cc2[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int idx = base + u * 256;
-        const int pix = idx / NCG, g = idx % NCG;
+        const int pix = idx / V8, g = idx % V8;
         const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
-        const int c = cbase + g * 4;
+        const int c = cbase + g * 8;
         cc2[u] = -1;
-        rdz[u] = rh[u] = make_uint2(0u, 0u);
-        if (idx < NV && oy >= 0 && oy < p.Ho && ox >= 0 && ox < p.Wo && c < p.C) {
-          const size_t o = ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c;
+        rdz[u] = rh[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (idx < NV && (unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C) {
+          const size_t o = img_o + (unsigned)((oy * p.Wo + ox) * p.ldc + c);
           cc2[u] = c;
-          rdz[u] = __ldg(reinterpret_cast<const uint2*>(p.dz + o));
-          rh[u] = __ldg(reinterpret_cast<const uint2*>(p.h + o));
+          rdz[u] = __ldg(reinterpret_cast<const uint4*>(p.dz + o));
+          rh[u] = __ldg(reinterpret_cast<const uint4*>(p.h + o));
         }
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int idx = base + u * 256;
         if (idx >= NV) break;
-        float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
         if (cc2[u] >= 0) {
           const int c = cc2[u];
-          const float4 ca = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
-          const float4 cb = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
-          const float4 cc = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
-          dh.x = fmaf(ca.x, bf16lo(rdz[u].x), fmaf(cb.x, bf16lo(rh[u].x), cc.x));
-          dh.y = fmaf(ca.y, bf16hi(rdz[u].x), fmaf(cb.y, bf16hi(rh[u].x), cc.y));
-          dh.z = fmaf(ca.z, bf16lo(rdz[u].y), fmaf(cb.z, bf16lo(rh[u].y), cc.z));
-          dh.w = fmaf(ca.w, bf16hi(rdz[u].y), fmaf(cb.w, bf16hi(rh[u].y), cc.w));
+          const float4 ca0 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
+          const float4 ca1 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c + 4);
+          const float4 cb0 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
+          const float4 cb1 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c + 4);
+          const float4 cc0 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
+          const float4 cc1 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c + 4);
+          d0.x = fmaf(ca0.x, bf16lo(rdz[u].x), fmaf(cb0.x, bf16lo(rh[u].x), cc0.x));
+          d0.y = fmaf(ca0.y, bf16hi(rdz[u].x), fmaf(cb0.y, bf16hi(rh[u].x), cc0.y));
+          d0.z = fmaf(ca0.z, bf16lo(rdz[u].y), fmaf(cb0.z, bf16lo(rh[u].y), cc0.z));
+          d0.w = fmaf(ca0.w, bf16hi(rdz[u].y), fmaf(cb0.w, bf16hi(rh[u].y), cc0.w));
+          d1.x = fmaf(ca1.x, bf16lo(rdz[u].z), fmaf(cb1.x, bf16lo(rh[u].z), cc1.x));
+          d1.y = fmaf(ca1.y, bf16hi(rdz[u].z), fmaf(cb1.y, bf16hi(rh[u].z), cc1.y));
+          d1.z = fmaf(ca1.z, bf16lo(rdz[u].w), fmaf(cb1.z, bf16lo(rh[u].w), cc1.z));
+          d1.w = fmaf(ca1.w, bf16hi(rdz[u].w), fmaf(cb1.w, bf16hi(rh[u].w), cc1.w));
         }
-        *reinterpret_cast<float4*>(s_dh + (size_t)(idx / NCG) * CT + (idx % NCG) * 4) = dh;
+        float* dst = s_dh + (idx / V8) * CT + (idx % V8) * 8;
+        *reinterpret_cast<float4*>(dst) = d0;
+        *reinterpret_cast<float4*>(dst + 4) = d1;
       }
     }
     __syncthreads();
@@ -404,25 +426,24 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
                             fmaf(sc.z, xv[it][2], sh.z), fmaf(sc.w, xv[it][3], sh.w)};
         float a1[4], da[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int v = 0; v < 4; ++v) a1[v] = act_fwd(z[v], act);
+        for (int v = 0; v < 4; ++v) a1[v] = act_rt(z[v], ap);
+        // The staged region is zero outside the image and covers every tap of every pixel of the
+        // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
+        // parity test of the transposed convolution.
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
           const int yy = y + P - ky;
           if (S == 2 && (yy & 1)) continue;
           const int oy = S == 1 ? yy : yy >> 1;
-          if (yy < 0 || oy >= p.Ho) continue;
 #pragma unroll
           for (int kx = 0; kx < K; ++kx) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int tp = ky * K + kx;  // compile-time after unrolling
             if (!DGRAD && (tp < TAP0 || tp >= TAP1)) continue;
             const int xx = x + P - kx;
             if (S == 2 && (xx & 1)) continue;
             const int ox = S == 1 ? xx : xx >> 1;
-            if (xx < 0 || ox >= p.Wo) continue;
             const float4 dh = *reinterpret_cast<const float4*>(
-                s_dh + (size_t)((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
+                s_dh + ((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
             if (DGRAD) {
               const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
               da[0] = fmaf(dh.x, wv.x, da[0]);
@@ -440,7 +461,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
         }
         if (DGRAD) {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) da[v] *= act_bwd(z[v], act);
+          for (int v = 0; v < 4; ++v) da[v] *= act_bwd_rt(z[v], ap, act);
           const size_t off = ((size_t)((size_t)n * p.H + y) * p.W + x) * p.ldc + c0;
           if (p.residual) {
             float rv[4];
@@ -479,7 +500,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
 // ------------------------------------------------------------------------------------------------
 static int check_common(int N, int H, int W, int C, int ldc, int k, int stride) {
   if (N <= 0 || H <= 0 || W <= 0 || C <= 0) return set_error(YAMB_EINVAL, "depthwise: bad shape");
-  if (C % 4 || ldc % 4 || C > ldc) return set_error(YAMB_EINVAL, "depthwise: C=%d ldc=%d", C, ldc);
+  if (C % 8 || ldc % 8 || C > ldc) return set_error(YAMB_EINVAL, "depthwise: C=%d ldc=%d", C, ldc);
   if (k != 3 && k != 5 && k != 7) return set_error(YAMB_EINVAL, "depthwise: k=%d", k);
   if (stride != 1 && stride != 2) return set_error(YAMB_EINVAL, "depthwise: stride=%d", stride);
   if (C > 4096) return set_error(YAMB_EINVAL, "depthwise: C > 4096 per slice");
@@ -546,8 +567,8 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   p.w = a->w;
   p.has_bn = a->bn ? 1 : 0;
   if (a->bn) p.bn = *a->bn;
-  if ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 7)
-    return set_error(YAMB_EINVAL, "depthwise: activations must be 8-byte aligned");
+  if ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 15)
+    return set_error(YAMB_EINVAL, "depthwise: activations must be 16-byte aligned");
   const int toh = ct == 64 ? 8 : 16, tow = 8;
   p.tiles_h = (p.Ho + toh - 1) / toh;
   p.tiles_w = (p.Wo + tow - 1) / tow;

@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bn_finalize.cuh"
@@ -57,6 +58,7 @@ struct GemmDev {
   const __nv_bfloat16* side;  // residual (epi 0) or H (epi 1), row-major [M][lds]
   long long lds;
   int out_bufs;               // staging buffers per epilogue warp (1 or 2)
+  int dbg;                    // YAMB_GEMM_DEBUG bits: 1 skip transform math, 2 skip proxy fence
   yamb_bn_fwd bnf;
   int has_bnf;
   const float *h_scale, *h_shift;
@@ -136,25 +138,6 @@ __device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t 
     }
   }
 }
-// Activation as data: relu / relu6 / none are clamp(z, lo, hi); swish / h-swish take the uniform
-// slow branch.  Keeps ONE copy of the transform per (R, MODE) instead of one per activation.
-struct ActParam {
-  float lo, hi;
-  int kind;  // 0: clamp only, ACT_SWISH, ACT_HSWISH
-};
-__device__ __forceinline__ ActParam make_act(int act) {
-  ActParam a;
-  a.lo = (act == ACT_RELU || act == ACT_RELU6) ? 0.f : -3.0e38f;
-  a.hi = (act == ACT_RELU6) ? 6.f : 3.0e38f;
-  a.kind = (act == ACT_SWISH || act == ACT_HSWISH) ? act : 0;
-  return a;
-}
-__device__ __forceinline__ float act_rt(float z, const ActParam& a) {
-  if (a.kind == 0) return fminf(fmaxf(z, a.lo), a.hi);
-  if (a.kind == ACT_SWISH) return z / (1.f + __expf(-z));
-  return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
-}
-
 template <int MODE>
 __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap) {
   if (!k.ok) return;
@@ -179,40 +162,37 @@ __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap
                             pack_bf16(x6, x7)));
 }
 
-// In-place transform of one panel (R rows x 128 B, SWIZZLE_128B) by 128 threads.
-//   MODE 1: v = act(s[c]*v + b[c])        MODE 2: v = s[c]*v + s2[c]*v2 + b[c]
+// In-place transform of one panel (R = 64 or 128 rows x 128 B, SWIZZLE_128B) by 128 threads.
+//   mode 1: v = act(s[c]*v + b[c])        mode 2: v = s[c]*v + s2[c]*v2 + b[c]
 // `t` in [0,128).  Channel of (logical 16B chunk lc, element e) = cbase + lc*8 + e.
 // All addresses are 32-bit shared-window addresses; tab_* point at fp32 tables indexed by channel.
-// Two chunks' loads are in flight before the first use.
-template <int R, int MODE>
-__device__ __forceinline__ void xform_panel_t(uint32_t panel, uint32_t panel2, int t,
-                                              const ActParam& ap, uint32_t tab_s, uint32_t tab_b,
-                                              uint32_t tab_s2, int cbase, int C, int row_limit) {
-  constexpr int PARTS = 128 / R;   // threads per row
-  constexpr int PER = 8 / PARTS;   // chunks per thread (8 or 4)
-  const int row = t % R;
-  const int part = t / R;
+// ONE copy of this code exists in the kernel (single call site, runtime R / mode): two chunks'
+// loads are in flight before the first use.
+__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int logR, int t,
+                                            int mode, const ActParam& ap, uint32_t tab_s,
+                                            uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
+                                            int row_limit) {
+  const int row = t & ((1 << logR) - 1);
+  const int part = t >> logR;          // 0 (R=128) or 0..1 (R=64)
+  const int per = 1 << (logR - 4);     // chunks per thread: 8 (R=128) or 4 (R=64)
   if (row >= row_limit) return;
   const uint32_t rbase = panel + row * 128;
   const uint32_t rbase2 = panel2 + row * 128;
 #pragma unroll 1
-  for (int j0 = 0; j0 < PER; j0 += 2) {
+  for (int j0 = 0; j0 < per; j0 += 2) {
     XChunk a, b;
-    xchunk_load<MODE>(a, rbase, rbase2, row, part * PER + j0, tab_s, tab_b, tab_s2, cbase, C);
-    xchunk_load<MODE>(b, rbase, rbase2, row, part * PER + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
-    xchunk_apply<MODE>(a, ap);
-    xchunk_apply<MODE>(b, ap);
+    if (mode == 2) {
+      xchunk_load<2>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C);
+      xchunk_load<2>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
+      xchunk_apply<2>(a, ap);
+      xchunk_apply<2>(b, ap);
+    } else {
+      xchunk_load<1>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C);
+      xchunk_load<1>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
+      xchunk_apply<1>(a, ap);
+      xchunk_apply<1>(b, ap);
+    }
   }
-}
-
-// Runtime mode -> compile-time specialisation; the branch is uniform per kernel.
-template <int R>
-__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int t, int mode,
-                                            int act, uint32_t tab_s, uint32_t tab_b,
-                                            uint32_t tab_s2, int cbase, int C, int row_limit) {
-  const ActParam ap = make_act(act);
-  if (mode == 2) xform_panel_t<R, 2>(panel, panel2, t, ap, tab_s, tab_b, tab_s2, cbase, C, row_limit);
-  else xform_panel_t<R, 1>(panel, panel2, t, ap, tab_s, tab_b, tab_s2, cbase, C, row_limit);
 }
 
 template <bool kXform>
@@ -587,6 +567,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         xb[2 * Cb + i] = p.b_xform == 2 ? p.b_scale2[i] : 0.f;
       }
       named_bar_sync(2, 128);
+      const ActParam apa = make_act(p.a_xform == 1 ? p.a_act : ACT_NONE);
+      const ActParam apb = make_act(p.b_xform == 1 ? p.b_act : ACT_NONE);
       int stage = 0, phase = 0;
       for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
         const int mn = w / p.ksplit, slab = w % p.ksplit;
@@ -597,36 +579,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&bars->full[stage], phase);
           const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t sB = sA + kABytes;
-          const uint32_t ta_s = smem_u32(xa), ta_b = smem_u32(xa + Ca), ta_s2 = smem_u32(xa + 2 * Ca);
-          const uint32_t tb_s = smem_u32(xb), tb_b = smem_u32(xb + Cb), tb_s2 = smem_u32(xb + 2 * Cb);
-          if (p.a_xform) {
-            if (!p.a_mn) {
-              xform_panel<128>(sA, sA + p.a2_off, t, p.a_xform, p.a_act, ta_s, ta_b, ta_s2,
-                               kb * kBlockK, p.K, p.M - m_blk * kBlockM);
-            } else {
-              for (int q = 0; q < 2; ++q)
-                if (m_blk * kBlockM + q * 64 < p.M)
-                  xform_panel<64>(sA + q * kPanelBytes64, sA + p.a2_off + q * kPanelBytes64, t,
-                                  p.a_xform, p.a_act, ta_s, ta_b, ta_s2, m_blk * kBlockM + q * 64,
-                                  p.M, p.K - kb * kBlockK);
+          // panels of this stage: A (1 K-major / 2 MN-major) then B (ceil(block_n/128) K-major /
+          // ceil(block_n/64) MN-major); one loop, one call site
+          const int na = p.a_xform ? (p.a_mn ? 2 : 1) : 0;
+          const int nb = p.b_xform ? (p.b_mn ? (p.block_n + 63) / 64 : (p.block_n + 127) / 128) : 0;
+          if (!(p.dbg & 1)) {
+#pragma unroll 1
+            for (int pi = 0; pi < na + nb; ++pi) {
+              const bool isA = pi < na;
+              const int q = isA ? pi : pi - na;
+              const bool mn = isA ? p.a_mn : p.b_mn;
+              const uint32_t opbase = isA ? sA : sB;
+              const uint32_t op2 = sA + (isA ? p.a2_off : p.b2_off);
+              const uint32_t poff = (uint32_t)q * (mn ? kPanelBytes64 : 128 * 128);
+              const int mode = isA ? p.a_xform : p.b_xform;
+              const ActParam& ap = isA ? apa : apb;
+              const float* tab = isA ? xa : xb;
+              const int Ct = isA ? Ca : Cb;
+              const uint32_t t_s = smem_u32(tab), t_b = smem_u32(tab + Ct), t_s2 = smem_u32(tab + 2 * Ct);
+              int cbase, climit, rlimit;
+              if (!mn) {  // K-major: channels along K, rows are M (A) or N (B)
+                cbase = kb * kBlockK; climit = p.K;
+                rlimit = isA ? p.M - m_blk * kBlockM : min(128, p.block_n - q * 128);
+              } else {    // MN-major: channels along M/N (64 per panel), rows are K (pixels)
+                const int c0p = (isA ? m_blk * kBlockM : n_blk * p.block_n) + q * 64;
+                cbase = c0p; climit = isA ? p.M : p.N;
+                rlimit = (c0p < climit) ? p.K - kb * kBlockK : 0;
+              }
+              xform_panel(opbase + poff, op2 + poff, mn ? 6 : 7, t, mode, ap, t_s, t_b, t_s2, cbase,
+                          climit, rlimit);
             }
           }
-          if (p.b_xform) {
-            if (!p.b_mn) {
-              // K-major B: rows are output channels; transform is along K
-              for (int r0 = 0; r0 < p.block_n; r0 += 128)
-                xform_panel<128>(sB + r0 * 128, sA + p.b2_off + r0 * 128, t, p.b_xform, p.b_act,
-                                 tb_s, tb_b, tb_s2, kb * kBlockK, p.K, min(128, p.block_n - r0));
-            } else {
-              const int b_panels = (p.block_n + 63) / 64;
-              for (int q = 0; q < b_panels; ++q)
-                if (n_blk * p.block_n + q * 64 < p.N)
-                  xform_panel<64>(sB + q * kPanelBytes64, sA + p.b2_off + q * kPanelBytes64, t,
-                                  p.b_xform, p.b_act, tb_s, tb_b, tb_s2,
-                                  n_blk * p.block_n + q * 64, p.N, p.K - kb * kBlockK);
-            }
-          }
-          fence_proxy_async_smem();
+          if (!(p.dbg & 2)) fence_proxy_async_smem();
           mbar_arrive(&bars->xdone[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -717,6 +701,7 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   if ((p.a_xform == 2 && (!a->A2 || !a->a_scale2)) || (p.b_xform == 2 && (!a->B2 || !a->b_scale2)))
     return set_error(YAMB_EINVAL, "two-source transform without second tensor");
   p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
+  { const char* d = getenv("YAMB_GEMM_DEBUG"); p.dbg = d ? atoi(d) : 0; }
   p.D = a->D; p.ldd = a->ldd;
   if (a->epi == 0 && a->bn_fwd) { p.bnf = *a->bn_fwd; p.has_bnf = 1; }
   if (a->epi == 1) {

@@ -235,6 +235,29 @@ __device__ __forceinline__ float act_bwd(float z, int act) {
     default: return 1.f;
   }
 }
+// Activation as data: relu / relu6 / none are clamp(z, lo, hi) — two instructions, no branch;
+// swish / h-swish take a (warp-uniform) slow branch.
+struct ActParam {
+  float lo, hi;
+  int kind;  // 0: clamp only, else ACT_SWISH / ACT_HSWISH
+};
+__device__ __forceinline__ ActParam make_act(int act) {
+  ActParam a;
+  a.lo = (act == ACT_RELU || act == ACT_RELU6) ? 0.f : -3.0e38f;
+  a.hi = (act == ACT_RELU6) ? 6.f : 3.0e38f;
+  a.kind = (act == ACT_SWISH || act == ACT_HSWISH) ? act : 0;
+  return a;
+}
+__device__ __forceinline__ float act_rt(float z, const ActParam& a) {
+  if (a.kind == 0) return fminf(fmaxf(z, a.lo), a.hi);
+  if (a.kind == ACT_SWISH) return z / (1.f + __expf(-z));
+  return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
+}
+// d act / dz for the clamp family: 1 strictly inside (lo, hi), else 0
+__device__ __forceinline__ float act_bwd_rt(float z, const ActParam& a, int act) {
+  if (a.kind == 0) return (z > a.lo && z < a.hi) ? 1.f : 0.f;
+  return act_bwd(z, act);
+}
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
