@@ -123,6 +123,9 @@ typedef struct yamb_gemm {
   const float* h_scale; const float* h_shift; int32_t h_act;
   const yamb_bn_bwd* bn_bwd;           /* epi 1 */
   int32_t max_ctas;                    /* 0 = one CTA per SM */
+  /* optional per-(sample, channel) gate applied after an xform=1 transform (SE: x * gate[n][c]);
+   * the operand's rows must be pixels (A K-major, or A/B MN-major): n = pixel / rows_per_sample */
+  const float* a_gate; const float* b_gate; int64_t gate_rows_per_sample;
 } yamb_gemm;
 
 int yamb_pointwise_gemm(const yamb_gemm* args, yamb_stream_t stream);
@@ -186,7 +189,28 @@ typedef struct yamb_se_pool {
   float* pooled;
 } yamb_se_pool;
 
+/* Squeeze-and-Excitation backward pieces (autograd of reference models/mobilenet_base.py:110-113,
+ * y = x * gate, gate = sigmoid(W_e act(W_r mean_HW(x) + b_r) + b_e), x = act(scale*h+shift)):
+ *   se_bwd_reduce: dgate[n][c] = sum_HW dY * x
+ *   se_bwd_apply : dz = (dY*gate[n][c] + dpool[n][c]) * act'(scale*h+shift)  (+ BN-bwd statistics);
+ *                  dpool = (d mean)/HW comes from the host-side tiny FC backward. */
+typedef struct yamb_se_bwd_reduce {
+  int32_t N, HW, C, ldd, ldh;
+  const void* dy; const void* h; const float* scale; const float* shift; int32_t act;
+  float* dgate;
+} yamb_se_bwd_reduce;
+
+typedef struct yamb_se_bwd_apply {
+  int64_t M; int32_t C, ldd, ldh, ldz; int64_t rows_per_sample;
+  const void* dy; const void* h; const float* scale; const float* shift; int32_t act;
+  const float* gate; const float* dpool; int32_t ldg; /* row pitch of gate / dpool */
+  void* dz;
+  const yamb_bn_bwd* bn;
+} yamb_se_bwd_apply;
+
 int yamb_bn_apply_fwd(const yamb_bn_apply* args, yamb_stream_t stream);
+int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* args, yamb_stream_t stream);
+int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* args, yamb_stream_t stream);
 int yamb_bn_reduce_bwd(const yamb_bn_reduce* args, yamb_stream_t stream);
 int yamb_se_pool_fwd(const yamb_se_pool* args, yamb_stream_t stream);
 
@@ -217,7 +241,7 @@ int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t stream)
 int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
- * 6 bn_reduce, 7 se_pool, 8 rmsprop) so bindings can self-check */
+ * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

@@ -248,6 +248,7 @@ def backward(dy, cfg, P, S, training=True, quant=False):
     G["w_proj"] = torch.einsum("nohw,nchw->oc", dh3, a2_in)
     da2 = torch.einsum("nohw,oc->nchw", dh3, wp)
     if cfg.se_hidden:
+        da2 = _rnd(da2, q)  # the CUDA path materialises d(a2*gate) in bf16 before the SE backward
         gate, a2 = S["se_gate"], S["a2"]
         hw = a2.shape[2] * a2.shape[3]
         dgate = (da2 * a2).sum((2, 3))

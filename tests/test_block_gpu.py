@@ -41,7 +41,7 @@ def _cases():
 
 
 GOLD = _cases()
-SUPPORTED = [k for k, v in GOLD.items() if not v["extra"].get("se_ratio")]
+SUPPORTED = list(GOLD)
 
 
 @pytest.mark.parametrize("name", SUPPORTED)
@@ -111,6 +111,12 @@ def test_block_vs_golden_and_oracle(built_lib, name, mode):
     assert _rel(torch.cat([d[1].bias.grad for d in dws]), G["bn2_b"]) < 1.5e-2
     assert _rel(bn3.weight.grad, G["bn3_g"]) < 1.5e-2
     assert _rel(bn3.bias.grad, G["bn3_b"]) < 1.5e-2
+    if "se_wr" in G:
+        se = blk.se_op
+        assert _rel(se.se_reduce.weight.grad.flatten(1), G["se_wr"]) < 1.5e-2
+        assert _rel(se.se_reduce.bias.grad, G["se_br"]) < 1.5e-2
+        assert _rel(se.se_expand.weight.grad.flatten(1), G["se_we"]) < 1.5e-2
+        assert _rel(se.se_expand.bias.grad, G["se_be"]) < 1.5e-2
 
 
 def test_block_rejects_cpu_input(built_lib):

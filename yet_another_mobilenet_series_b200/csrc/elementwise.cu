@@ -166,6 +166,126 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ Se
   }
 }
 
+// dgate[n][c] = sum over HW of dY[n,hw,c] * round_bf16(act(scale*h + shift))  (SE backward, the
+// gradient of x*gate w.r.t. gate; reference models/mobilenet_base.py:113 via autograd)
+struct SeBwdReduceDev {
+  int N, HW, C, ldd, ldh;
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* h;
+  const float *scale, *shift;
+  int act;
+  float* dgate;  // [N][C]
+};
+__global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const __grid_constant__ SeBwdReduceDev p) {
+  const int n = blockIdx.x;
+  const int cg = blockIdx.y * 32 + (threadIdx.x & 31);
+  const int pl = threadIdx.x >> 5;
+  __shared__ float red[8][32][8];
+  float s[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = 0.f;
+  const bool ok = cg * 8 < p.C;
+  if (ok) {
+    const int c0 = cg * 8;
+    const ActParam ap = make_act(p.act);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
+    for (int i = pl; i < p.HW; i += 8) {
+      float v[8], d[8];
+      const size_t row = (size_t)n * p.HW + i;
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), v);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ldd + c0)), d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = fmaf(d[e], round_bf16(act_rt(fmaf(sc[e], v[e], sh[e]), ap)), s[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[pl][threadIdx.x & 31][e] = s[e];
+  __syncthreads();
+  if (pl == 0 && ok) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x & 31][e];
+      p.dgate[(size_t)n * p.C + cg * 8 + e] = t;
+    }
+  }
+}
+
+// dz = (dY * gate[n][c] + dpool[n][c]) * act'(scale*h + shift)   (in place allowed: dz == dY)
+// + BatchNorm-backward statistics sum(dz), sum(dz*xhat) and finalize (last CTA).
+struct SeBwdApplyDev {
+  long long M;
+  int C, ldd, ldh, ldz;
+  long long rows_per_sample;
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* h;
+  const float *scale, *shift;
+  int act;
+  const float* gate;   // [N][C]
+  const float* dpool;  // [N][C]  (already divided by HW)
+  int ldg;             // row pitch of gate / dpool
+  __nv_bfloat16* dz;
+  yamb_bn_bwd bn;
+};
+__global__ void __launch_bounds__(256) se_bwd_apply_kernel(const __grid_constant__ SeBwdApplyDev p) {
+  extern __shared__ float s_part[];  // [2][C]
+  const int CG = p.C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  const ActParam ap = make_act(p.act);
+  for (int cgb = 0; cgb < CG; cgb += 256) {
+    const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
+    const int px = CG >= 256 ? 0 : threadIdx.x / CG;
+    if (cg < CG && px < PX) {
+      const int c0 = cg * 8;
+      float sc[8], sh[8], mu[8], rs[8], s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e);
+        mu[e] = __ldg(p.bn.mean + c0 + e); rs[e] = __ldg(p.bn.invstd + c0 + e);
+        s[e] = q[e] = 0.f;
+      }
+      for (long long row = (long long)blockIdx.x * PX + px; row < p.M;
+           row += (long long)gridDim.x * PX) {
+        const long long n = row / p.rows_per_sample;
+        float d[8], hv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ldd + c0)), d);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
+        const float* g = p.gate + n * p.ldg + c0;
+        const float* dp = p.dpool + n * p.ldg + c0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaf(sc[e], hv[e], sh[e]);
+          d[e] = fmaf(d[e], __ldg(g + e), __ldg(dp + e)) * act_bwd_rt(z, ap, p.act);
+        }
+        const uint4 o = pack8(d);
+        *reinterpret_cast<uint4*>(p.dz + row * p.ldz + c0) = o;
+        float r[8];
+        unpack8(o, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e] += r[e];
+          q[e] = fmaf(r[e], (hv[e] - mu[e]) * rs[e], q[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_part[c0 + e], s[e]);
+        atomicAdd(&s_part[p.C + c0 + e], q[e]);
+      }
+    }
+  }
+  __syncthreads();
+  if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
+    bn_bwd_finalize(p.bn, p.C, gridDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) *p.bn.counter = 0;
+  }
+}
+
 int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t st) {
   if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8)) return set_error(YAMB_EINVAL, "bn_apply shape");
   if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
@@ -212,6 +332,42 @@ int se_pool_launch(const yamb_se_pool* a, cudaStream_t st) {
   se_pool_kernel<<<grid, 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t st) {
+  if (!a || a->N <= 0 || a->HW <= 0 || a->C <= 0 || (a->C % 8))
+    return set_error(YAMB_EINVAL, "se_bwd_reduce shape");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  SeBwdReduceDev p;
+  p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldd = a->ldd; p.ldh = a->ldh;
+  p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
+  p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dgate = a->dgate;
+  dim3 grid(a->N, (a->C / 8 + 31) / 32);
+  se_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_reduce: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t st) {
+  if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8) || !a->bn || a->rows_per_sample <= 0)
+    return set_error(YAMB_EINVAL, "se_bwd_apply shape");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  SeBwdApplyDev p;
+  p.M = a->M; p.C = a->C; p.ldd = a->ldd; p.ldh = a->ldh; p.ldz = a->ldz;
+  p.rows_per_sample = a->rows_per_sample;
+  p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
+  p.scale = a->scale; p.shift = a->shift; p.act = a->act;
+  p.gate = a->gate; p.dpool = a->dpool; p.ldg = a->ldg > 0 ? a->ldg : a->C;
+  p.dz = (__nv_bfloat16*)a->dz; p.bn = *a->bn;
+  const int CG = a->C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  long long want = (a->M + PX - 1) / PX;
+  int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
+  se_bwd_apply_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_apply: %s", cudaGetErrorString(e));
   return 0;
 }
 

@@ -58,6 +58,8 @@ struct GemmDev {
   const __nv_bfloat16* side;  // residual (epi 0) or H (epi 1), row-major [M][lds]
   long long lds;
   int out_bufs;               // staging buffers per epilogue warp (1 or 2)
+  const float *a_gate, *b_gate;  // optional per-(sample, channel) gates [n][C] (SE)
+  long long gate_rps;            // pixels per sample
   int dbg;                    // YAMB_GEMM_DEBUG bits: 1 skip transform math, 2 skip proxy fence
   yamb_bn_fwd bnf;
   int has_bnf;
@@ -113,14 +115,15 @@ __device__ __forceinline__ float act_c(float z) {
 // One 16-byte chunk (8 channels) of one row of a panel: loads first, math later.
 struct XChunk {
   uint4 v, v2;
-  float4 sa, sb, ba, bb, ta, tb;
+  float4 sa, sb, ba, bb, ta, tb;  // ta/tb: second-source scale (mode 2) or the SE gate (mode 1)
   uint32_t addr;
   bool ok;
 };
 template <int MODE>
 __device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t rbase2, int row,
                                             int lc, uint32_t tab_s, uint32_t tab_b,
-                                            uint32_t tab_s2, int cbase, int C) {
+                                            uint32_t tab_s2, int cbase, int C,
+                                            const float* gate_row) {
   const int c0 = cbase + lc * 8;
   k.ok = c0 < C;
   const uint32_t off = (uint32_t)((lc ^ (row & 7)) << 4);
@@ -135,11 +138,14 @@ __device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t 
     if (MODE == 2) {
       k.ta = lds128f(tab_s2 + c0 * 4);
       k.tb = lds128f(tab_s2 + c0 * 4 + 16);
+    } else if (gate_row != nullptr) {
+      k.ta = __ldg(reinterpret_cast<const float4*>(gate_row + c0));
+      k.tb = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + 4));
     }
   }
 }
 template <int MODE>
-__device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap) {
+__device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap, bool gated) {
   if (!k.ok) return;
   float x0 = bf16lo(k.v.x), x1 = bf16hi(k.v.x), x2 = bf16lo(k.v.y), x3 = bf16hi(k.v.y);
   float x4 = bf16lo(k.v.z), x5 = bf16hi(k.v.z), x6 = bf16lo(k.v.w), x7 = bf16hi(k.v.w);
@@ -148,6 +154,12 @@ __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap
     x2 = act_rt(fmaf(k.sa.z, x2, k.ba.z), ap); x3 = act_rt(fmaf(k.sa.w, x3, k.ba.w), ap);
     x4 = act_rt(fmaf(k.sb.x, x4, k.bb.x), ap); x5 = act_rt(fmaf(k.sb.y, x5, k.bb.y), ap);
     x6 = act_rt(fmaf(k.sb.z, x6, k.bb.z), ap); x7 = act_rt(fmaf(k.sb.w, x7, k.bb.w), ap);
+    if (gated) {  // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
+      x0 = round_bf16(x0) * k.ta.x; x1 = round_bf16(x1) * k.ta.y;
+      x2 = round_bf16(x2) * k.ta.z; x3 = round_bf16(x3) * k.ta.w;
+      x4 = round_bf16(x4) * k.tb.x; x5 = round_bf16(x5) * k.tb.y;
+      x6 = round_bf16(x6) * k.tb.z; x7 = round_bf16(x7) * k.tb.w;
+    }
   } else {
     x0 = fmaf(k.sa.x, x0, fmaf(k.ta.x, bf16lo(k.v2.x), k.ba.x));
     x1 = fmaf(k.sa.y, x1, fmaf(k.ta.y, bf16hi(k.v2.x), k.ba.y));
@@ -171,26 +183,30 @@ __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap
 __device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int logR, int t,
                                             int mode, const ActParam& ap, uint32_t tab_s,
                                             uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
-                                            int row_limit) {
+                                            int row_limit, const float* gate, long long pixbase,
+                                            long long rps) {
   const int row = t & ((1 << logR) - 1);
   const int part = t >> logR;          // 0 (R=128) or 0..1 (R=64)
   const int per = 1 << (logR - 4);     // chunks per thread: 8 (R=128) or 4 (R=64)
   if (row >= row_limit) return;
   const uint32_t rbase = panel + row * 128;
   const uint32_t rbase2 = panel2 + row * 128;
+  const float* grow = gate ? gate + ((pixbase + row) / rps) * C : nullptr;
 #pragma unroll 1
   for (int j0 = 0; j0 < per; j0 += 2) {
     XChunk a, b;
     if (mode == 2) {
-      xchunk_load<2>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C);
-      xchunk_load<2>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
-      xchunk_apply<2>(a, ap);
-      xchunk_apply<2>(b, ap);
+      xchunk_load<2>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C, nullptr);
+      xchunk_load<2>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C,
+                     nullptr);
+      xchunk_apply<2>(a, ap, false);
+      xchunk_apply<2>(b, ap, false);
     } else {
-      xchunk_load<1>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C);
-      xchunk_load<1>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C);
-      xchunk_apply<1>(a, ap);
-      xchunk_apply<1>(b, ap);
+      xchunk_load<1>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C, grow);
+      xchunk_load<1>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C,
+                     grow);
+      xchunk_apply<1>(a, ap, grow != nullptr);
+      xchunk_apply<1>(b, ap, grow != nullptr);
     }
   }
 }
@@ -200,9 +216,11 @@ __global__ void __launch_bounds__(kXform ? 512 : 384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (SWIZZLE_128B atoms) comes from the declaration, not from pointer
+  // arithmetic, so the compiler keeps every access in the shared address space (LDS/STS, not
+  // generic LD/ST).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
   Bars* bars = reinterpret_cast<Bars*>(smem + p.off_bars);
   float* s_stats = reinterpret_cast<float*>(smem + p.off_stats);  // [2][N]
   float* s_coef = reinterpret_cast<float*>(smem + p.off_coef);
@@ -381,6 +399,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     uint32_t sub_count = 0;   // running sub-tile counter of this warp -> staging buffer parity
     const bool side_in = (p.epi == 1) || p.has_residual;
+    const ActParam hap = make_act(p.epi == 1 ? p.h_act : ACT_NONE);
     // Column statistics: with a single n-block every lane owns the same 2 columns of sub-tile j in
     // every tile, so the sums live in registers for the whole kernel (shared-memory float atomics
     // are CAS loops and serialise the 8 epilogue warps); flushed once at the end.
@@ -469,13 +488,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               const int cb = col0 + ch * 8;
               if (cb < p.N) {
+                const float4 s0 = *reinterpret_cast<const float4*>(cz_s + cb);
+                const float4 s1 = *reinterpret_cast<const float4*>(cz_s + cb + 4);
+                const float4 t0 = *reinterpret_cast<const float4*>(cz_t + cb);
+                const float4 t1 = *reinterpret_cast<const float4*>(cz_t + cb + 4);
+                const float zs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float zt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float h0 = bf16lo(sw[e]), h1 = bf16hi(sw[e]);
-                  const float z0 = fmaf(cz_s[cb + 2 * e], h0, cz_t[cb + 2 * e]);
-                  const float z1 = fmaf(cz_s[cb + 2 * e + 1], h1, cz_t[cb + 2 * e + 1]);
-                  v[2 * e] *= act_bwd(z0, p.h_act);
-                  v[2 * e + 1] *= act_bwd(z1, p.h_act);
+                  const float z0 = fmaf(zs[2 * e], bf16lo(sw[e]), zt[2 * e]);
+                  const float z1 = fmaf(zs[2 * e + 1], bf16hi(sw[e]), zt[2 * e + 1]);
+                  v[2 * e] *= act_bwd_rt(z0, hap, p.h_act);
+                  v[2 * e + 1] *= act_bwd_rt(z1, hap, p.h_act);
                 }
               }
               *reinterpret_cast<uint4*>(s_h + lane * 128 + (pc << 4)) = sv[ch];
@@ -606,8 +630,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 cbase = c0p; climit = isA ? p.M : p.N;
                 rlimit = (c0p < climit) ? p.K - kb * kBlockK : 0;
               }
+              // rows of a K-major A tile are pixels m; rows of an MN-major tile are pixels k
+              const long long pixbase = mn ? (long long)kb * kBlockK : (long long)m_blk * kBlockM;
+              const float* gate = (mode == 1 && (mn || isA)) ? (isA ? p.a_gate : p.b_gate) : nullptr;
               xform_panel(opbase + poff, op2 + poff, mn ? 6 : 7, t, mode, ap, t_s, t_b, t_s2, cbase,
-                          climit, rlimit);
+                          climit, rlimit, gate, pixbase, p.gate_rps);
             }
           }
           if (!(p.dbg & 2)) fence_proxy_async_smem();
@@ -702,6 +729,12 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     return set_error(YAMB_EINVAL, "two-source transform without second tensor");
   p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
   { const char* d = getenv("YAMB_GEMM_DEBUG"); p.dbg = d ? atoi(d) : 0; }
+  p.a_gate = a->a_xform == 1 ? a->a_gate : nullptr;
+  p.b_gate = a->b_xform == 1 ? a->b_gate : nullptr;
+  p.gate_rps = a->gate_rows_per_sample > 0 ? a->gate_rows_per_sample : 1;
+  if ((p.a_gate || p.b_gate) && a->gate_rows_per_sample <= 0)
+    return set_error(YAMB_EINVAL, "gate without gate_rows_per_sample");
+  if (p.b_gate && !p.b_mn) return set_error(YAMB_EINVAL, "b_gate needs an MN-major B (rows = pixels)");
   p.D = a->D; p.ldd = a->ldd;
   if (a->epi == 0 && a->bn_fwd) { p.bnf = *a->bn_fwd; p.has_bnf = 1; }
   if (a->epi == 1) {
@@ -740,7 +773,7 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   const int side_bytes = (a->epi == 1) ? kEpiWarps * kWarpOutBytes : 0;  // raw H rows (epi 1)
   const int coef_bytes = ((a->epi == 1 ? 4 * p.N : 0) + 3 * Ca + 3 * Cb) * 4;
   const int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * 4 : 0;
-  const int budget = 232448 - 1024;  // 227 KB minus alignment slack
+  const int budget = 232448 - 2048;  // 227 KB minus the kernel's static shared memory
   int stages = 0, out_bytes = 0;
   for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
     out_bytes = (a->epi == 2) ? 0 : p.out_bufs * kEpiWarps * kWarpOutBytes;
@@ -758,7 +791,7 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   p.off_coef = off; off += (coef_bytes + 15) & ~15;
   p.off_stats = off; off += (stats_bytes + 15) & ~15;
   p.off_bars = (off + 15) & ~15; off = p.off_bars + (int)sizeof(Bars);
-  const int smem_total = off + 1024;
+  const int smem_total = off;  // the extern array is declared 1024-aligned: no slack needed
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB, tmA2, tmB2, tmD;

@@ -22,6 +22,8 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t stream);
 int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t stream);
 int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t stream);
 int se_pool_launch(const yamb_se_pool* a, cudaStream_t stream);
+int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t stream);
+int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t stream);
 int rmsprop_launch(const yamb_rmsprop* a, cudaStream_t stream);
 int ema_launch(float* shadow, const float* x, long long n, const float* hyper, float m,
                cudaStream_t stream);

@@ -187,8 +187,7 @@ class BlockPlan:
             dws = [list(op.children())[-1] for op in block.depth_ops]
             self.conv_proj = [block.project_conv[0]]
             bn3 = block.project_conv[1]
-            if type(block.se_op).__name__ != "Identity":
-                raise nat.NativeError("Squeeze-and-Excitation is not yet on the sm_100a path")
+            self.se = block.se_op if type(block.se_op).__name__ != "Identity" else None
             if type(block.nl_op).__name__ != "Identity":
                 raise nat.NativeError("Nonlocal is not yet on the sm_100a path")
         else:
@@ -202,6 +201,14 @@ class BlockPlan:
                 dws = [op[0] for op in block.ops]
                 self.conv_proj = [op[1] for op in block.ops]
             bn3 = block.pw_bn
+        if not self.fused:
+            self.se = None
+        if self.se is not None:
+            self.se_act = act_code_of(self.se.active_fn)
+            self.pooled = _f32(N * Chid, dev).view(N, Chid)
+            self.gate = _f32(N * Chid, dev).view(N, Chid)
+            self.dgate = _f32(N * Chid, dev).view(N, Chid)
+            self.dpool = _f32(N * Chid, dev).view(N, Chid)
         self.conv_dw = [d[0] for d in dws]
         self.bn1 = _Bn(bn1, dev) if self.expand else None
         self.bn2 = _Bn([d[1] for d in dws], dev)
@@ -360,6 +367,23 @@ class BlockPlan:
             self._call(lib.yamb_depthwise_fwd, d, "dw_fwd", 2 * cb * (self.M_in + self.M_out),
                        2 * self.M_out * cb * k * k)
             c0 += cb
+        # 2b. Squeeze-and-Excitation gate (reference mobilenet_base.py:110-113): spatial mean of
+        #     a2 = act(bn2(h2)) by a kernel, the two tiny FCs on [N, C] by torch, gate applied
+        #     inside the project GEMM's operand transform
+        if self.se is not None:
+            sp = nat.SePool()
+            sp.N, sp.HW, sp.C, sp.ldh = self.N, self.Ho * self.Wo, self.Chid, self.Chid
+            sp.h, sp.scale, sp.shift, sp.act = self.h2.data_ptr(), self.bn2.scale.data_ptr(), \
+                self.bn2.shift.data_ptr(), self.act
+            sp.pooled = self.pooled.data_ptr()
+            self._call(lib.yamb_se_pool_fwd, sp, "se_pool", 2 * self.M_out * self.Chid)
+            se = self.se
+            with torch.no_grad():
+                self.se_u = torch.addmm(se.se_reduce.bias, self.pooled,
+                                        se.se_reduce.weight.flatten(1).t())
+                self.se_v = _torch_act(self.se_u, self.se_act)
+                t = torch.addmm(se.se_expand.bias, self.se_v, se.se_expand.weight.flatten(1).t())
+                torch.sigmoid(t, out=self.gate)
         # 3. project 1x1 (BN2+act as operand transform) + BN3 statistics
         g = nat.Gemm()
         g.M, g.N, g.K = self.M_out, self.Cout, self.Chid
@@ -368,6 +392,8 @@ class BlockPlan:
         g.D, g.ldd = self.h3.data_ptr(), self.Cout
         g.a_xform, g.a_act = 1, self.act
         g.a_scale, g.a_shift = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr()
+        if self.se is not None:
+            g.a_gate, g.gate_rows_per_sample = self.gate.data_ptr(), self.Ho * self.Wo
         if self.bn3.batch_stats:
             g.bn_fwd = C.pointer(self._bn_fwd_struct(self.bn3, self.M_out))
         else:
@@ -402,6 +428,51 @@ class BlockPlan:
             self._call(lib.yamb_pointwise_gemm, gs, "pw_expand_fwd", 2 * gs.M * (gs.K + cb),
                        2 * gs.M * gs.K * cb)
 
+    def _se_backward(self, grads):
+        """SE backward: dgate by a reduction kernel, the two tiny FCs by torch, then
+        dz2 = (d(a2*gate)*gate + dpool) * act'(z2) with the BN2-backward statistics."""
+        lib = self.lib
+        se = self.se
+        HW = self.Ho * self.Wo
+        r = nat.SeBwdReduce()
+        r.N, r.HW, r.C, r.ldd, r.ldh = self.N, HW, self.Chid, self.Chid, self.Chid
+        r.dy, r.h = self.dz2.data_ptr(), self.h2.data_ptr()
+        r.scale, r.shift, r.act = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr(), self.act
+        r.dgate = self.dgate.data_ptr()
+        self._call(lib.yamb_se_bwd_reduce_bwd, r, "se_bwd_reduce", 4 * self.M_out * self.Chid)
+        with torch.no_grad():
+            gate = self.gate
+            dt = self.dgate * gate * (1 - gate)
+            we = se.se_expand.weight.flatten(1)          # [C, r]
+            wr = se.se_reduce.weight.flatten(1)          # [r, C]
+            g_we = dt.t() @ self.se_v
+            g_be = dt.sum(0)
+            du = (dt @ we) * _torch_act_grad(self.se_u, self.se_act)
+            g_wr = du.t() @ self.pooled
+            g_br = du.sum(0)
+            torch.mul(du @ wr, 1.0 / HW, out=self.dpool)
+            grads["se"] = {
+                id(se.se_expand.weight): g_we.view_as(se.se_expand.weight),
+                id(se.se_expand.bias): g_be,
+                id(se.se_reduce.weight): g_wr.view_as(se.se_reduce.weight),
+                id(se.se_reduce.bias): g_br,
+            }
+        for (c0, cb) in self.bn2.slices:
+            a = nat.SeBwdApply()
+            a.M, a.C, a.ldd, a.ldh, a.ldz = self.M_out, cb, self.Chid, self.Chid, self.Chid
+            a.rows_per_sample = HW
+            a.dy = self.dz2.data_ptr() + c0 * 2
+            a.h = self.h2.data_ptr() + c0 * 2
+            a.scale = self.bn2.scale.data_ptr() + c0 * 4
+            a.shift = self.bn2.shift.data_ptr() + c0 * 4
+            a.act = self.act
+            a.gate = self.gate.data_ptr() + c0 * 4
+            a.dpool = self.dpool.data_ptr() + c0 * 4
+            a.ldg = self.Chid
+            a.dz = self.dz2.data_ptr() + c0 * 2
+            a.bn = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"], c0, cb))
+            self._call(lib.yamb_se_bwd_apply_bwd, a, "se_bwd_apply", 6 * self.M_out * cb)
+
     # -- backward --------------------------------------------------------------------------------
     def backward(self, x, dy, grads):
         """grads: dict with fp32 accumulation targets:
@@ -434,29 +505,38 @@ class BlockPlan:
         g.A2, g.lda2 = self.h3.data_ptr(), self.Cout
         g.B, g.ldb, g.b_mn_major = self.w_proj_bf.data_ptr(), self.Chid, 1
         g.D, g.ldd = self.dz2.data_ptr(), self.Chid
-        g.epi = 1
-        g.H, g.ldh = self.h2.data_ptr(), self.Chid
-        g.h_scale, g.h_shift, g.h_act = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr(), \
-            self.act
-        if len(self.bn2.mods) == 1:
-            g.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"]))
+        if self.se is not None:
+            # SE: the GEMM writes d(a2*gate); the gate / pooling gradients need a reduction over
+            # HW first, so act'/BN2-backward happen in se_bwd_apply afterwards
             self._call(lib.yamb_pointwise_gemm, g, "pw_project_dgrad",
-                       4 * self.M_out * (self.Cout + self.Chid),
+                       2 * self.M_out * (2 * self.Cout + self.Chid),
                        2 * self.M_out * self.Chid * self.Cout)
+            self._se_backward(grads)
         else:
-            for (c0, cb) in self.bn2.slices:
-                gs = nat.Gemm()
-                C.memmove(C.byref(gs), C.byref(g), C.sizeof(nat.Gemm))
-                gs.N = cb
-                gs.B = g.B + c0 * 2
-                gs.D = g.D + c0 * 2
-                gs.H = g.H + c0 * 2
-                gs.h_scale = g.h_scale + c0 * 4
-                gs.h_shift = g.h_shift + c0 * 4
-                gs.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"], c0,
-                                                          cb))
-                self._call(lib.yamb_pointwise_gemm, gs, "pw_project_dgrad",
-                           4 * self.M_out * (self.Cout + cb), 2 * self.M_out * cb * self.Cout)
+            g.epi = 1
+            g.H, g.ldh = self.h2.data_ptr(), self.Chid
+            g.h_scale, g.h_shift, g.h_act = self.bn2.scale.data_ptr(), \
+                self.bn2.shift.data_ptr(), self.act
+            if len(self.bn2.mods) == 1:
+                g.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"]))
+                self._call(lib.yamb_pointwise_gemm, g, "pw_project_dgrad",
+                           4 * self.M_out * (self.Cout + self.Chid),
+                           2 * self.M_out * self.Chid * self.Cout)
+            else:
+                for (c0, cb) in self.bn2.slices:
+                    gs = nat.Gemm()
+                    C.memmove(C.byref(gs), C.byref(g), C.sizeof(nat.Gemm))
+                    gs.N = cb
+                    gs.B = g.B + c0 * 2
+                    gs.D = g.D + c0 * 2
+                    gs.H = g.H + c0 * 2
+                    gs.h_scale = g.h_scale + c0 * 4
+                    gs.h_shift = g.h_shift + c0 * 4
+                    gs.bn_bwd = C.pointer(self._bn_bwd_struct(self.bn2, self.M_out, grads["bn2"],
+                                                              c0, cb))
+                    self._call(lib.yamb_pointwise_gemm, gs, "pw_project_dgrad",
+                               4 * self.M_out * (self.Cout + cb),
+                               2 * self.M_out * cb * self.Cout)
         # 3. project wgrad: dW3[Cout,Chid] += dh3^T * a2
         g = nat.Gemm()
         g.M, g.N, g.K = self.Cout, self.Chid, self.M_out
@@ -469,6 +549,8 @@ class BlockPlan:
         g.B, g.ldb = self.h2.data_ptr(), self.Chid
         g.b_xform, g.b_act = 1, self.act
         g.b_scale, g.b_shift = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr()
+        if self.se is not None:
+            g.b_gate, g.gate_rows_per_sample = self.gate.data_ptr(), self.Ho * self.Wo
         g.D, g.ldd = grads["proj"].data_ptr(), self.Chid
         g.epi = 2
         self._call(lib.yamb_pointwise_gemm, g, "pw_project_wgrad",
@@ -534,6 +616,32 @@ class BlockPlan:
                    2 * self.M_in * (2 * self.Chid + self.Cin),
                    2 * self.M_in * self.Chid * self.Cin)
         return dx
+
+
+def _torch_act(z, code):
+    if code == 1:
+        return torch.relu(z)
+    if code == 2:
+        return torch.clamp(z, 0.0, 6.0)
+    if code == 3:
+        return z * torch.sigmoid(z)
+    if code == 4:
+        return z * torch.clamp(z + 3.0, 0.0, 6.0) / 6.0
+    return z
+
+
+def _torch_act_grad(z, code):
+    if code == 1:
+        return (z > 0).to(z.dtype)
+    if code == 2:
+        return ((z > 0) & (z < 6)).to(z.dtype)
+    if code == 3:
+        sg = torch.sigmoid(z)
+        return sg * (1 + z * (1 - sg))
+    if code == 4:
+        return torch.where(z <= -3, torch.zeros_like(z),
+                           torch.where(z >= 3, torch.ones_like(z), (2 * z + 3) / 6))
+    return torch.ones_like(z)
 
 
 def _plan_for(block, x):
@@ -657,6 +765,12 @@ class _BlockFn(torch.autograd.Function):
                     dg, db = g[key][i]
                     gmap[id(m.weight)] = dg
                     gmap[id(m.bias)] = db
+        for pid, t in g.get("se", {}).items():
+            if direct:
+                pmap = {id(p): p for p in params}
+                pmap[pid].grad.add_(t)
+            else:
+                gmap[pid] = t
         pgrads = []
         for p in params:
             t = gmap.get(id(p))

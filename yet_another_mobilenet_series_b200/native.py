@@ -58,6 +58,7 @@ class Gemm(C.Structure):
         ("h_scale", C.c_void_p), ("h_shift", C.c_void_p), ("h_act", C.c_int32),
         ("bn_bwd", C.POINTER(BnBwd)),
         ("max_ctas", C.c_int32),
+        ("a_gate", C.c_void_p), ("b_gate", C.c_void_p), ("gate_rows_per_sample", C.c_int64),
     ]
 
 
@@ -112,6 +113,27 @@ class SePool(C.Structure):
     ]
 
 
+class SeBwdReduce(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("HW", C.c_int32), ("C", C.c_int32), ("ldd", C.c_int32),
+        ("ldh", C.c_int32),
+        ("dy", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("act", C.c_int32),
+        ("dgate", C.c_void_p),
+    ]
+
+
+class SeBwdApply(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("C", C.c_int32), ("ldd", C.c_int32), ("ldh", C.c_int32),
+        ("ldz", C.c_int32), ("rows_per_sample", C.c_int64),
+        ("dy", C.c_void_p), ("h", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("act", C.c_int32),
+        ("gate", C.c_void_p), ("dpool", C.c_void_p), ("ldg", C.c_int32), ("dz", C.c_void_p),
+        ("bn", C.POINTER(BnBwd)),
+    ]
+
+
 class Rmsprop(C.Structure):
     _fields_ = [
         ("n", C.c_int64),
@@ -127,11 +149,11 @@ class Rmsprop(C.Structure):
 
 
 _STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
-            8: Rmsprop}
+            8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply}
 
 # every symbol include/yamb200.h declares
 SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
-           "yamb_bn_reduce_bwd", "yamb_se_pool_fwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_bn_reduce_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_rmsprop_step", "yamb_ema_update",
            "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
            "yamb_version"]
 _lib = None
@@ -162,6 +184,8 @@ def lib():
         l.yamb_bn_apply_fwd.argtypes = [C.POINTER(BnApply), C.c_void_p]
         l.yamb_bn_reduce_bwd.argtypes = [C.POINTER(BnReduce), C.c_void_p]
         l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
+        l.yamb_se_bwd_reduce_bwd.argtypes = [C.POINTER(SeBwdReduce), C.c_void_p]
+        l.yamb_se_bwd_apply_bwd.argtypes = [C.POINTER(SeBwdApply), C.c_void_p]
         l.yamb_rmsprop_step.argtypes = [C.POINTER(Rmsprop), C.c_void_p]
         l.yamb_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                       C.c_void_p]
