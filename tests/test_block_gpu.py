@@ -155,3 +155,50 @@ def test_bn_calibration_cumulative(built_lib):
     assert int(bn3.num_batches_tracked) == 3
     want = torch.stack(means).mean(0)
     assert torch.allclose(bn3.running_mean.cpu(), want, rtol=5e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("cls,act,extra", [
+    ("InvertedResidualChannels", "nn.ReLU6", {}),
+    ("InvertedResidualChannelsFused", "nn.Swish", {"se_ratio": 0.5}),
+])
+def test_odd_width_block_runs_through_padded_shadow(built_lib, cls, act, extra):
+    """AtomNAS-style hidden widths (not multiples of 8; reference
+    apps/searched/models/atomnas_c.yml:14) go through the zero-padded shadow block; results are
+    compared with the oracle evaluated on the REAL (unpadded) parameters."""
+    from oracle import ir_block as ob
+    from yet_another_mobilenet_series_b200 import mobilenet_base as mb
+    torch.manual_seed(5)
+    bn = {"momentum": 0.01, "eps": 1e-3}
+    args = (24, 24, 1, [15, 23, 13], [3, 5, 7], True)
+    blk = getattr(mb, cls)(*args, active_fn=mb.get_active_fn(act), batch_norm_kwargs=bn, **extra)
+    blk.apply(mb.init_weights_mnas)
+    for m in blk.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.3)
+    ref = getattr(mb, cls)(*args, active_fn=mb.get_active_fn(act), batch_norm_kwargs=bn, **extra)
+    ref.load_state_dict(blk.state_dict())
+    x = torch.randn(4, 24, 12, 12)
+    dy = torch.randn(4, 24, 12, 12)
+    blk = blk.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    y = blk(xg)
+    y.backward(dy.cuda().to(y.dtype))
+    torch.cuda.synchronize()
+    cfg, P = ob.extract(ref)
+    yo, S = ob.forward(x, cfg, P, training=True, quant=True)
+    dxo, G = ob.backward(dy, cfg, P, S, training=True, quant=True)
+    assert _rel(y, yo) < 3e-3
+    assert _rel(xg.grad, dxo) < 1.5e-2
+    for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and p.grad.shape == q.shape, k
+    fused = hasattr(blk, "expand_conv")
+    proj = [blk.project_conv[0]] if fused else [op[2] for op in blk.ops]
+    got = torch.cat([c.weight.grad.flatten(1) for c in proj], 1)
+    assert _rel(got, G["w_proj"]) < 1.5e-2
+    # running statistics came back un-padded
+    bn3 = blk.project_conv[1] if fused else blk.pw_bn
+    rm, _, _ = ob.bn_running_update(P["bn3_rm"], P["bn3_rv"], S["bn3_mean"], S["bn3_var"],
+                                    S["count_out"], cfg.momentum, 0)
+    assert torch.allclose(bn3.running_mean.cpu(), rm, rtol=5e-3, atol=2e-3)
+    assert int(bn3.num_batches_tracked) == 1

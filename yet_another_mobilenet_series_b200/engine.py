@@ -685,10 +685,22 @@ class _BlockFn(torch.autograd.Function):
                 "yamb: this block ran another forward before backward of the previous one; the "
                 "saved intermediates were overwritten (one forward/backward in flight per block)")
         (x,) = ctx.saved_tensors
+        dx, gmap = run_backward(block, plan, x, dy)
+        params = list(block.parameters())
+        pgrads = []
+        for p in params:
+            t = gmap.get(id(p))
+            pgrads.append(t.clone() if t is not None else None)
+        return (dx, None) + tuple(pgrads)
+
+
+def run_backward(block, plan, x, dy):
+    """Backward kernel sequence of one block; returns dx and {id(param): grad} for the parameters
+    whose gradient was NOT accumulated straight into `.grad` (flat-arena direct mode)."""
+    if True:
         dy = to_nhwc_bf16(dy)
         params = list(block.parameters())
         direct = all(getattr(p, "_yamb_direct", False) and p.grad is not None for p in params)
-        out = {}
 
         def target(p, zero_buf):
             if direct:
@@ -771,10 +783,143 @@ class _BlockFn(torch.autograd.Function):
                 pmap[pid].grad.add_(t)
             else:
                 gmap[pid] = t
+        return dx, gmap
+
+
+# ---- channel padding ---------------------------------------------------------------------------
+# The kernels need every channel count to be a multiple of 8 (16-byte rows, TMA strides).  Searched
+# networks (AtomNAS: hidden widths like [15, 23, 13], reference apps/searched/models/atomnas_c.yml)
+# are run through a SHADOW block of the same class whose branch widths are rounded up to 8: the
+# real parameters are scattered into the shadow's (padding: zero weights, gamma = beta = 0 so padded
+# channels stay exactly 0 through BN + activation), the shadow runs the ordinary kernel sequence,
+# gradients and running statistics are gathered back.  User-visible parameters are never padded.
+def _ceil8(c):
+    return (c + 7) // 8 * 8
+
+
+def needs_padding(block):
+    return any(c % 8 for c in block.channels)
+
+
+class _PadShadow:
+    def __init__(self, block, device):
+        from . import mobilenet_base as mb
+        fused = hasattr(block, "expand_conv")
+        base = mb.InvertedResidualChannelsFused if fused else mb.InvertedResidualChannels
+        self.real_ch = list(block.channels)
+        self.pad_ch = [_ceil8(c) for c in self.real_ch]
+        if block.input_dim % 8 or block.output_dim % 8:
+            raise nat.NativeError("block input/output widths must be multiples of 8 (got %d -> %d)"
+                                  % (block.input_dim, block.output_dim))
+        if not block.expand:
+            raise nat.NativeError("expand=False blocks need hidden == inp, a multiple of 8")
+        kw = dict(active_fn=block.active_fn, batch_norm_kwargs=block.batch_norm_kwargs)
+        if fused:
+            kw.update(se_ratio=block.se_ratio, nl_c=block.nl_c, nl_s=block.nl_s)
+        import logging
+        lvl = logging.root.level
+        self.shadow = base(block.input_dim, block.output_dim, block.stride, self.pad_ch,
+                           list(block.kernel_sizes), block.expand, **kw).to(device)
+        logging.root.setLevel(lvl)
+        for p in self.shadow.parameters():
+            p.requires_grad_(False)
+        real = dict(block.named_parameters())
+        real.update(dict(block.named_buffers()))
+        shad = dict(self.shadow.named_parameters())
+        shad.update(dict(self.shadow.named_buffers()))
+        tot_r, tot_p = sum(self.real_ch), sum(self.pad_ch)
+        concat_idx, off = [], 0
+        for c, cp in zip(self.real_ch, self.pad_ch):
+            concat_idx.append(torch.arange(off, off + c))
+            off += cp
+        concat_idx = torch.cat(concat_idx)
+        self.maps = {}
+        for name, t in real.items():
+            st = shad[name]
+            if t.dim() == 0:
+                self.maps[name] = None
+                continue
+            grids = []
+            for d, (r, sdim) in enumerate(zip(t.shape, st.shape)):
+                if r == sdim:
+                    grids.append(torch.arange(r))
+                elif r == tot_r and sdim == tot_p:
+                    grids.append(concat_idx)          # concatenated hidden dimension
+                elif r < sdim:
+                    grids.append(torch.arange(r))     # one branch: its first r channels are real
+                else:
+                    raise nat.NativeError("cannot map %s %s -> %s" % (name, tuple(t.shape),
+                                                                       tuple(st.shape)))
+            pos = torch.arange(st.numel()).view(st.shape)
+            for d, gi in enumerate(grids):
+                pos = pos.index_select(d, gi)
+            self.maps[name] = pos.reshape(-1).to(device)
+        self.real_names = list(real.keys())
+
+    def push(self, block):
+        """real -> shadow (parameters, running statistics, BN / module modes)."""
+        real = dict(block.named_parameters())
+        real.update(dict(block.named_buffers()))
+        shad = dict(self.shadow.named_parameters())
+        shad.update(dict(self.shadow.named_buffers()))
+        with torch.no_grad():
+            for name, t in real.items():
+                st, m = shad[name], self.maps[name]
+                if m is None:
+                    st.copy_(t)
+                else:
+                    if name.endswith("running_var"):
+                        st.fill_(1.0)
+                    else:
+                        st.zero_()
+                    st.view(-1).index_copy_(0, m, t.reshape(-1))
+        for (_, rm), (_, sm) in zip(block.named_modules(), self.shadow.named_modules()):
+            sm.training = rm.training
+            if isinstance(rm, torch.nn.BatchNorm2d):
+                sm.momentum, sm.eps = rm.momentum, rm.eps
+
+    def pull_stats(self, block):
+        """shadow -> real running statistics after a training-mode forward."""
+        shad = dict(self.shadow.named_buffers())
+        with torch.no_grad():
+            for name, t in block.named_buffers():
+                st, m = shad[name], self.maps[name]
+                if m is None:
+                    t.copy_(st)
+                else:
+                    t.copy_(st.view(-1).index_select(0, m).view(t.shape))
+
+
+class _PadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, block, *params):
+        sh = block.__dict__.get("_yamb_shadow")
+        if sh is None:
+            sh = _PadShadow(block, x.device)
+            block.__dict__["_yamb_shadow"] = sh
+        sh.push(block)
+        plan = _plan_for(sh.shadow, x)
+        y = plan.forward(x)
+        sh.pull_stats(block)
+        ctx.block, ctx.sh, ctx.plan, ctx.generation = block, sh, plan, plan.generation
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        sh, plan, block = ctx.sh, ctx.plan, ctx.block
+        if plan.generation != ctx.generation:
+            raise RuntimeError("yamb: block re-entered before its backward (see _BlockFn)")
+        (x,) = ctx.saved_tensors
+        dx, gmap = run_backward(sh.shadow, plan, x, dy)
+        sp = dict(sh.shadow.named_parameters())
         pgrads = []
-        for p in params:
-            t = gmap.get(id(p))
-            pgrads.append(t.clone() if t is not None else None)
+        for name, p in block.named_parameters():
+            g = gmap.get(id(sp[name]))
+            if g is None:
+                pgrads.append(None)
+            else:
+                pgrads.append(g.reshape(-1).index_select(0, sh.maps[name]).view(p.shape))
         return (dx, None) + tuple(pgrads)
 
 
@@ -786,4 +931,6 @@ def block_apply(block, x):
             "tensor" % x.device)
     x = to_nhwc_bf16(x)
     params = list(block.parameters())
+    if needs_padding(block):
+        return _PadFn.apply(x, block, *params)
     return _BlockFn.apply(x, block, *params)

@@ -182,7 +182,7 @@ class _FusedBlockBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_yamb_plans":
+            if k in ("_yamb_plans", "_yamb_shadow"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         return new
