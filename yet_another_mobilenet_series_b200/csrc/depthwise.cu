@@ -51,7 +51,7 @@ struct DwFwdDev {
   int has_bn;
   yamb_bn_fwd bn;
   int tiles_h, tiles_w, chunks;
-  long long num_tiles;
+  int num_tiles;
 };
 
 // CT channels per tile (32 or 64); 256 threads = NCG channel groups x NSTRIP vertical strips.
@@ -90,14 +90,16 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
   float wreg[K * K][4];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   int cur_chunk = -1;
-  const long long tiles_per_chunk = (long long)p.N * p.tiles_h * p.tiles_w;
+  // 32-bit tile arithmetic (64-bit div/mod costs ~100 instructions each on the SM)
+  const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
+  const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
 
-  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+  for (unsigned t = blockIdx.x; t < (unsigned)p.num_tiles; t += gridDim.x) {
     const int chunk = (int)(t / tiles_per_chunk);
-    long long r = t % tiles_per_chunk;
-    const int n = (int)(r / (p.tiles_h * p.tiles_w));
-    r %= (p.tiles_h * p.tiles_w);
-    const int ty = (int)(r / p.tiles_w), tx = (int)(r % p.tiles_w);
+    unsigned r = t - (unsigned)chunk * tiles_per_chunk;
+    const int n = (int)(r / tiles_per_img);
+    r -= (unsigned)n * tiles_per_img;
+    const int ty = (int)(r / (unsigned)p.tiles_w), tx = (int)(r - (unsigned)ty * p.tiles_w);
     const int cbase = chunk * CT;
     const int c0 = cbase + cg * 4;
     const bool cvalid = c0 < p.C;
@@ -155,14 +157,13 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
           const float4 s1 = *reinterpret_cast<const float4*>(s_sc + cc[u] + 4);
           const float4 h0 = *reinterpret_cast<const float4*>(s_sh + cc[u]);
           const float4 h1 = *reinterpret_cast<const float4*>(s_sh + cc[u] + 4);
-          a0.x = act_rt(fmaf(s0.x, bf16lo(raw[u].x), h0.x), ap);
-          a0.y = act_rt(fmaf(s0.y, bf16hi(raw[u].x), h0.y), ap);
-          a0.z = act_rt(fmaf(s0.z, bf16lo(raw[u].y), h0.z), ap);
-          a0.w = act_rt(fmaf(s0.w, bf16hi(raw[u].y), h0.w), ap);
-          a1.x = act_rt(fmaf(s1.x, bf16lo(raw[u].z), h1.x), ap);
-          a1.y = act_rt(fmaf(s1.y, bf16hi(raw[u].z), h1.y), ap);
-          a1.z = act_rt(fmaf(s1.z, bf16lo(raw[u].w), h1.z), ap);
-          a1.w = act_rt(fmaf(s1.w, bf16hi(raw[u].w), h1.w), ap);
+          float e8[8] = {fmaf(s0.x, bf16lo(raw[u].x), h0.x), fmaf(s0.y, bf16hi(raw[u].x), h0.y),
+                         fmaf(s0.z, bf16lo(raw[u].y), h0.z), fmaf(s0.w, bf16hi(raw[u].y), h0.w),
+                         fmaf(s1.x, bf16lo(raw[u].z), h1.x), fmaf(s1.y, bf16hi(raw[u].z), h1.y),
+                         fmaf(s1.z, bf16lo(raw[u].w), h1.z), fmaf(s1.w, bf16hi(raw[u].w), h1.w)};
+          act_vec<8>(e8, ap);
+          a0 = make_float4(e8[0], e8[1], e8[2], e8[3]);
+          a1 = make_float4(e8[4], e8[5], e8[6], e8[7]);
         }
         float* dst = s_tile + (idx / V8) * CT + (idx % V8) * 8;
         *reinterpret_cast<float4*>(dst) = a0;
@@ -196,11 +197,12 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
     }
     const int ox = ox0 + sx;
     if (cvalid && ox < p.Wo) {
+      __nv_bfloat16* yimg = p.y + (size_t)n * p.Ho * p.Wo * p.ldc + c0;
 #pragma unroll
       for (int j = 0; j < TH; ++j) {
         const int oy = oy0 + sy * TH + j;
         if (oy < p.Ho) {
-          st4_round(p.y + ((size_t)((size_t)n * p.Ho + oy) * p.Wo + ox) * p.ldc + c0, acc[j]);
+          st4_round(yimg + (unsigned)((oy * p.Wo + ox) * p.ldc), acc[j]);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             ssum[v] += acc[j][v];
@@ -248,7 +250,7 @@ struct DwBwdDev {
   int has_bn;
   yamb_bn_bwd bn;
   int tiles_h, tiles_w, chunks;
-  long long num_tiles;
+  int num_tiles;
 };
 
 // Input-space tile TI x TI (8 for stride 1, 16 for stride 2); the gradient region that touches it
@@ -305,7 +307,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
 #pragma unroll
     for (int v = 0; v < 4; ++v) gw[tp][v] = 0.f;
   int cur_chunk = -1;
-  const long long tiles_per_chunk = (long long)p.N * p.tiles_h * p.tiles_w;
+  const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
+  const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
   __syncthreads();
 
   auto flush = [&](int chunk) {
@@ -327,12 +330,12 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
     }
   };
 
-  for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+  for (unsigned t = blockIdx.x; t < (unsigned)p.num_tiles; t += gridDim.x) {
     const int chunk = (int)(t / tiles_per_chunk);
-    long long r = t % tiles_per_chunk;
-    const int n = (int)(r / (p.tiles_h * p.tiles_w));
-    r %= (p.tiles_h * p.tiles_w);
-    const int ty = (int)(r / p.tiles_w), tx = (int)(r % p.tiles_w);
+    unsigned r = t - (unsigned)chunk * tiles_per_chunk;
+    const int n = (int)(r / tiles_per_img);
+    r -= (unsigned)n * tiles_per_img;
+    const int ty = (int)(r / (unsigned)p.tiles_w), tx = (int)(r - (unsigned)ty * p.tiles_w);
     const int cbase = chunk * CT;
     const int c0 = cbase + cg * 4;
     const bool cvalid = c0 < p.C;
@@ -406,6 +409,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
       mu = *reinterpret_cast<const float4*>(s_tab + 5 * p.C + c0);
       rs = *reinterpret_cast<const float4*>(s_tab + 6 * p.C + c0);
     }
+    const size_t img_in = (size_t)n * p.H * p.W * p.ldc + c0;
+    const __nv_bfloat16* ximg = p.x + img_in;
 #pragma unroll 1
     for (int ib = 0; ib < ITEMS; ib += IB) {
       float xv[IB][4];
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
         const int pix = (ib + it) * NPIX + pslot;
         const int y = y0 + pix / TI, x = x0 + pix % TI;
         ok[it] = cvalid && y < p.H && x < p.W;
-        if (ok[it]) ld4(p.x + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.ldc + c0, xv[it]);
+        if (ok[it]) ld4(ximg + (unsigned)((y * p.W + x) * p.ldc), xv[it]);
       }
 #pragma unroll
       for (int it = 0; it < IB; ++it) {
@@ -424,9 +429,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
         const int y = y0 + pix / TI, x = x0 + pix % TI;
         const float z[4] = {fmaf(sc.x, xv[it][0], sh.x), fmaf(sc.y, xv[it][1], sh.y),
                             fmaf(sc.z, xv[it][2], sh.z), fmaf(sc.w, xv[it][3], sh.w)};
-        float a1[4], da[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int v = 0; v < 4; ++v) a1[v] = act_rt(z[v], ap);
+        float a1[4] = {z[0], z[1], z[2], z[3]}, da[4] = {0.f, 0.f, 0.f, 0.f};
+        act_vec<4>(a1, ap);
         // The staged region is zero outside the image and covers every tap of every pixel of the
         // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
         // parity test of the transposed convolution.
@@ -460,9 +464,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
           }
         }
         if (DGRAD) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) da[v] *= act_bwd_rt(z[v], ap, act);
-          const size_t off = ((size_t)((size_t)n * p.H + y) * p.W + x) * p.ldc + c0;
+          act_bwd_vec<4>(da, z, ap, act);
+          const size_t off = img_in + (unsigned)((y * p.W + x) * p.ldc);
           if (p.residual) {
             float rv[4];
             ld4(p.residual + off, rv);
@@ -573,7 +576,11 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   p.tiles_h = (p.Ho + toh - 1) / toh;
   p.tiles_w = (p.Wo + tow - 1) / tow;
   p.chunks = (a->C + ct - 1) / ct;
-  p.num_tiles = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+  {
+    long long nt = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+    if (nt > 0x7fffffffLL) return set_error(YAMB_EINVAL, "depthwise: too many tiles");
+    p.num_tiles = (int)nt;
+  }
   const int ih = (toh - 1) * s + k, iw = (tow - 1) * s + k;
   const size_t smem = ((size_t)ih * iw * ct + 4 * (size_t)a->C) * sizeof(float);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise fwd: tile too large");
@@ -610,7 +617,11 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   p.tiles_h = (a->H + ti - 1) / ti;
   p.tiles_w = (a->W + ti - 1) / ti;
   p.chunks = (a->C + ct - 1) / ct;
-  p.num_tiles = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+  {
+    long long nt = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
+    if (nt > 0x7fffffffLL) return set_error(YAMB_EINVAL, "depthwise: too many tiles");
+    p.num_tiles = (int)nt;
+  }
   const size_t smem =
       ((size_t)rmax * rmax * ct + (size_t)(7 + 2 * k * k + 2) * a->C) * sizeof(float);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");

@@ -39,6 +39,7 @@ struct BnApplyDev {
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __grid_constant__ BnApplyDev p) {
   const int CG = p.C / 8;
   const long long total = p.M * CG;
+  const ActParam ap = make_act(p.act);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / CG;
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __grid_constant__ B
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     const float sh[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = act_fwd(fmaf(sc[e], v[e], sh[e]), p.act);
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+    act_vec<8>(v, ap);
     if (p.gate) {
       const float* g = p.gate + (row / p.rows_per_sample) * p.C + c0;
 #pragma unroll

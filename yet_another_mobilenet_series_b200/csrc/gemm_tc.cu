@@ -147,31 +147,27 @@ __device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t 
 template <int MODE>
 __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap, bool gated) {
   if (!k.ok) return;
-  float x0 = bf16lo(k.v.x), x1 = bf16hi(k.v.x), x2 = bf16lo(k.v.y), x3 = bf16hi(k.v.y);
-  float x4 = bf16lo(k.v.z), x5 = bf16hi(k.v.z), x6 = bf16lo(k.v.w), x7 = bf16hi(k.v.w);
+  float x[8] = {bf16lo(k.v.x), bf16hi(k.v.x), bf16lo(k.v.y), bf16hi(k.v.y),
+                bf16lo(k.v.z), bf16hi(k.v.z), bf16lo(k.v.w), bf16hi(k.v.w)};
+  const float sc[8] = {k.sa.x, k.sa.y, k.sa.z, k.sa.w, k.sb.x, k.sb.y, k.sb.z, k.sb.w};
+  const float sh[8] = {k.ba.x, k.ba.y, k.ba.z, k.ba.w, k.bb.x, k.bb.y, k.bb.z, k.bb.w};
+  const float t2[8] = {k.ta.x, k.ta.y, k.ta.z, k.ta.w, k.tb.x, k.tb.y, k.tb.z, k.tb.w};
   if (MODE == 1) {
-    x0 = act_rt(fmaf(k.sa.x, x0, k.ba.x), ap); x1 = act_rt(fmaf(k.sa.y, x1, k.ba.y), ap);
-    x2 = act_rt(fmaf(k.sa.z, x2, k.ba.z), ap); x3 = act_rt(fmaf(k.sa.w, x3, k.ba.w), ap);
-    x4 = act_rt(fmaf(k.sb.x, x4, k.bb.x), ap); x5 = act_rt(fmaf(k.sb.y, x5, k.bb.y), ap);
-    x6 = act_rt(fmaf(k.sb.z, x6, k.bb.z), ap); x7 = act_rt(fmaf(k.sb.w, x7, k.bb.w), ap);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = fmaf(sc[e], x[e], sh[e]);
+    act_vec<8>(x, ap);
     if (gated) {  // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
-      x0 = round_bf16(x0) * k.ta.x; x1 = round_bf16(x1) * k.ta.y;
-      x2 = round_bf16(x2) * k.ta.z; x3 = round_bf16(x3) * k.ta.w;
-      x4 = round_bf16(x4) * k.tb.x; x5 = round_bf16(x5) * k.tb.y;
-      x6 = round_bf16(x6) * k.tb.z; x7 = round_bf16(x7) * k.tb.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = round_bf16(x[e]) * t2[e];
     }
   } else {
-    x0 = fmaf(k.sa.x, x0, fmaf(k.ta.x, bf16lo(k.v2.x), k.ba.x));
-    x1 = fmaf(k.sa.y, x1, fmaf(k.ta.y, bf16hi(k.v2.x), k.ba.y));
-    x2 = fmaf(k.sa.z, x2, fmaf(k.ta.z, bf16lo(k.v2.y), k.ba.z));
-    x3 = fmaf(k.sa.w, x3, fmaf(k.ta.w, bf16hi(k.v2.y), k.ba.w));
-    x4 = fmaf(k.sb.x, x4, fmaf(k.tb.x, bf16lo(k.v2.z), k.bb.x));
-    x5 = fmaf(k.sb.y, x5, fmaf(k.tb.y, bf16hi(k.v2.z), k.bb.y));
-    x6 = fmaf(k.sb.z, x6, fmaf(k.tb.z, bf16lo(k.v2.w), k.bb.z));
-    x7 = fmaf(k.sb.w, x7, fmaf(k.tb.w, bf16hi(k.v2.w), k.bb.w));
+    const float y[8] = {bf16lo(k.v2.x), bf16hi(k.v2.x), bf16lo(k.v2.y), bf16hi(k.v2.y),
+                        bf16lo(k.v2.z), bf16hi(k.v2.z), bf16lo(k.v2.w), bf16hi(k.v2.w)};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = fmaf(sc[e], x[e], fmaf(t2[e], y[e], sh[e]));
   }
-  sts128(k.addr, make_uint4(pack_bf16(x0, x1), pack_bf16(x2, x3), pack_bf16(x4, x5),
-                            pack_bf16(x6, x7)));
+  sts128(k.addr, make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                            pack_bf16(x[6], x[7])));
 }
 
 // In-place transform of one panel (R = 64 or 128 rows x 128 B, SWIZZLE_128B) by 128 threads.
@@ -184,7 +180,7 @@ __device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int
                                             int mode, const ActParam& ap, uint32_t tab_s,
                                             uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
                                             int row_limit, const float* gate, long long pixbase,
-                                            long long rps) {
+                                            long long rps, int dbg) {
   const int row = t & ((1 << logR) - 1);
   const int part = t >> logR;          // 0 (R=128) or 0..1 (R=64)
   const int per = 1 << (logR - 4);     // chunks per thread: 8 (R=128) or 4 (R=64)
@@ -494,13 +490,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 t1 = *reinterpret_cast<const float4*>(cz_t + cb + 4);
                 const float zs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
                 const float zt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                float zz[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float z0 = fmaf(zs[2 * e], bf16lo(sw[e]), zt[2 * e]);
-                  const float z1 = fmaf(zs[2 * e + 1], bf16hi(sw[e]), zt[2 * e + 1]);
-                  v[2 * e] *= act_bwd_rt(z0, hap, p.h_act);
-                  v[2 * e + 1] *= act_bwd_rt(z1, hap, p.h_act);
+                  zz[2 * e] = fmaf(zs[2 * e], bf16lo(sw[e]), zt[2 * e]);
+                  zz[2 * e + 1] = fmaf(zs[2 * e + 1], bf16hi(sw[e]), zt[2 * e + 1]);
                 }
+                act_bwd_vec<8>(v, zz, hap, p.h_act);
               }
               *reinterpret_cast<uint4*>(s_h + lane * 128 + (pc << 4)) = sv[ch];
             }
@@ -634,7 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const long long pixbase = mn ? (long long)kb * kBlockK : (long long)m_blk * kBlockM;
               const float* gate = (mode == 1 && (mn || isA)) ? (isA ? p.a_gate : p.b_gate) : nullptr;
               xform_panel(opbase + poff, op2 + poff, mn ? 6 : 7, t, mode, ap, t_s, t_b, t_s2, cbase,
-                          climit, rlimit, gate, pixbase, p.gate_rps);
+                          climit, rlimit, gate, pixbase, p.gate_rps, p.dbg);
             }
           }
           if (!(p.dbg & 2)) fence_proxy_async_smem();
