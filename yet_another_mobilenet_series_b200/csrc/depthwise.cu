@@ -67,7 +67,7 @@ struct FwdGeom {
 };
 
 template <int K, int S, int CT>
-__global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwFwdDev p) {
+__global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __grid_constant__ DwFwdDev p) {
   using G = FwdGeom<K, S, CT>;
   constexpr int P = (K - 1) / 2;
   constexpr int TH = G::TH, NCG = G::NCG, IH = G::IH, IW = G::IW;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
   const int cg = tid % NCG;
   const int strip = tid / NCG;
   const int sx = strip % G::TOW, sy = strip / G::TOW;
-  float wreg[K * K][4];
+  float2 wreg[K * K][2];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   int cur_chunk = -1;
   // 32-bit tile arithmetic (64-bit div/mod costs ~100 instructions each on the SM)
@@ -117,25 +117,30 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
       }
       cur_chunk = chunk;
 #pragma unroll
-      for (int tp = 0; tp < K * K; ++tp)
+      for (int tp = 0; tp < K * K; ++tp) {
+        float wv[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v)
-          wreg[tp][v] = cvalid ? __ldg(p.w + (size_t)(c0 + v) * K * K + tp) : 0.f;
+          wv[v] = cvalid ? __ldg(p.w + (size_t)(c0 + v) * K * K + tp) : 0.f;
+        wreg[tp][0] = make_float2(wv[0], wv[1]);
+        wreg[tp][1] = make_float2(wv[2], wv[3]);
+      }
     }
     const int oy0 = ty * G::TOH, ox0 = tx * G::TOW;
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
     __syncthreads();  // previous tile's compute is done with s_tile (and the tables are written)
     // ---- stage the input tile: BN + activation applied once per element, halo / padding = 0 ----
-    // 16-byte (8-channel) vectors, two independent global loads in flight per thread
+    // 16-byte (8-channel) vectors, NU independent global loads in flight per thread
     constexpr int V8 = CT / 8;              // vectors per pixel
     constexpr int NV = IH * IW * V8;
+    constexpr int NU = 4;
     const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc;
 #pragma unroll 1
-    for (int base = tid; base < NV; base += 2 * 256) {
-      uint4 raw[2];
-      int cc[2];
+    for (int base = tid; base < NV; base += NU * 256) {
+      uint4 raw[NU];
+      int cc[NU];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const int idx = base + u * 256;
         const int pix = idx / V8, g = idx % V8;
         const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const int idx = base + u * 256;
         if (idx >= NV) break;
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
@@ -171,29 +176,32 @@ __global__ void __launch_bounds__(256) dw_fwd_kernel(const __grid_constant__ DwF
       }
     }
     __syncthreads();
-    // ---- stencil: TH output rows x 4 channels per thread ----
-    float acc[TH][4];
+    // ---- stencil: TH output rows x 4 channels per thread (packed fp32x2 FMAs) ----
+    float2 acc2[TH][2];
 #pragma unroll
-    for (int j = 0; j < TH; ++j)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) acc[j][v] = 0.f;
+    for (int j = 0; j < TH; ++j) acc2[j][0] = acc2[j][1] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int rr = 0; rr < IR; ++rr) {
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
         const float4 a = *reinterpret_cast<const float4*>(
-            s_tile + (size_t)((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
+            s_tile + ((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
+        const float2 alo = make_float2(a.x, a.y), ahi = make_float2(a.z, a.w);
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           const int ky = rr - j * S;  // compile-time after unrolling
           if (ky >= 0 && ky < K) {
-            acc[j][0] = fmaf(wreg[ky * K + dx][0], a.x, acc[j][0]);
-            acc[j][1] = fmaf(wreg[ky * K + dx][1], a.y, acc[j][1]);
-            acc[j][2] = fmaf(wreg[ky * K + dx][2], a.z, acc[j][2]);
-            acc[j][3] = fmaf(wreg[ky * K + dx][3], a.w, acc[j][3]);
+            acc2[j][0] = ffma2(wreg[ky * K + dx][0], alo, acc2[j][0]);
+            acc2[j][1] = ffma2(wreg[ky * K + dx][1], ahi, acc2[j][1]);
           }
         }
       }
+    }
+    float acc[TH][4];
+#pragma unroll
+    for (int j = 0; j < TH; ++j) {
+      acc[j][0] = acc2[j][0].x; acc[j][1] = acc2[j][0].y;
+      acc[j][2] = acc2[j][1].x; acc[j][3] = acc2[j][1].y;
     }
     const int ox = ox0 + sx;
     if (cvalid && ox < p.Wo) {
@@ -300,12 +308,10 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
   const ActParam ap = make_act(act);
   const int cg = tid % NCG;
   const int pslot = tid / NCG;
-  float gw[NT][4];
+  float2 gw[NT][2];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int tp = 0; tp < NT; ++tp)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) gw[tp][v] = 0.f;
+  for (int tp = 0; tp < NT; ++tp) gw[tp][0] = gw[tp][1] = make_float2(0.f, 0.f);
   int cur_chunk = -1;
   const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
   const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
@@ -315,12 +321,14 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
     const int pc = chunk * CT + cg * 4;
     if (pc < p.C) {
 #pragma unroll
-      for (int tp = 0; tp < NT; ++tp)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          atomicAdd(&s_gw[(TAP0 + tp) * p.C + pc + v], gw[tp][v]);
-          gw[tp][v] = 0.f;
-        }
+      for (int tp = 0; tp < NT; ++tp) {
+        float* dst = &s_gw[(TAP0 + tp) * p.C + pc];
+        atomicAdd(dst + 0, gw[tp][0].x);
+        atomicAdd(dst + 1, gw[tp][0].y);
+        atomicAdd(dst + 2, gw[tp][1].x);
+        atomicAdd(dst + 3, gw[tp][1].y);
+        gw[tp][0] = gw[tp][1] = make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         atomicAdd(&s_part[pc + v], ssum[v]);
@@ -429,8 +437,10 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
         const int y = y0 + pix / TI, x = x0 + pix % TI;
         const float z[4] = {fmaf(sc.x, xv[it][0], sh.x), fmaf(sc.y, xv[it][1], sh.y),
                             fmaf(sc.z, xv[it][2], sh.z), fmaf(sc.w, xv[it][3], sh.w)};
-        float a1[4] = {z[0], z[1], z[2], z[3]}, da[4] = {0.f, 0.f, 0.f, 0.f};
+        float a1[4] = {z[0], z[1], z[2], z[3]};
         act_vec<4>(a1, ap);
+        const float2 a1lo = make_float2(a1[0], a1[1]), a1hi = make_float2(a1[2], a1[3]);
+        float2 da2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         // The staged region is zero outside the image and covers every tap of every pixel of the
         // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
         // parity test of the transposed convolution.
@@ -448,22 +458,20 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
             const int ox = S == 1 ? xx : xx >> 1;
             const float4 dh = *reinterpret_cast<const float4*>(
                 s_dh + ((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
+            const float2 dlo = make_float2(dh.x, dh.y), dhi = make_float2(dh.z, dh.w);
             if (DGRAD) {
               const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
-              da[0] = fmaf(dh.x, wv.x, da[0]);
-              da[1] = fmaf(dh.y, wv.y, da[1]);
-              da[2] = fmaf(dh.z, wv.z, da[2]);
-              da[3] = fmaf(dh.w, wv.w, da[3]);
+              da2[0] = ffma2(dlo, make_float2(wv.x, wv.y), da2[0]);
+              da2[1] = ffma2(dhi, make_float2(wv.z, wv.w), da2[1]);
             }
             if (tp >= TAP0 && tp < TAP1) {
-              gw[tp - TAP0][0] = fmaf(dh.x, a1[0], gw[tp - TAP0][0]);
-              gw[tp - TAP0][1] = fmaf(dh.y, a1[1], gw[tp - TAP0][1]);
-              gw[tp - TAP0][2] = fmaf(dh.z, a1[2], gw[tp - TAP0][2]);
-              gw[tp - TAP0][3] = fmaf(dh.w, a1[3], gw[tp - TAP0][3]);
+              gw[tp - TAP0][0] = ffma2(dlo, a1lo, gw[tp - TAP0][0]);
+              gw[tp - TAP0][1] = ffma2(dhi, a1hi, gw[tp - TAP0][1]);
             }
           }
         }
         if (DGRAD) {
+          float da[4] = {da2[0].x, da2[0].y, da2[1].x, da2[1].y};
           act_bwd_vec<4>(da, z, ap, act);
           const size_t off = img_in + (unsigned)((y * p.W + x) * p.ldc);
           if (p.residual) {

@@ -60,6 +60,7 @@ struct GemmDev {
   int out_bufs;               // staging buffers per epilogue warp (1 or 2)
   const float *a_gate, *b_gate;  // optional per-(sample, channel) gates [n][C] (SE)
   long long gate_rps;            // pixels per sample
+  int wg2x;                   // 1: warps 8-11 transform (light epilogue), 0: they are epilogue WG 1
   int dbg;                    // YAMB_GEMM_DEBUG bits: 1 skip transform math, 2 skip proxy fence
   yamb_bn_fwd bnf;
   int has_bnf;
@@ -180,10 +181,11 @@ __device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int
                                             int mode, const ActParam& ap, uint32_t tab_s,
                                             uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
                                             int row_limit, const float* gate, long long pixbase,
-                                            long long rps, int dbg) {
+                                            long long rps, int lognt) {
+  // lognt = log2(#transform threads) (7 or 8); threads per row = nt / R, chunks per thread = 8R/nt
   const int row = t & ((1 << logR) - 1);
-  const int part = t >> logR;          // 0 (R=128) or 0..1 (R=64)
-  const int per = 1 << (logR - 4);     // chunks per thread: 8 (R=128) or 4 (R=64)
+  const int part = t >> logR;
+  const int per = 1 << (logR + 3 - lognt);
   if (row >= row_limit) return;
   const uint32_t rbase = panel + row * 128;
   const uint32_t rbase2 = panel2 + row * 128;
@@ -234,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&bars->full[i], 1);
-      mbar_init(&bars->xdone[i], 128);
+      mbar_init(&bars->xdone[i], p.wg2x ? 256 : 128);
       mbar_init(&bars->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -369,7 +371,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
    }
-  } else if (warp < 4 + kEpiWarps) {
+  } else if (warp < 8 || (warp < 12 && !(kXform && p.wg2x))) {
     // ======================================= epilogue =======================================
     if (kXform) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     const int ew = warp - 4;           // 0..7
@@ -385,14 +387,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* cz_r = s_coef + 3 * p.N;
     if (p.epi == 1) {
       float* wr = s_coef;
-      for (int i = threadIdx.x - 128; i < p.N; i += 32 * kEpiWarps) {
+      const int n_epi_thr = (kXform && p.wg2x) ? 128 : 256;
+      for (int i = threadIdx.x - 128; i < p.N; i += n_epi_thr) {
         wr[i] = p.h_scale[i];
         wr[p.N + i] = p.h_shift[i];
         wr[2 * p.N + i] = p.bnb.mean[i];
         wr[3 * p.N + i] = p.bnb.invstd[i];
       }
-      named_bar_sync(1, 32 * kEpiWarps);
+      named_bar_sync(1, n_epi_thr);
     }
+    const int n_epi_wg = (kXform && p.wg2x) ? 1 : 2;
     uint32_t sub_count = 0;   // running sub-tile counter of this warp -> staging buffer parity
     const bool side_in = (p.epi == 1) || p.has_residual;
     const ActParam hap = make_act(p.epi == 1 ? p.h_act : ACT_NONE);
@@ -407,10 +411,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int e = 0; e < 4; ++e) racc[j][e] = 0.f;
     int it = 0;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
-      if ((it & 1) != wg) continue;    // the other warpgroup owns this tile
+      if (n_epi_wg == 2 && (it & 1) != wg) continue;  // the other warpgroup owns this tile
       const int mn = w / p.ksplit;
       const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
-      const int as = wg;
+      const int as = it & 1;
       const int grow = m_blk * kBlockM + row;
       const bool row_ok = grow < p.M;
       // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
@@ -567,26 +571,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (lane == 0 && p.epi != 2) tma_store_wait_all<0>();
-  } else if (kXform && warp >= 4 + kEpiWarps) {
+  } else if (kXform) {
     // ================================== operand transform ==================================
     if (use_x) {
-      const int t = threadIdx.x - 32 * (4 + kEpiWarps);
+      // transform threads: warps 12-15 (t 0..127) plus, when wg2x, warps 8-11 (t 128..255)
+      const int nxt = p.wg2x ? 256 : 128;
+      const int t = warp >= 12 ? threadIdx.x - 384 : threadIdx.x - 256 + 128;
       // coefficient tables in smem: A: [scale|shift|scale2] x Ca, then B likewise
       const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
       const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
       float* xa = s_coef + (p.epi == 1 ? 4 * p.N : 0);
       float* xb = xa + 3 * Ca;
-      for (int i = t; i < Ca; i += 128) {
+      for (int i = t; i < Ca; i += nxt) {
         xa[i] = p.a_scale[i];
         xa[Ca + i] = p.a_shift[i];
         xa[2 * Ca + i] = p.a_xform == 2 ? p.a_scale2[i] : 0.f;
       }
-      for (int i = t; i < Cb; i += 128) {
+      for (int i = t; i < Cb; i += nxt) {
         xb[i] = p.b_scale[i];
         xb[Cb + i] = p.b_shift[i];
         xb[2 * Cb + i] = p.b_xform == 2 ? p.b_scale2[i] : 0.f;
       }
-      named_bar_sync(2, 128);
+      named_bar_sync(2, nxt);
       const ActParam apa = make_act(p.a_xform == 1 ? p.a_act : ACT_NONE);
       const ActParam apb = make_act(p.b_xform == 1 ? p.b_act : ACT_NONE);
       int stage = 0, phase = 0;
@@ -630,7 +636,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const long long pixbase = mn ? (long long)kb * kBlockK : (long long)m_blk * kBlockM;
               const float* gate = (mode == 1 && (mn || isA)) ? (isA ? p.a_gate : p.b_gate) : nullptr;
               xform_panel(opbase + poff, op2 + poff, mn ? 6 : 7, t, mode, ap, t_s, t_b, t_s2, cbase,
-                          climit, rlimit, gate, pixbase, p.gate_rps, p.dbg);
+                          climit, rlimit, gate, pixbase, p.gate_rps, p.wg2x ? 8 : 7);
             }
           }
           if (!(p.dbg & 2)) fence_proxy_async_smem();
@@ -725,6 +731,10 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     return set_error(YAMB_EINVAL, "two-source transform without second tensor");
   p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
   { const char* d = getenv("YAMB_GEMM_DEBUG"); p.dbg = d ? atoi(d) : 0; }
+  // transform-heavy / epilogue-light launches give warps 8-11 to the transform
+  p.wg2x = ((a->a_xform || a->b_xform) && (a->epi == 2 || (a->epi == 0 && p.block_n <= 192))) ? 1 : 0;
+  if (p.dbg & 16) p.wg2x = 0;
+  if (p.dbg & 32) p.wg2x = (a->a_xform || a->b_xform) ? 1 : 0;
   p.a_gate = a->a_xform == 1 ? a->a_gate : nullptr;
   p.b_gate = a->b_xform == 1 ? a->b_gate : nullptr;
   p.gate_rps = a->gate_rows_per_sample > 0 ? a->gate_rows_per_sample : 1;

@@ -262,6 +262,18 @@ __device__ __forceinline__ float act_bwd_rt(float z, const ActParam& a, int act)
   if (a.kind == 0) return (z > a.lo && z < a.hi) ? 1.f : 0.f;
   return act_bwd(z, act);
 }
+// Packed fp32x2 FMA (Blackwell FFMA2): two FMAs per issue slot — the depthwise stencils are bound
+// by instruction issue, not by the FMA pipe.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return d;
+}
+
 // N-element forms: ONE warp-uniform branch for the whole vector (a branch per element serialises
 // the elements: measured 4x slowdown of the operand transform).
 template <int N>
