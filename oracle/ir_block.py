@@ -188,7 +188,7 @@ def forward(x, cfg, P, training=True, quant=False):
     if cfg.expand:
         h1 = _rnd(F.conv2d(x, _rnd(P["w_exp"], q)[:, :, None, None]), q)
         S["h1"] = h1
-        a1 = act_fwd(bn(h1, "bn1"), cfg.act)  # consumed in fp32 by the depthwise stencil
+        a1 = _rnd(act_fwd(bn(h1, "bn1"), cfg.act), q)  # staged in shared memory as bf16
     else:
         # unfused, expand=False: each branch sees the whole input (hidden == inp)
         a1 = x if len(cfg.channels) == 1 else torch.cat([x] * len(cfg.channels), 1)
@@ -266,6 +266,7 @@ def backward(dy, cfg, P, S, training=True, quant=False):
     dz2 = _rnd(da2 * act_bwd(z2, cfg.act), q)  # materialised bf16
     G["bn2_g"], G["bn2_b"], dh2 = _bn_bwd(dz2, S["h2"], S["bn2_mean"], S["bn2_invstd"], P["bn2_g"],
                                           training)
+    dh2 = _rnd(dh2, q)  # staged in shared memory as bf16 by the depthwise backward
     # --- depthwise k x k ---
     a1 = S["a1"]
     da1_parts, G["w_dw"], c0 = [], [], 0

@@ -73,7 +73,9 @@ def test_depthwise_fwd_bwd(built_lib, N, H, W, Ct, c0, Cs, k, s, act, pro):
     d.bn = C.pointer(bn)
     nat.check(lib.yamb_depthwise_fwd(C.byref(d), nat.stream_handle()))
     torch.cuda.synchronize()
-    a1 = _act(xf * sc[None, :, None, None] + sh[None, :, None, None], act) if pro else xf
+    # the kernel stages act(bn(x)) in shared memory as bf16
+    a1 = _act(xf * sc[None, :, None, None] + sh[None, :, None, None], act).to(
+        torch.bfloat16).float() if pro else xf
     y_ref = F.conv2d(a1, w, None, s, pad, 1, Cs).to(torch.bfloat16).float()
     y_got = yb.float().permute(0, 3, 1, 2)[:, c0:c0 + Cs]
     assert _rel(y_got, y_ref) < 4e-3
@@ -129,7 +131,7 @@ def test_depthwise_fwd_bwd(built_lib, N, H, W, Ct, c0, Cs, k, s, act, pro):
     dzf = dzb.float().permute(0, 3, 1, 2)[:, sl]
     hf = hb.float().permute(0, 3, 1, 2)[:, sl]
     v = lambda t: t[None, :, None, None]
-    dh = v(ca) * dzf + v(cb) * hf + v(cc)
+    dh = (v(ca) * dzf + v(cb) * hf + v(cc)).to(torch.bfloat16).float()  # staged as bf16
     da = torch.nn.grad.conv2d_input(a1.shape, w, dh, s, pad, 1, Cs)
     dw_ref = torch.nn.grad.conv2d_weight(a1, w.shape, dh, s, pad, 1, Cs)
     if pro:

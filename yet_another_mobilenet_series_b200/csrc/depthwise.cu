@@ -4,9 +4,9 @@
 // nn.Conv2d(groups=C) + BatchNorm2d + activation library calls of the reference block
 // (models/mobilenet_base.py:405-411 unfused, :275-281 fused) and their autograd backward.
 //
-// forward : y = dwconv(act(in_scale*x + in_shift))   — the producer's BatchNorm + activation is
-//           applied ONCE per element while the input tile (with halo) is staged into shared
-//           memory in fp32; per-channel sum / sum^2 of the bf16 output feed the next BatchNorm
+// forward : y = dwconv(act(in_scale*x + in_shift))   — raw bf16 tiles (with halo) stream into
+//           shared memory with cp.async (double-buffered); the producer's BatchNorm + activation
+//           is applied ONCE per element, in place; per-channel sum / sum^2 of the bf16 output feed the next BatchNorm
 //           (last-CTA finalize).
 // backward: dh = ca*dz + cb*h + cc (BatchNorm backward of the depthwise output) is formed ONCE per
 //           element while the gradient tile (with halo) is staged; da = dwconv^T(dh, w),
@@ -66,17 +66,35 @@ struct FwdGeom {
   static constexpr int IW = (TOW - 1) * S + K;
 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Forward, v3: the raw bf16 input tile (with halo) of tile t+1 streams into shared memory with
+// cp.async (zero-fill outside the image) while tile t is transformed IN PLACE (BN + activation,
+// rounded to bf16 like every other materialised activation) and convolved.
 template <int K, int S, int CT>
-__global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __grid_constant__ DwFwdDev p) {
+__global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
+    const __grid_constant__ DwFwdDev p) {
   using G = FwdGeom<K, S, CT>;
   constexpr int P = (K - 1) / 2;
   constexpr int TH = G::TH, NCG = G::NCG, IH = G::IH, IW = G::IW;
   constexpr int IR = (TH - 1) * S + K;
+  constexpr int V8 = CT / 8;               // 16-byte vectors per pixel
+  constexpr int NV = IH * IW * V8;
+  constexpr int TILE_ELEMS = IH * IW * CT;  // bf16 elements per staging buffer
   extern __shared__ __align__(16) float smem_f[];
-  float* s_tile = smem_f;                       // [IH*IW][CT]
-  float* s_sc = s_tile + IH * IW * CT;          // [C]
-  float* s_sh = s_sc + p.C;                     // [C]
-  float* s_part = s_sh + p.C;                   // [2][C]
+  __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(smem_f);  // [2][TILE_ELEMS]
+  float* s_sc = smem_f + TILE_ELEMS;       // 2 * TILE_ELEMS bf16 == TILE_ELEMS floats
+  float* s_sh = s_sc + p.C;
+  float* s_part = s_sh + p.C;              // [2][C]
   const int tid = threadIdx.x;
   for (int i = tid; i < p.C; i += 256) {
     s_sc[i] = p.in_scale ? __ldg(p.in_scale + i) : 1.f;
@@ -84,22 +102,50 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __g
   }
   for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
   const ActParam ap = make_act(p.in_scale ? p.in_act : ACT_NONE);
+  const bool identity = p.in_scale == nullptr;
   const int cg = tid % NCG;
   const int strip = tid / NCG;
   const int sx = strip % G::TOW, sy = strip / G::TOW;
   float2 wreg[K * K][2];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   int cur_chunk = -1;
-  // 32-bit tile arithmetic (64-bit div/mod costs ~100 instructions each on the SM)
   const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
   const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
 
-  for (unsigned t = blockIdx.x; t < (unsigned)p.num_tiles; t += gridDim.x) {
-    const int chunk = (int)(t / tiles_per_chunk);
+  auto decode = [&](unsigned t, int& chunk, int& n, int& ty, int& tx) {
+    chunk = (int)(t / tiles_per_chunk);
     unsigned r = t - (unsigned)chunk * tiles_per_chunk;
-    const int n = (int)(r / tiles_per_img);
+    n = (int)(r / tiles_per_img);
     r -= (unsigned)n * tiles_per_img;
-    const int ty = (int)(r / (unsigned)p.tiles_w), tx = (int)(r - (unsigned)ty * p.tiles_w);
+    ty = (int)(r / (unsigned)p.tiles_w);
+    tx = (int)(r - (unsigned)ty * p.tiles_w);
+  };
+  // enqueue the cp.async copies of one tile into staging buffer `buf`
+  auto prefetch = [&](unsigned t, int buf) {
+    int chunk, n, ty, tx;
+    decode(t, chunk, n, ty, tx);
+    const int iy0 = ty * G::TOH * S - P, ix0 = tx * G::TOW * S - P;
+    const int cbase = chunk * CT;
+    const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc;
+    __nv_bfloat16* dst = s_raw + buf * TILE_ELEMS;
+#pragma unroll 4
+    for (int idx = tid; idx < NV; idx += 256) {
+      const int pix = idx / V8, g = idx % V8;
+      const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
+      const int c = cbase + g * 8;
+      const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C;
+      const __nv_bfloat16* src = ok ? img + (unsigned)((iy * p.W + ix) * p.ldc + c) : p.x;
+      cp_async16(dst + pix * CT + g * 8, src, ok ? 16 : 0);
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  if (t < (unsigned)p.num_tiles) prefetch(t, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (; t < (unsigned)p.num_tiles; t += gridDim.x, buf ^= 1) {
+    int chunk, n, ty, tx;
+    decode(t, chunk, n, ty, tx);
     const int cbase = chunk * CT;
     const int c0 = cbase + cg * 4;
     const bool cvalid = c0 < p.C;
@@ -128,54 +174,40 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __g
     }
     const int oy0 = ty * G::TOH, ox0 = tx * G::TOW;
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
-    __syncthreads();  // previous tile's compute is done with s_tile (and the tables are written)
-    // ---- stage the input tile: BN + activation applied once per element, halo / padding = 0 ----
-    // 16-byte (8-channel) vectors, NU independent global loads in flight per thread
-    constexpr int V8 = CT / 8;              // vectors per pixel
-    constexpr int NV = IH * IW * V8;
-    constexpr int NU = 4;
-    const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc;
-#pragma unroll 1
-    for (int base = tid; base < NV; base += NU * 256) {
-      uint4 raw[NU];
-      int cc[NU];
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int idx = base + u * 256;
+    __syncthreads();  // everyone is done computing from the buffer the next prefetch overwrites
+    {
+      const unsigned tn = t + gridDim.x;
+      if (tn < (unsigned)p.num_tiles) prefetch(tn, buf ^ 1);
+      cp_async_commit();
+    }
+    cp_async_wait<1>();  // this tile's copies (the older group) have landed
+    __syncthreads();
+    __nv_bfloat16* tile = s_raw + buf * TILE_ELEMS;
+    // ---- in-place BN + activation (bf16 -> fp32 -> bf16); padding / halo stays exactly 0 ----
+    if (!identity) {
+#pragma unroll 2
+      for (int idx = tid; idx < NV; idx += 256) {
         const int pix = idx / V8, g = idx % V8;
         const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
         const int c = cbase + g * 8;
-        cc[u] = -1;
-        raw[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (idx < NV && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C) {
-          cc[u] = c;
-          raw[u] = __ldg(reinterpret_cast<const uint4*>(img + (unsigned)((iy * p.W + ix) * p.ldc + c)));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int idx = base + u * 256;
-        if (idx >= NV) break;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        if (cc[u] >= 0) {
-          const float4 s0 = *reinterpret_cast<const float4*>(s_sc + cc[u]);
-          const float4 s1 = *reinterpret_cast<const float4*>(s_sc + cc[u] + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(s_sh + cc[u]);
-          const float4 h1 = *reinterpret_cast<const float4*>(s_sh + cc[u] + 4);
-          float e8[8] = {fmaf(s0.x, bf16lo(raw[u].x), h0.x), fmaf(s0.y, bf16hi(raw[u].x), h0.y),
-                         fmaf(s0.z, bf16lo(raw[u].y), h0.z), fmaf(s0.w, bf16hi(raw[u].y), h0.w),
-                         fmaf(s1.x, bf16lo(raw[u].z), h1.x), fmaf(s1.y, bf16hi(raw[u].z), h1.y),
-                         fmaf(s1.z, bf16lo(raw[u].w), h1.z), fmaf(s1.w, bf16hi(raw[u].w), h1.w)};
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C) {
+          uint4* q = reinterpret_cast<uint4*>(tile + pix * CT + g * 8);
+          const uint4 raw = *q;
+          const float4 s0 = *reinterpret_cast<const float4*>(s_sc + c);
+          const float4 s1 = *reinterpret_cast<const float4*>(s_sc + c + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(s_sh + c);
+          const float4 h1 = *reinterpret_cast<const float4*>(s_sh + c + 4);
+          float e8[8] = {fmaf(s0.x, bf16lo(raw.x), h0.x), fmaf(s0.y, bf16hi(raw.x), h0.y),
+                         fmaf(s0.z, bf16lo(raw.y), h0.z), fmaf(s0.w, bf16hi(raw.y), h0.w),
+                         fmaf(s1.x, bf16lo(raw.z), h1.x), fmaf(s1.y, bf16hi(raw.z), h1.y),
+                         fmaf(s1.z, bf16lo(raw.w), h1.z), fmaf(s1.w, bf16hi(raw.w), h1.w)};
           act_vec<8>(e8, ap);
-          a0 = make_float4(e8[0], e8[1], e8[2], e8[3]);
-          a1 = make_float4(e8[4], e8[5], e8[6], e8[7]);
+          *q = make_uint4(pack_bf16(e8[0], e8[1]), pack_bf16(e8[2], e8[3]),
+                          pack_bf16(e8[4], e8[5]), pack_bf16(e8[6], e8[7]));
         }
-        float* dst = s_tile + (idx / V8) * CT + (idx % V8) * 8;
-        *reinterpret_cast<float4*>(dst) = a0;
-        *reinterpret_cast<float4*>(dst + 4) = a1;
       }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- stencil: TH output rows x 4 channels per thread (packed fp32x2 FMAs) ----
     float2 acc2[TH][2];
 #pragma unroll
@@ -184,9 +216,10 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __g
     for (int rr = 0; rr < IR; ++rr) {
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
-        const float4 a = *reinterpret_cast<const float4*>(
-            s_tile + ((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
-        const float2 alo = make_float2(a.x, a.y), ahi = make_float2(a.z, a.w);
+        const uint2 a = *reinterpret_cast<const uint2*>(
+            tile + ((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
+        const float2 alo = make_float2(bf16lo(a.x), bf16hi(a.x));
+        const float2 ahi = make_float2(bf16lo(a.y), bf16hi(a.y));
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           const int ky = rr - j * S;  // compile-time after unrolling
@@ -220,6 +253,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(const __g
       }
     }
   }
+  cp_async_wait<0>();
   if (p.has_bn) {
     if (cur_chunk >= 0) {
       const int pc = cur_chunk * CT + cg * 4;
@@ -261,30 +295,40 @@ struct DwBwdDev {
   int num_tiles;
 };
 
-// Input-space tile TI x TI (8 for stride 1, 16 for stride 2); the gradient region that touches it
-// is at most RMAX x RMAX output pixels.
+// Input-space tile TI x TI; the gradient region that touches it is at most RMAX x RMAX output
+// pixels.
 template <int K, int S>
 struct BwdGeom {
   static constexpr int P = (K - 1) / 2;
-  static constexpr int TI = S == 1 ? 8 : 16;
+  static constexpr int TI = 8;
   static constexpr int RMAX = S == 1 ? TI + K - 1 : (TI + K - 1) / 2 + 1;
 };
 
 // TAP0..TAP1: taps whose weight gradient this launch accumulates (all of them unless K == 7, where
 // 49 x 4 accumulators do not fit the register file and a second, wgrad-only launch covers the rest).
 // DGRAD: compute and store dx (+ statistics); false for that second launch.
+//
+// v3: the raw bf16 tiles of tile t+1 (dz and h over the gradient region, x over the input tile)
+// stream into shared memory with cp.async while tile t is processed; dh = ca*dz + cb*h + cc is
+// formed once per element, in place (bf16, like every other materialised gradient).
 template <int K, int S, int CT, int TAP0, int TAP1, bool DGRAD>
-__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __grid_constant__ DwBwdDev p) {
+__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
+    const __grid_constant__ DwBwdDev p) {
   using G = BwdGeom<K, S>;
   constexpr int P = G::P, TI = G::TI, RMAX = G::RMAX;
   constexpr int NCG = CT / 4;
   constexpr int NPIX = 256 / NCG;           // pixels processed concurrently
   constexpr int ITEMS = TI * TI / NPIX;     // pixels per thread per tile
-  constexpr int IB = ITEMS < 4 ? ITEMS : 4; // pixels per thread whose loads are batched
   constexpr int NT = TAP1 - TAP0;
+  constexpr int V8 = CT / 8;
+  constexpr int NVR = RMAX * RMAX * V8;     // 16-byte vectors of one gradient-region tensor
+  constexpr int NVX = TI * TI * V8;         // 16-byte vectors of the input tile
+  constexpr int REG_ELEMS = RMAX * RMAX * CT;
+  constexpr int X_ELEMS = TI * TI * CT;
+  constexpr int BUF_ELEMS = 2 * REG_ELEMS + X_ELEMS;  // one staging buffer: dz | h | x
   extern __shared__ __align__(16) float smem_f[];
-  float* s_dh = smem_f;                      // [RMAX*RMAX][CT]
-  float* s_tab = s_dh + RMAX * RMAX * CT;    // 7 tables x C: sc sh ca cb cc mu rs
+  __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(smem_f);  // [2][BUF_ELEMS]
+  float* s_tab = smem_f + BUF_ELEMS;         // 2 * BUF_ELEMS bf16 == BUF_ELEMS floats
   float* s_w = s_tab + 7 * p.C;              // [K*K][C]
   float* s_gw = s_w + K * K * p.C;           // [K*K][C]
   float* s_part = s_gw + K * K * p.C;        // [2][C]
@@ -315,7 +359,6 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
   int cur_chunk = -1;
   const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
   const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
-  __syncthreads();
 
   auto flush = [&](int chunk) {
     const int pc = chunk * CT + cg * 4;
@@ -337,13 +380,60 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
       }
     }
   };
-
-  for (unsigned t = blockIdx.x; t < (unsigned)p.num_tiles; t += gridDim.x) {
-    const int chunk = (int)(t / tiles_per_chunk);
+  auto decode = [&](unsigned t, int& chunk, int& n, int& ty, int& tx) {
+    chunk = (int)(t / tiles_per_chunk);
     unsigned r = t - (unsigned)chunk * tiles_per_chunk;
-    const int n = (int)(r / tiles_per_img);
+    n = (int)(r / tiles_per_img);
     r -= (unsigned)n * tiles_per_img;
-    const int ty = (int)(r / (unsigned)p.tiles_w), tx = (int)(r - (unsigned)ty * p.tiles_w);
+    ty = (int)(r / (unsigned)p.tiles_w);
+    tx = (int)(r - (unsigned)ty * p.tiles_w);
+  };
+  auto region_origin = [&](int ty, int tx, int& ry0, int& rx0) {
+    const int y0 = ty * TI, x0 = tx * TI;
+    ry0 = S == 1 ? y0 - P : (y0 - P + 1) >> 1;   // ceil((y0-P)/2), also right for < 0
+    rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
+  };
+  auto prefetch = [&](unsigned t, int buf) {
+    int chunk, n, ty, tx, ry0, rx0;
+    decode(t, chunk, n, ty, tx);
+    region_origin(ty, tx, ry0, rx0);
+    const int cbase = chunk * CT;
+    __nv_bfloat16* b_dz = s_raw + buf * BUF_ELEMS;
+    __nv_bfloat16* b_h = b_dz + REG_ELEMS;
+    __nv_bfloat16* b_x = b_h + REG_ELEMS;
+    const size_t img_o = (size_t)n * p.Ho * p.Wo * p.ldc;
+#pragma unroll 2
+    for (int idx = tid; idx < NVR; idx += 256) {
+      const int pix = idx / V8, g = idx % V8;
+      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
+      const int c = cbase + g * 8;
+      const bool ok = (unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C;
+      const size_t o = ok ? img_o + (unsigned)((oy * p.Wo + ox) * p.ldc + c) : 0;
+      cp_async16(b_dz + pix * CT + g * 8, p.dz + o, ok ? 16 : 0);
+      cp_async16(b_h + pix * CT + g * 8, p.h + o, ok ? 16 : 0);
+    }
+    const size_t img_i = (size_t)n * p.H * p.W * p.ldc;
+    const int y0 = ty * TI, x0 = tx * TI;
+#pragma unroll 2
+    for (int idx = tid; idx < NVX; idx += 256) {
+      const int pix = idx / V8, g = idx % V8;
+      const int y = y0 + pix / TI, x = x0 + pix % TI;
+      const int c = cbase + g * 8;
+      const bool ok = y < p.H && x < p.W && c < p.C;
+      const size_t o = ok ? img_i + (unsigned)((y * p.W + x) * p.ldc + c) : 0;
+      cp_async16(b_x + pix * CT + g * 8, p.x + o, ok ? 16 : 0);
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  __syncthreads();
+  if (t < (unsigned)p.num_tiles) prefetch(t, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (; t < (unsigned)p.num_tiles; t += gridDim.x, buf ^= 1) {
+    int chunk, n, ty, tx, ry0, rx0;
+    decode(t, chunk, n, ty, tx);
+    region_origin(ty, tx, ry0, rx0);
     const int cbase = chunk * CT;
     const int c0 = cbase + cg * 4;
     const bool cvalid = c0 < p.C;
@@ -352,59 +442,42 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
       cur_chunk = chunk;
     }
     const int y0 = ty * TI, x0 = tx * TI;
-    // first output row / col whose receptive field reaches this input tile
-    const int ry0 = S == 1 ? y0 - P : (y0 - P + 1) >> 1;   // ceil((y0-P)/2), also right for < 0
-    const int rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
+    __syncthreads();  // previous tile's compute is done with the buffer the prefetch overwrites
+    {
+      const unsigned tn = t + gridDim.x;
+      if (tn < (unsigned)p.num_tiles) prefetch(tn, buf ^ 1);
+      cp_async_commit();
+    }
+    cp_async_wait<1>();
     __syncthreads();
-    // ---- stage dh = ca*dz + cb*h + cc over the gradient region (0 outside the image) ----
-    // 16-byte (8-channel) vectors; 2 x 2 independent global loads in flight per thread
-    constexpr int V8 = CT / 8;
-    constexpr int NV = RMAX * RMAX * V8;
-    const size_t img_o = (size_t)n * p.Ho * p.Wo * p.ldc;
-#pragma unroll 1
-    for (int base = tid; base < NV; base += 2 * 256) {
-      uint4 rdz[2], rh[2];
-      int cc2[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int idx = base + u * 256;
-        const int pix = idx / V8, g = idx % V8;
-        const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
-        const int c = cbase + g * 8;
-        cc2[u] = -1;
-        rdz[u] = rh[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (idx < NV && (unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C) {
-          const size_t o = img_o + (unsigned)((oy * p.Wo + ox) * p.ldc + c);
-          cc2[u] = c;
-          rdz[u] = __ldg(reinterpret_cast<const uint4*>(p.dz + o));
-          rh[u] = __ldg(reinterpret_cast<const uint4*>(p.h + o));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int idx = base + u * 256;
-        if (idx >= NV) break;
-        float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
-        if (cc2[u] >= 0) {
-          const int c = cc2[u];
-          const float4 ca0 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
-          const float4 ca1 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c + 4);
-          const float4 cb0 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
-          const float4 cb1 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c + 4);
-          const float4 cc0 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
-          const float4 cc1 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c + 4);
-          d0.x = fmaf(ca0.x, bf16lo(rdz[u].x), fmaf(cb0.x, bf16lo(rh[u].x), cc0.x));
-          d0.y = fmaf(ca0.y, bf16hi(rdz[u].x), fmaf(cb0.y, bf16hi(rh[u].x), cc0.y));
-          d0.z = fmaf(ca0.z, bf16lo(rdz[u].y), fmaf(cb0.z, bf16lo(rh[u].y), cc0.z));
-          d0.w = fmaf(ca0.w, bf16hi(rdz[u].y), fmaf(cb0.w, bf16hi(rh[u].y), cc0.w));
-          d1.x = fmaf(ca1.x, bf16lo(rdz[u].z), fmaf(cb1.x, bf16lo(rh[u].z), cc1.x));
-          d1.y = fmaf(ca1.y, bf16hi(rdz[u].z), fmaf(cb1.y, bf16hi(rh[u].z), cc1.y));
-          d1.z = fmaf(ca1.z, bf16lo(rdz[u].w), fmaf(cb1.z, bf16lo(rh[u].w), cc1.z));
-          d1.w = fmaf(ca1.w, bf16hi(rdz[u].w), fmaf(cb1.w, bf16hi(rh[u].w), cc1.w));
-        }
-        float* dst = s_dh + (idx / V8) * CT + (idx % V8) * 8;
-        *reinterpret_cast<float4*>(dst) = d0;
-        *reinterpret_cast<float4*>(dst + 4) = d1;
+    __nv_bfloat16* b_dz = s_raw + buf * BUF_ELEMS;
+    const __nv_bfloat16* b_h = b_dz + REG_ELEMS;
+    const __nv_bfloat16* b_x = b_h + REG_ELEMS;
+    // ---- dh = ca*dz + cb*h + cc in place over the gradient region (0 outside the image) ----
+#pragma unroll 2
+    for (int idx = tid; idx < NVR; idx += 256) {
+      const int pix = idx / V8, g = idx % V8;
+      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
+      const int c = cbase + g * 8;
+      if ((unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C) {
+        uint4* q = reinterpret_cast<uint4*>(b_dz + pix * CT + g * 8);
+        const uint4 rdz = *q;
+        const uint4 rh = *reinterpret_cast<const uint4*>(b_h + pix * CT + g * 8);
+        const float4 ca0 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
+        const float4 ca1 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c + 4);
+        const float4 cb0 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
+        const float4 cb1 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c + 4);
+        const float4 cc0 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
+        const float4 cc1 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c + 4);
+        const float d0 = fmaf(ca0.x, bf16lo(rdz.x), fmaf(cb0.x, bf16lo(rh.x), cc0.x));
+        const float d1 = fmaf(ca0.y, bf16hi(rdz.x), fmaf(cb0.y, bf16hi(rh.x), cc0.y));
+        const float d2 = fmaf(ca0.z, bf16lo(rdz.y), fmaf(cb0.z, bf16lo(rh.y), cc0.z));
+        const float d3 = fmaf(ca0.w, bf16hi(rdz.y), fmaf(cb0.w, bf16hi(rh.y), cc0.w));
+        const float d4 = fmaf(ca1.x, bf16lo(rdz.z), fmaf(cb1.x, bf16lo(rh.z), cc1.x));
+        const float d5 = fmaf(ca1.y, bf16hi(rdz.z), fmaf(cb1.y, bf16hi(rh.z), cc1.y));
+        const float d6 = fmaf(ca1.z, bf16lo(rdz.w), fmaf(cb1.z, bf16lo(rh.w), cc1.z));
+        const float d7 = fmaf(ca1.w, bf16hi(rdz.w), fmaf(cb1.w, bf16hi(rh.w), cc1.w));
+        *q = make_uint4(pack_bf16(d0, d1), pack_bf16(d2, d3), pack_bf16(d4, d5), pack_bf16(d6, d7));
       }
     }
     __syncthreads();
@@ -418,78 +491,73 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(const __g
       rs = *reinterpret_cast<const float4*>(s_tab + 6 * p.C + c0);
     }
     const size_t img_in = (size_t)n * p.H * p.W * p.ldc + c0;
-    const __nv_bfloat16* ximg = p.x + img_in;
 #pragma unroll 1
-    for (int ib = 0; ib < ITEMS; ib += IB) {
-      float xv[IB][4];
-      bool ok[IB];
+    for (int it = 0; it < ITEMS; ++it) {
+      const int pix = it * NPIX + pslot;
+      const int y = y0 + pix / TI, x = x0 + pix % TI;
+      if (!(cvalid && y < p.H && x < p.W)) continue;
+      const uint2 xr = *reinterpret_cast<const uint2*>(b_x + pix * CT + cg * 4);
+      const float xv[4] = {bf16lo(xr.x), bf16hi(xr.x), bf16lo(xr.y), bf16hi(xr.y)};
+      const float z[4] = {fmaf(sc.x, xv[0], sh.x), fmaf(sc.y, xv[1], sh.y),
+                          fmaf(sc.z, xv[2], sh.z), fmaf(sc.w, xv[3], sh.w)};
+      float a1[4] = {z[0], z[1], z[2], z[3]};
+      act_vec<4>(a1, ap);
+      if (p.in_scale) {  // the forward convolved the bf16-rounded activation
 #pragma unroll
-      for (int it = 0; it < IB; ++it) {  // batch the global loads of IB pixels
-        const int pix = (ib + it) * NPIX + pslot;
-        const int y = y0 + pix / TI, x = x0 + pix % TI;
-        ok[it] = cvalid && y < p.H && x < p.W;
-        if (ok[it]) ld4(ximg + (unsigned)((y * p.W + x) * p.ldc), xv[it]);
+        for (int v = 0; v < 4; ++v) a1[v] = round_bf16(a1[v]);
       }
+      const float2 a1lo = make_float2(a1[0], a1[1]), a1hi = make_float2(a1[2], a1[3]);
+      float2 da2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      // The staged region is zero outside the image and covers every tap of every pixel of the
+      // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
+      // parity test of the transposed convolution.
 #pragma unroll
-      for (int it = 0; it < IB; ++it) {
-        if (!ok[it]) continue;
-        const int pix = (ib + it) * NPIX + pslot;
-        const int y = y0 + pix / TI, x = x0 + pix % TI;
-        const float z[4] = {fmaf(sc.x, xv[it][0], sh.x), fmaf(sc.y, xv[it][1], sh.y),
-                            fmaf(sc.z, xv[it][2], sh.z), fmaf(sc.w, xv[it][3], sh.w)};
-        float a1[4] = {z[0], z[1], z[2], z[3]};
-        act_vec<4>(a1, ap);
-        const float2 a1lo = make_float2(a1[0], a1[1]), a1hi = make_float2(a1[2], a1[3]);
-        float2 da2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        // The staged region is zero outside the image and covers every tap of every pixel of the
-        // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
-        // parity test of the transposed convolution.
+      for (int ky = 0; ky < K; ++ky) {
+        const int yy = y + P - ky;
+        if (S == 2 && (yy & 1)) continue;
+        const int oy = S == 1 ? yy : yy >> 1;
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-          const int yy = y + P - ky;
-          if (S == 2 && (yy & 1)) continue;
-          const int oy = S == 1 ? yy : yy >> 1;
-#pragma unroll
-          for (int kx = 0; kx < K; ++kx) {
-            const int tp = ky * K + kx;  // compile-time after unrolling
-            if (!DGRAD && (tp < TAP0 || tp >= TAP1)) continue;
-            const int xx = x + P - kx;
-            if (S == 2 && (xx & 1)) continue;
-            const int ox = S == 1 ? xx : xx >> 1;
-            const float4 dh = *reinterpret_cast<const float4*>(
-                s_dh + ((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
-            const float2 dlo = make_float2(dh.x, dh.y), dhi = make_float2(dh.z, dh.w);
-            if (DGRAD) {
-              const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
-              da2[0] = ffma2(dlo, make_float2(wv.x, wv.y), da2[0]);
-              da2[1] = ffma2(dhi, make_float2(wv.z, wv.w), da2[1]);
-            }
-            if (tp >= TAP0 && tp < TAP1) {
-              gw[tp - TAP0][0] = ffma2(dlo, a1lo, gw[tp - TAP0][0]);
-              gw[tp - TAP0][1] = ffma2(dhi, a1hi, gw[tp - TAP0][1]);
-            }
+        for (int kx = 0; kx < K; ++kx) {
+          const int tp = ky * K + kx;  // compile-time after unrolling
+          if (!DGRAD && (tp < TAP0 || tp >= TAP1)) continue;
+          const int xx = x + P - kx;
+          if (S == 2 && (xx & 1)) continue;
+          const int ox = S == 1 ? xx : xx >> 1;
+          const uint2 dr = *reinterpret_cast<const uint2*>(
+              b_dz + ((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
+          const float2 dlo = make_float2(bf16lo(dr.x), bf16hi(dr.x));
+          const float2 dhi = make_float2(bf16lo(dr.y), bf16hi(dr.y));
+          if (DGRAD) {
+            const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
+            da2[0] = ffma2(dlo, make_float2(wv.x, wv.y), da2[0]);
+            da2[1] = ffma2(dhi, make_float2(wv.z, wv.w), da2[1]);
+          }
+          if (tp >= TAP0 && tp < TAP1) {
+            gw[tp - TAP0][0] = ffma2(dlo, a1lo, gw[tp - TAP0][0]);
+            gw[tp - TAP0][1] = ffma2(dhi, a1hi, gw[tp - TAP0][1]);
           }
         }
-        if (DGRAD) {
-          float da[4] = {da2[0].x, da2[0].y, da2[1].x, da2[1].y};
-          act_bwd_vec<4>(da, z, ap, act);
-          const size_t off = img_in + (unsigned)((y * p.W + x) * p.ldc);
-          if (p.residual) {
-            float rv[4];
-            ld4(p.residual + off, rv);
+      }
+      if (DGRAD) {
+        float da[4] = {da2[0].x, da2[0].y, da2[1].x, da2[1].y};
+        act_bwd_vec<4>(da, z, ap, act);
+        const size_t off = img_in + (unsigned)((y * p.W + x) * p.ldc);
+        if (p.residual) {
+          float rv[4];
+          ld4(p.residual + off, rv);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) da[v] += rv[v];
-          }
-          st4_round(p.dx + off, da);
-          ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
-          ssq[0] = fmaf(da[0], (xv[it][0] - mu.x) * rs.x, ssq[0]);
-          ssq[1] = fmaf(da[1], (xv[it][1] - mu.y) * rs.y, ssq[1]);
-          ssq[2] = fmaf(da[2], (xv[it][2] - mu.z) * rs.z, ssq[2]);
-          ssq[3] = fmaf(da[3], (xv[it][3] - mu.w) * rs.w, ssq[3]);
+          for (int v = 0; v < 4; ++v) da[v] += rv[v];
         }
+        st4_round(p.dx + off, da);
+        ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
+        ssq[0] = fmaf(da[0], (xv[0] - mu.x) * rs.x, ssq[0]);
+        ssq[1] = fmaf(da[1], (xv[1] - mu.y) * rs.y, ssq[1]);
+        ssq[2] = fmaf(da[2], (xv[2] - mu.z) * rs.z, ssq[2]);
+        ssq[3] = fmaf(da[3], (xv[3] - mu.w) * rs.w, ssq[3]);
       }
     }
   }
+  cp_async_wait<0>();
   if (cur_chunk >= 0) flush(cur_chunk);
   __syncthreads();
   for (int i = tid; i < K * K * p.C; i += 256) {
@@ -620,7 +688,7 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   p.residual = (const __nv_bfloat16*)a->residual;
   p.has_bn = a->bn ? 1 : 0;
   if (a->bn) p.bn = *a->bn;
-  const int ti = s == 1 ? 8 : 16;
+  const int ti = 8;
   const int rmax = s == 1 ? ti + k - 1 : (ti + k - 1) / 2 + 1;
   p.tiles_h = (a->H + ti - 1) / ti;
   p.tiles_w = (a->W + ti - 1) / ti;
@@ -630,8 +698,9 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
     if (nt > 0x7fffffffLL) return set_error(YAMB_EINVAL, "depthwise: too many tiles");
     p.num_tiles = (int)nt;
   }
+  // two staging buffers of bf16 {dz, h over the region; x over the tile} + fp32 tables
   const size_t smem =
-      ((size_t)rmax * rmax * ct + (size_t)(7 + 2 * k * k + 2) * a->C) * sizeof(float);
+      ((size_t)(2 * rmax * rmax + ti * ti) * ct + (size_t)(7 + 2 * k * k + 2) * a->C) * sizeof(float);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");
   cudaError_t e;
   if (k == 3 && s == 1 && ct == 64) YAMB_DW_BWD(3, 1, 64, p, smem, p.num_tiles, st);
