@@ -1,0 +1,122 @@
+"""Turn the ncu CSV exports brought back from the GPU box (gpurun_out/<round>_*.csv) into the
+committed evidence under profiles/:
+  <round>_launches_step.csv      every launch of one training step: time + DRAM bytes (trimmed)
+  <round>_step_summary.md        per-kernel-class totals and shares of the step
+  <round>_ncu_b3_summary.md      --set full highlights of one block's kernels
+  traffic.json                   measured DRAM bytes per launch per kernel class (bench.py reads it)
+Usage: python profiles/summarize.py r01
+"""
+import csv
+import json
+import os
+import re
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+
+
+def tag_of(name, prev_gemm=[0]):
+    if "dw_fwd_kernel" in name:
+        return "dw_fwd"
+    if "dw_bwd_kernel" in name:
+        return "dw_bwd"
+    if "gemm_tc_kernel" in name:
+        return "pw_gemm"
+    for k in ("bn_apply", "bn_reduce", "se_pool", "se_bwd_reduce", "se_bwd_apply", "rmsprop",
+              "ema_kernel", "cast_bf16"):
+        if k in name:
+            return k
+    return "torch:" + re.sub(r"<.*", "", name.replace("void ", ""))[:48]
+
+
+def read_ncu_csv(path):
+    rows = list(csv.reader(open(path)))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    return rows[hi], rows[hi + 2:]
+
+
+def step(rnd):
+    path = os.path.join(SRC, rnd + "_launches_step.csv")
+    hdr, body = read_ncu_csv(path)
+    col = {h: i for i, h in enumerate(hdr)}
+    # long format: one row per (launch, metric)
+    launches = {}
+    for r in body:
+        if len(r) < len(hdr):
+            continue
+        lid = int(r[col["ID"]])
+        d = launches.setdefault(lid, {"name": r[col["Kernel Name"]]})
+        d[r[col["Metric Name"]]] = (float(r[col["Metric Value"]].replace(",", "")),
+                                    r[col["Metric Unit"]])
+    def to_bytes(v):
+        val, unit = v
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        return val * mult
+    def to_us(v):
+        val, unit = v
+        return val * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(unit, 1)
+    agg, lines = {}, []
+    for lid in sorted(launches):
+        d = launches[lid]
+        t = to_us(d["gpu__time_duration.sum"])
+        rd = to_bytes(d["dram__bytes_read.sum"])
+        wr = to_bytes(d["dram__bytes_write.sum"])
+        tg = tag_of(d["name"])
+        a = agg.setdefault(tg, {"us": 0.0, "dram": 0.0, "n": 0})
+        a["us"] += t
+        a["dram"] += rd + wr
+        a["n"] += 1
+        lines.append((lid, tg, d["name"][:70], round(t, 2), int(rd), int(wr)))
+    with open(os.path.join(OUT, rnd + "_launches_step.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["id", "class", "kernel", "time_us", "dram_read_bytes", "dram_write_bytes"])
+        w.writerows(lines)
+    tot = sum(a["us"] for a in agg.values())
+    ours = sum(a["us"] for k, a in agg.items() if not k.startswith("torch:"))
+    with open(os.path.join(OUT, rnd + "_step_summary.md"), "w") as f:
+        f.write("# %s — one eager MobileNetV2-1.0 training step under ncu (N=256, B200)\n\n" % rnd)
+        f.write("`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                "--clock-control none` over `tests/gpu_step_once.py` (serialised, cold caches: "
+                "use the SHARES).  %d launches, %.2f ms of kernel time, %.1f %% in this repo's "
+                "kernels.\n\n" % (len(lines), tot / 1e3, 100 * ours / tot))
+        f.write("| class | launches | time ms | share | DRAM GB | DRAM GB/s |\n|---|---|---|---|---|---|\n")
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"])[:30]:
+            f.write("| %s | %d | %.3f | %.1f %% | %.3f | %.0f |\n" % (
+                k, a["n"], a["us"] / 1e3, 100 * a["us"] / tot, a["dram"] / 1e9,
+                a["dram"] / (a["us"] * 1e-6) / 1e9 if a["us"] else 0))
+    traffic = {k: a["dram"] / a["n"] for k, a in agg.items() if not k.startswith("torch:")}
+    json.dump(traffic, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+    print("step:", len(lines), "launches", round(tot / 1e3, 2), "ms")
+
+
+def block(rnd):
+    path = os.path.join(SRC, rnd + "_ncu_b3_raw.csv")
+    if not os.path.exists(path):
+        return
+    hdr, body = read_ncu_csv(path)
+    col = {h: i for i, h in enumerate(hdr)}
+    want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
+            ("dram__bytes_write.sum", "dram wr"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+            ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+    with open(os.path.join(OUT, rnd + "_ncu_b3_summary.md"), "w") as f:
+        f.write("# %s — ncu --set full, block b3 (24->144->24, 56x56, N=256) forward+backward\n\n" % rnd)
+        f.write("| kernel | " + " | ".join(w[1] for w in want) + " |\n|---|" + "---|" * len(want) + "\n")
+        for r in body:
+            if len(r) < len(hdr) or "yamb::" not in r[col["Kernel Name"]]:
+                continue
+            name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("void yamb::", ""))[:44]
+            f.write("| %s | " % name + " | ".join(r[col[w[0]]] if w[0] in col else "-" for w in want) + " |\n")
+    print("block summary written")
+
+
+if __name__ == "__main__":
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    step(rnd)
+    block(rnd)

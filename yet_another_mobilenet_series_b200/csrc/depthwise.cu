@@ -139,11 +139,15 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     }
   };
 
-  unsigned t = blockIdx.x;
-  if (t < (unsigned)p.num_tiles) prefetch(t, 0);
+  // Each CTA walks a CONTIGUOUS range of tiles (row-major inside an image): the halo a tile
+  // shares with its left / upper neighbours was fetched by the same SM a few tiles earlier and is
+  // still in L2, instead of being requested by two SMs at the same instant.
+  const unsigned t_end = (unsigned)(((unsigned long long)(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
+  unsigned t = (unsigned)(((unsigned long long)blockIdx.x * p.num_tiles) / gridDim.x);
+  if (t < t_end) prefetch(t, 0);
   cp_async_commit();
   int buf = 0;
-  for (; t < (unsigned)p.num_tiles; t += gridDim.x, buf ^= 1) {
+  for (; t < t_end; ++t, buf ^= 1) {
     int chunk, n, ty, tx;
     decode(t, chunk, n, ty, tx);
     const int cbase = chunk * CT;
@@ -176,8 +180,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
     __syncthreads();  // everyone is done computing from the buffer the next prefetch overwrites
     {
-      const unsigned tn = t + gridDim.x;
-      if (tn < (unsigned)p.num_tiles) prefetch(tn, buf ^ 1);
+      if (t + 1 < t_end) prefetch(t + 1, buf ^ 1);
       cp_async_commit();
     }
     cp_async_wait<1>();  // this tile's copies (the older group) have landed
@@ -425,12 +428,14 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     }
   };
 
-  unsigned t = blockIdx.x;
+  // contiguous tile range per CTA (halo reuse in L2, see the forward kernel)
+  const unsigned t_end = (unsigned)(((unsigned long long)(blockIdx.x + 1) * p.num_tiles) / gridDim.x);
+  unsigned t = (unsigned)(((unsigned long long)blockIdx.x * p.num_tiles) / gridDim.x);
   __syncthreads();
-  if (t < (unsigned)p.num_tiles) prefetch(t, 0);
+  if (t < t_end) prefetch(t, 0);
   cp_async_commit();
   int buf = 0;
-  for (; t < (unsigned)p.num_tiles; t += gridDim.x, buf ^= 1) {
+  for (; t < t_end; ++t, buf ^= 1) {
     int chunk, n, ty, tx, ry0, rx0;
     decode(t, chunk, n, ty, tx);
     region_origin(ty, tx, ry0, rx0);
@@ -444,8 +449,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     const int y0 = ty * TI, x0 = tx * TI;
     __syncthreads();  // previous tile's compute is done with the buffer the prefetch overwrites
     {
-      const unsigned tn = t + gridDim.x;
-      if (tn < (unsigned)p.num_tiles) prefetch(tn, buf ^ 1);
+      if (t + 1 < t_end) prefetch(t + 1, buf ^ 1);
       cp_async_commit();
     }
     cp_async_wait<1>();
