@@ -52,7 +52,7 @@ typedef void* yamb_stream_t; /* cudaStream_t */
  *   momentum < 0  => momentum=None in PyTorch: cumulative average with factor 1/num_batches_tracked
  *   (utils/common.py:175-187 bn_calibration). */
 typedef struct yamb_bn_fwd {
-  float* partials;              /* workspace, >= grid*2*C floats (see yamb_max_ctas) */
+  float* partials;              /* accumulator, >= 2*C floats, ZERO on entry, returned to zero */
   uint32_t* counter;            /* one zero-initialised word, self-resetting */
   const float* gamma;           /* [C] or NULL (=1) */
   const float* beta;            /* [C] or NULL (=0) */
@@ -236,8 +236,8 @@ int yamb_ema_update(float* shadow, const float* x, int64_t n, const float* hyper
 /* dst(bf16) = src(fp32) */
 int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t stream);
 
-/* upper bound of CTAs any statistics-producing kernel launches (sizes `partials`: 2*C floats
- * per CTA); 4 x SM count; <= 0 without a device */
+/* upper bound of CTAs any statistics-producing kernel launches; 4 x SM count; <= 0 without a
+ * device */
 int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,

@@ -133,13 +133,16 @@ def test_graph_replay_equals_eager(built_lib):
     out = []
     for use_graph in (True, False):
         m = _model(64).cuda()
+        for mod in m.modules():  # the dropout stream differs between capture and eager: switch it off
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
         ts = TrainStep(m, B, image_size=64, use_graph=use_graph)
         ls = [float(ts(x, t)) for _ in range(5)]
         torch.cuda.synchronize()
         out.append((ls, m.classifier[1].weight.detach().clone()))
     # identical first step; afterwards only fp32-atomic ordering differs between runs, which bf16
     # rounding flips amplify on this 8-image batch -> a loose bound on the trajectory
-    assert abs(out[0][0][0] - out[1][0][0]) < 1e-2 * abs(out[1][0][0])
+    assert abs(out[0][0][0] - out[1][0][0]) < 1e-3 * abs(out[1][0][0]), (out[0][0], out[1][0])
     for a, b in zip(out[0][0], out[1][0]):
         assert abs(a - b) < 1.5e-1 * abs(b), (out[0][0], out[1][0])
     assert _rel(out[0][1], out[1][1]) < 0.2

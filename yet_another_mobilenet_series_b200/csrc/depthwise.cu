@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     }
     __syncthreads();
     if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
-      bn_fwd_finalize(p.bn, p.C, gridDim.x);
+      bn_fwd_finalize(p.bn, p.C);
       __syncthreads();
       if (threadIdx.x == 0) *p.bn.counter = 0;
     }
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
   }
   if (p.has_bn && DGRAD) {
     if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
-      bn_bwd_finalize(p.bn, p.C, gridDim.x);
+      bn_bwd_finalize(p.bn, p.C);
       __syncthreads();
       if (threadIdx.x == 0) *p.bn.counter = 0;
     }

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ 
   }
   __syncthreads();
   if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
-    bn_bwd_finalize(p.bn, p.C, gridDim.x);
+    bn_bwd_finalize(p.bn, p.C);
     __syncthreads();
     if (threadIdx.x == 0) *p.bn.counter = 0;
   }
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) se_bwd_apply_kernel(const __grid_constant
   }
   __syncthreads();
   if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
-    bn_bwd_finalize(p.bn, p.C, gridDim.x);
+    bn_bwd_finalize(p.bn, p.C);
     __syncthreads();
     if (threadIdx.x == 0) *p.bn.counter = 0;
   }

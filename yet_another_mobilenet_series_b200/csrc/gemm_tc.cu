@@ -656,13 +656,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (p.has_bnf) {
     if (publish_partials(s_stats, p.N, p.bnf.partials, p.bnf.counter)) {
-      bn_fwd_finalize(p.bnf, p.N, gridDim.x);
+      bn_fwd_finalize(p.bnf, p.N);
       __syncthreads();
       if (threadIdx.x == 0) *p.bnf.counter = 0;
     }
   } else if (p.has_bnb) {
     if (publish_partials(s_stats, p.N, p.bnb.partials, p.bnb.counter)) {
-      bn_bwd_finalize(p.bnb, p.N, gridDim.x);
+      bn_bwd_finalize(p.bnb, p.N);
       __syncthreads();
       if (threadIdx.x == 0) *p.bnb.counter = 0;
     }
