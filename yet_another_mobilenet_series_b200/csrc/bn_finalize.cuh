@@ -18,15 +18,10 @@
 
 namespace yamb {
 
-// Add this CTA's partials (s_part: [2][C] in shared memory) to the global accumulator and return
-// true in the last CTA.  Must be called by ALL threads of the CTA.
-__device__ __forceinline__ bool publish_partials(const float* s_part, int C, float* partials,
-                                                 uint32_t* counter) {
+// Count this CTA as finished; true in the LAST CTA of the grid (whose later reads see every other
+// CTA's earlier global reductions).  Must be called by ALL threads of the CTA.
+__device__ __forceinline__ bool arrive_last(uint32_t* counter) {
   __shared__ uint32_t s_is_last;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float v = s_part[i];
-    if (v != 0.f) atomicAdd(partials + i, v);  // result unused -> RED.E.ADD.F32
-  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -36,6 +31,17 @@ __device__ __forceinline__ bool publish_partials(const float* s_part, int C, flo
   __syncthreads();
   if (s_is_last) __threadfence();
   return s_is_last != 0;
+}
+
+// Add this CTA's partials (s_part: [2][C] in shared memory) to the global accumulator and return
+// true in the last CTA.  Must be called by ALL threads of the CTA.
+__device__ __forceinline__ bool publish_partials(const float* s_part, int C, float* partials,
+                                                 uint32_t* counter) {
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float v = s_part[i];
+    if (v != 0.f) atomicAdd(partials + i, v);  // result unused -> RED.E.ADD.F32
+  }
+  return arrive_last(counter);
 }
 
 // Read-and-clear one total (L2 is the point of coherence for the reductions above).

@@ -54,14 +54,16 @@ struct DwFwdDev {
   int num_tiles;
 };
 
-// CT channels per tile (32 or 64); 256 threads = NCG channel groups x NSTRIP vertical strips.
-template <int K, int S, int CT>
+// CT channels per tile (32 or 64); 256 threads = NCG channel groups x NSTRIP spatial threads, each
+// computing TH x TW outputs of 4 channels from registers (every shared-memory load feeds up to
+// K*K/S^2 FMAs: the stencil is bound by issue slots and shared-memory bandwidth, not by HBM).
+template <int K, int S, int CT, int TW>
 struct FwdGeom {
   static constexpr int TH = 4;                    // output rows per thread
   static constexpr int NCG = CT / 4;
   static constexpr int NSTRIP = 256 / NCG;
-  static constexpr int TOW = 8;
-  static constexpr int TOH = NSTRIP / TOW * TH;   // 8 (CT=64) or 16 (CT=32)
+  static constexpr int TOW = 8 * TW;
+  static constexpr int TOH = NSTRIP / 8 * TH;     // 8 (CT=64) or 16 (CT=32)
   static constexpr int IH = (TOH - 1) * S + K;
   static constexpr int IW = (TOW - 1) * S + K;
 };
@@ -77,36 +79,34 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Forward, v3: the raw bf16 input tile (with halo) of tile t+1 streams into shared memory with
+// Forward, v4: the raw bf16 input tile (with halo) of tile t+1 streams into shared memory with
 // cp.async (zero-fill outside the image) while tile t is transformed IN PLACE (BN + activation,
 // rounded to bf16 like every other materialised activation) and convolved.
-template <int K, int S, int CT>
-__global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
+template <int K, int S, int CT, int TW>
+__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_fwd_kernel(
     const __grid_constant__ DwFwdDev p) {
-  using G = FwdGeom<K, S, CT>;
+  using G = FwdGeom<K, S, CT, TW>;
   constexpr int P = (K - 1) / 2;
   constexpr int TH = G::TH, NCG = G::NCG, IH = G::IH, IW = G::IW;
-  constexpr int IR = (TH - 1) * S + K;
+  constexpr int IR = (TH - 1) * S + K;     // input rows one thread reads
+  constexpr int IC = (TW - 1) * S + K;     // input columns one thread reads
   constexpr int V8 = CT / 8;               // 16-byte vectors per pixel
-  constexpr int NV = IH * IW * V8;
-  constexpr int TILE_ELEMS = IH * IW * CT;  // bf16 elements per staging buffer
+  constexpr int PSTEP = 256 / V8;          // pixels one pass of the CTA covers
+  constexpr int NPIX = IH * IW;
+  constexpr int TILE_ELEMS = NPIX * CT;    // bf16 elements per staging buffer
   extern __shared__ __align__(16) float smem_f[];
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(smem_f);  // [2][TILE_ELEMS]
-  float* s_sc = smem_f + TILE_ELEMS;       // 2 * TILE_ELEMS bf16 == TILE_ELEMS floats
-  float* s_sh = s_sc + p.C;
-  float* s_part = s_sh + p.C;              // [2][C]
+  float* s_part = smem_f + TILE_ELEMS;     // [2][CT] statistics of the current channel chunk
   const int tid = threadIdx.x;
-  for (int i = tid; i < p.C; i += 256) {
-    s_sc[i] = p.in_scale ? __ldg(p.in_scale + i) : 1.f;
-    s_sh[i] = p.in_scale ? __ldg(p.in_shift + i) : 0.f;
-  }
-  for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
+  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.f;
   const ActParam ap = make_act(p.in_scale ? p.in_act : ACT_NONE);
   const bool identity = p.in_scale == nullptr;
   const int cg = tid % NCG;
   const int strip = tid / NCG;
-  const int sx = strip % G::TOW, sy = strip / G::TOW;
+  const int sx = strip % 8, sy = strip / 8;
+  const int g8 = tid % V8, pslot = tid / V8;   // staging / transform role: fixed 8-channel group
   float2 wreg[K * K][2];
+  float sc8[8], sh8[8];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
   int cur_chunk = -1;
   const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
@@ -125,18 +125,46 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     int chunk, n, ty, tx;
     decode(t, chunk, n, ty, tx);
     const int iy0 = ty * G::TOH * S - P, ix0 = tx * G::TOW * S - P;
-    const int cbase = chunk * CT;
-    const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc;
-    __nv_bfloat16* dst = s_raw + buf * TILE_ELEMS;
+    const int c = chunk * CT + g8 * 8;
+    const bool cok = c < p.C;
+    const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * p.ldc + c;
+    __nv_bfloat16* dst = s_raw + buf * TILE_ELEMS + g8 * 8;
 #pragma unroll 4
-    for (int idx = tid; idx < NV; idx += 256) {
-      const int pix = idx / V8, g = idx % V8;
+    for (int pix = pslot; pix < NPIX; pix += PSTEP) {
       const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
-      const int c = cbase + g * 8;
-      const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C;
-      const __nv_bfloat16* src = ok ? img + (unsigned)((iy * p.W + ix) * p.ldc + c) : p.x;
-      cp_async16(dst + pix * CT + g * 8, src, ok ? 16 : 0);
+      const bool ok = cok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+      const __nv_bfloat16* src = ok ? img + (unsigned)((iy * p.W + ix) * p.ldc) : p.x;
+      cp_async16(dst + pix * CT, src, ok ? 16 : 0);
     }
+  };
+  // per-chunk statistics: registers -> shared (once per chunk) -> one global reduction per channel
+  auto flush_stats = [&](int chunk) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float a = ssum[v], b = ssq[v];
+      if (NCG == 16) {  // lanes l and l+16 own the same channels
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        b += __shfl_xor_sync(0xffffffffu, b, 16);
+      } else {
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        b += __shfl_xor_sync(0xffffffffu, b, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+        b += __shfl_xor_sync(0xffffffffu, b, 16);
+      }
+      if ((tid & 31) < NCG) {
+        atomicAdd(&s_part[cg * 4 + v], a);
+        atomicAdd(&s_part[CT + cg * 4 + v], b);
+      }
+      ssum[v] = ssq[v] = 0.f;
+    }
+    __syncthreads();
+    if (tid < 2 * CT) {
+      const int c = chunk * CT + (tid % CT);
+      const float v = s_part[tid];
+      if (c < p.C && v != 0.f) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
+      s_part[tid] = 0.f;
+    }
+    __syncthreads();
   };
 
   // Each CTA walks a CONTIGUOUS range of tiles (row-major inside an image): the halo a tile
@@ -154,17 +182,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     const int c0 = cbase + cg * 4;
     const bool cvalid = c0 < p.C;
     if (chunk != cur_chunk) {
-      if (cur_chunk >= 0 && p.has_bn) {
-        const int pc = cur_chunk * CT + cg * 4;
-        if (pc < p.C) {
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            atomicAdd(&s_part[pc + v], ssum[v]);
-            atomicAdd(&s_part[p.C + pc + v], ssq[v]);
-            ssum[v] = ssq[v] = 0.f;
-          }
-        }
-      }
+      if (cur_chunk >= 0 && p.has_bn) flush_stats(cur_chunk);
       cur_chunk = chunk;
 #pragma unroll
       for (int tp = 0; tp < K * K; ++tp) {
@@ -174,6 +192,13 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
           wv[v] = cvalid ? __ldg(p.w + (size_t)(c0 + v) * K * K + tp) : 0.f;
         wreg[tp][0] = make_float2(wv[0], wv[1]);
         wreg[tp][1] = make_float2(wv[2], wv[3]);
+      }
+      const int c8 = cbase + g8 * 8;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const bool ok = !identity && c8 + v < p.C;
+        sc8[v] = ok ? __ldg(p.in_scale + c8 + v) : 1.f;
+        sh8[v] = ok ? __ldg(p.in_shift + c8 + v) : 0.f;
       }
     }
     const int oy0 = ty * G::TOH, ox0 = tx * G::TOW;
@@ -188,22 +213,17 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
     __nv_bfloat16* tile = s_raw + buf * TILE_ELEMS;
     // ---- in-place BN + activation (bf16 -> fp32 -> bf16); padding / halo stays exactly 0 ----
     if (!identity) {
+      const bool cok = cbase + g8 * 8 < p.C;
 #pragma unroll 2
-      for (int idx = tid; idx < NV; idx += 256) {
-        const int pix = idx / V8, g = idx % V8;
+      for (int pix = pslot; pix < NPIX; pix += PSTEP) {
         const int iy = iy0 + pix / IW, ix = ix0 + pix % IW;
-        const int c = cbase + g * 8;
-        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W && c < p.C) {
-          uint4* q = reinterpret_cast<uint4*>(tile + pix * CT + g * 8);
+        if (cok && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) {
+          uint4* q = reinterpret_cast<uint4*>(tile + pix * CT + g8 * 8);
           const uint4 raw = *q;
-          const float4 s0 = *reinterpret_cast<const float4*>(s_sc + c);
-          const float4 s1 = *reinterpret_cast<const float4*>(s_sc + c + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(s_sh + c);
-          const float4 h1 = *reinterpret_cast<const float4*>(s_sh + c + 4);
-          float e8[8] = {fmaf(s0.x, bf16lo(raw.x), h0.x), fmaf(s0.y, bf16hi(raw.x), h0.y),
-                         fmaf(s0.z, bf16lo(raw.y), h0.z), fmaf(s0.w, bf16hi(raw.y), h0.w),
-                         fmaf(s1.x, bf16lo(raw.z), h1.x), fmaf(s1.y, bf16hi(raw.z), h1.y),
-                         fmaf(s1.z, bf16lo(raw.w), h1.z), fmaf(s1.w, bf16hi(raw.w), h1.w)};
+          float e8[8] = {fmaf(sc8[0], bf16lo(raw.x), sh8[0]), fmaf(sc8[1], bf16hi(raw.x), sh8[1]),
+                         fmaf(sc8[2], bf16lo(raw.y), sh8[2]), fmaf(sc8[3], bf16hi(raw.y), sh8[3]),
+                         fmaf(sc8[4], bf16lo(raw.z), sh8[4]), fmaf(sc8[5], bf16hi(raw.z), sh8[5]),
+                         fmaf(sc8[6], bf16lo(raw.w), sh8[6]), fmaf(sc8[7], bf16hi(raw.w), sh8[7])};
           act_vec<8>(e8, ap);
           *q = make_uint4(pack_bf16(e8[0], e8[1]), pack_bf16(e8[2], e8[3]),
                           pack_bf16(e8[4], e8[5]), pack_bf16(e8[6], e8[7]));
@@ -211,46 +231,52 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
       }
       __syncthreads();
     }
-    // ---- stencil: TH output rows x 4 channels per thread (packed fp32x2 FMAs) ----
-    float2 acc2[TH][2];
+    // ---- stencil: TH x TW outputs x 4 channels per thread (packed fp32x2 FMAs) ----
+    float2 acc2[TH][TW][2];
 #pragma unroll
-    for (int j = 0; j < TH; ++j) acc2[j][0] = acc2[j][1] = make_float2(0.f, 0.f);
+    for (int j = 0; j < TH; ++j)
+#pragma unroll
+      for (int i = 0; i < TW; ++i) acc2[j][i][0] = acc2[j][i][1] = make_float2(0.f, 0.f);
+    const __nv_bfloat16* tbase = tile + ((sy * TH * S) * IW + sx * TW * S) * CT + cg * 4;
 #pragma unroll
     for (int rr = 0; rr < IR; ++rr) {
 #pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        const uint2 a = *reinterpret_cast<const uint2*>(
-            tile + ((sy * TH * S + rr) * IW + sx * S + dx) * CT + cg * 4);
+      for (int cc = 0; cc < IC; ++cc) {
+        const uint2 a = *reinterpret_cast<const uint2*>(tbase + (rr * IW + cc) * CT);
         const float2 alo = make_float2(bf16lo(a.x), bf16hi(a.x));
         const float2 ahi = make_float2(bf16lo(a.y), bf16hi(a.y));
 #pragma unroll
         for (int j = 0; j < TH; ++j) {
           const int ky = rr - j * S;  // compile-time after unrolling
           if (ky >= 0 && ky < K) {
-            acc2[j][0] = ffma2(wreg[ky * K + dx][0], alo, acc2[j][0]);
-            acc2[j][1] = ffma2(wreg[ky * K + dx][1], ahi, acc2[j][1]);
+#pragma unroll
+            for (int i = 0; i < TW; ++i) {
+              const int kx = cc - i * S;
+              if (kx >= 0 && kx < K) {
+                acc2[j][i][0] = ffma2(wreg[ky * K + kx][0], alo, acc2[j][i][0]);
+                acc2[j][i][1] = ffma2(wreg[ky * K + kx][1], ahi, acc2[j][i][1]);
+              }
+            }
           }
         }
       }
     }
-    float acc[TH][4];
-#pragma unroll
-    for (int j = 0; j < TH; ++j) {
-      acc[j][0] = acc2[j][0].x; acc[j][1] = acc2[j][0].y;
-      acc[j][2] = acc2[j][1].x; acc[j][3] = acc2[j][1].y;
-    }
-    const int ox = ox0 + sx;
-    if (cvalid && ox < p.Wo) {
+    if (cvalid) {
       __nv_bfloat16* yimg = p.y + (size_t)n * p.Ho * p.Wo * p.ldc + c0;
 #pragma unroll
       for (int j = 0; j < TH; ++j) {
         const int oy = oy0 + sy * TH + j;
-        if (oy < p.Ho) {
-          st4_round(yimg + (unsigned)((oy * p.Wo + ox) * p.ldc), acc[j]);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            ssum[v] += acc[j][v];
-            ssq[v] = fmaf(acc[j][v], acc[j][v], ssq[v]);
+        for (int i = 0; i < TW; ++i) {
+          const int ox = ox0 + sx * TW + i;
+          if (oy < p.Ho && ox < p.Wo) {
+            float acc[4] = {acc2[j][i][0].x, acc2[j][i][0].y, acc2[j][i][1].x, acc2[j][i][1].y};
+            st4_round(yimg + (unsigned)((oy * p.Wo + ox) * p.ldc), acc);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              ssum[v] += acc[v];
+              ssq[v] = fmaf(acc[v], acc[v], ssq[v]);
+            }
           }
         }
       }
@@ -258,18 +284,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? 3 : 1)) dw_fwd_kernel(
   }
   cp_async_wait<0>();
   if (p.has_bn) {
-    if (cur_chunk >= 0) {
-      const int pc = cur_chunk * CT + cg * 4;
-      if (pc < p.C) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          atomicAdd(&s_part[pc + v], ssum[v]);
-          atomicAdd(&s_part[p.C + pc + v], ssq[v]);
-        }
-      }
-    }
-    __syncthreads();
-    if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
+    if (cur_chunk >= 0) flush_stats(cur_chunk);
+    if (arrive_last(p.bn.counter)) {
       bn_fwd_finalize(p.bn, p.C);
       __syncthreads();
       if (threadIdx.x == 0) *p.bn.counter = 0;
@@ -617,22 +633,6 @@ static cudaError_t launch_bwd(const Dev& p, size_t smem, long long tiles, cudaSt
 }
 #define YAMB_DW_BWD(KK, SS, CC, ...) e = launch_bwd<KK, SS, CC>(__VA_ARGS__)
 
-#define YAMB_DW_DISPATCH(KERN, ...)                                           \
-  do {                                                                        \
-    if (k == 3 && s == 1 && ct == 64) e = launch_k(KERN<3, 1, 64>, __VA_ARGS__);      \
-    else if (k == 3 && s == 2 && ct == 64) e = launch_k(KERN<3, 2, 64>, __VA_ARGS__); \
-    else if (k == 3 && s == 1) e = launch_k(KERN<3, 1, 32>, __VA_ARGS__);             \
-    else if (k == 3 && s == 2) e = launch_k(KERN<3, 2, 32>, __VA_ARGS__);             \
-    else if (k == 5 && s == 1 && ct == 64) e = launch_k(KERN<5, 1, 64>, __VA_ARGS__); \
-    else if (k == 5 && s == 2 && ct == 64) e = launch_k(KERN<5, 2, 64>, __VA_ARGS__); \
-    else if (k == 5 && s == 1) e = launch_k(KERN<5, 1, 32>, __VA_ARGS__);             \
-    else if (k == 5 && s == 2) e = launch_k(KERN<5, 2, 32>, __VA_ARGS__);             \
-    else if (k == 7 && s == 1 && ct == 64) e = launch_k(KERN<7, 1, 64>, __VA_ARGS__); \
-    else if (k == 7 && s == 2 && ct == 64) e = launch_k(KERN<7, 2, 64>, __VA_ARGS__); \
-    else if (k == 7 && s == 1) e = launch_k(KERN<7, 1, 32>, __VA_ARGS__);             \
-    else e = launch_k(KERN<7, 2, 32>, __VA_ARGS__);                                   \
-  } while (0)
-
 int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   if (!a) return set_error(YAMB_EINVAL, "null args");
   int rc = check_common(a->N, a->H, a->W, a->C, a->ldc, a->k, a->stride);
@@ -652,7 +652,8 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   if (a->bn) p.bn = *a->bn;
   if ((((uintptr_t)a->x) | ((uintptr_t)a->y)) & 15)
     return set_error(YAMB_EINVAL, "depthwise: activations must be 16-byte aligned");
-  const int toh = ct == 64 ? 8 : 16, tow = 8;
+  const int tw = (k == 7 || p.Wo <= 8) ? 1 : 2;
+  const int toh = ct == 64 ? 8 : 16, tow = 8 * tw;
   p.tiles_h = (p.Ho + toh - 1) / toh;
   p.tiles_w = (p.Wo + tow - 1) / tow;
   p.chunks = (a->C + ct - 1) / ct;
@@ -662,10 +663,18 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
     p.num_tiles = (int)nt;
   }
   const int ih = (toh - 1) * s + k, iw = (tow - 1) * s + k;
-  const size_t smem = ((size_t)ih * iw * ct + 4 * (size_t)a->C) * sizeof(float);
+  const size_t smem = (size_t)ih * iw * ct * sizeof(float) + 2 * (size_t)ct * sizeof(float);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise fwd: tile too large");
   cudaError_t e;
-  YAMB_DW_DISPATCH(dw_fwd_kernel, p, smem, p.num_tiles, st);
+#define YAMB_FWD_CASE(KK, SS, CC, TT) \
+  if (k == KK && s == SS && ct == CC && tw == TT) e = launch_k(dw_fwd_kernel<KK, SS, CC, TT>, p, smem, p.num_tiles, st)
+  e = cudaErrorInvalidValue;
+  YAMB_FWD_CASE(3, 1, 64, 1); YAMB_FWD_CASE(3, 1, 64, 2); YAMB_FWD_CASE(3, 2, 64, 1); YAMB_FWD_CASE(3, 2, 64, 2);
+  YAMB_FWD_CASE(3, 1, 32, 1); YAMB_FWD_CASE(3, 1, 32, 2); YAMB_FWD_CASE(3, 2, 32, 1); YAMB_FWD_CASE(3, 2, 32, 2);
+  YAMB_FWD_CASE(5, 1, 64, 1); YAMB_FWD_CASE(5, 1, 64, 2); YAMB_FWD_CASE(5, 2, 64, 1); YAMB_FWD_CASE(5, 2, 64, 2);
+  YAMB_FWD_CASE(5, 1, 32, 1); YAMB_FWD_CASE(5, 1, 32, 2); YAMB_FWD_CASE(5, 2, 32, 1); YAMB_FWD_CASE(5, 2, 32, 2);
+  YAMB_FWD_CASE(7, 1, 64, 1); YAMB_FWD_CASE(7, 2, 64, 1); YAMB_FWD_CASE(7, 1, 32, 1); YAMB_FWD_CASE(7, 2, 32, 1);
+#undef YAMB_FWD_CASE
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "dw fwd launch: %s", cudaGetErrorString(e));
   return 0;
 }
