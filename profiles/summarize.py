@@ -34,7 +34,10 @@ def tag_of(name, prev_gemm=[0]):
 def read_ncu_csv(path):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-    return rows[hi], rows[hi + 2:]
+    body = rows[hi + 1:]
+    if body and body[0] and not body[0][0].strip().isdigit():   # wide format: a units row follows
+        body = body[1:]
+    return rows[hi], body
 
 
 def step(rnd):

@@ -314,63 +314,73 @@ struct DwBwdDev {
   int num_tiles;
 };
 
-// Input-space tile TI x TI; the gradient region that touches it is at most RMAX x RMAX output
-// pixels.
-template <int K, int S>
+// Input-space CTA tile TIH x TIW made of 2x2-pixel thread tiles (aligned to even coordinates, so
+// with stride 2 every thread sees the same, compile-time parity pattern of the transposed
+// convolution); the gradient region that touches it is RH x RW output pixels.
+template <int K, int S, int CT>
 struct BwdGeom {
   static constexpr int P = (K - 1) / 2;
-  static constexpr int TI = 8;
-  static constexpr int RMAX = S == 1 ? TI + K - 1 : (TI + K - 1) / 2 + 1;
+  static constexpr int NCG = CT / 4;
+  static constexpr int NSP = 256 / NCG;        // spatial threads: 16 (CT=64) or 32 (CT=32)
+  static constexpr int TIW = 8;
+  static constexpr int TIH = NSP / 4 * 2;      // 8 or 16
+  static constexpr int RH = S == 1 ? TIH + K - 1 : (TIH + K - 1) / 2 + 1;
+  static constexpr int RW = S == 1 ? TIW + K - 1 : (TIW + K - 1) / 2 + 1;
+  static constexpr int R = S == 1 ? K + 1 : (K + 1) / 2;   // region rows/cols one thread tile reads
 };
+
+// Does tap index k (one axis) connect pixel offset a (0/1 inside the thread tile) with region
+// offset r (relative to the thread tile's first region row)?  Compile-time after unrolling.
+template <int K, int S>
+__device__ __forceinline__ constexpr bool tap_hits(int a, int k, int r) {
+  constexpr int P = (K - 1) / 2;
+  if (S == 1) return a + 2 * P - k == r;
+  const int d = a + P - k;
+  if (d & 1) return false;
+  return d / 2 + P / 2 == r;
+}
 
 // TAP0..TAP1: taps whose weight gradient this launch accumulates (all of them unless K == 7, where
 // 49 x 4 accumulators do not fit the register file and a second, wgrad-only launch covers the rest).
 // DGRAD: compute and store dx (+ statistics); false for that second launch.
 //
-// v3: the raw bf16 tiles of tile t+1 (dz and h over the gradient region, x over the input tile)
+// v4: the raw bf16 tiles of tile t+1 (dz and h over the gradient region, x over the input tile)
 // stream into shared memory with cp.async while tile t is processed; dh = ca*dz + cb*h + cc is
-// formed once per element, in place (bf16, like every other materialised gradient).
+// formed once per element, in place (bf16, like every other materialised gradient); a thread
+// gathers a 2x2 pixel tile from registers: every staged gradient vector feeds up to 4 dgrad and
+// 4 wgrad FMAs, all shared-memory offsets are immediates, no bounds or parity branches.
 template <int K, int S, int CT, int TAP0, int TAP1, bool DGRAD>
 __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     const __grid_constant__ DwBwdDev p) {
-  using G = BwdGeom<K, S>;
-  constexpr int P = G::P, TI = G::TI, RMAX = G::RMAX;
-  constexpr int NCG = CT / 4;
-  constexpr int NPIX = 256 / NCG;           // pixels processed concurrently
-  constexpr int ITEMS = TI * TI / NPIX;     // pixels per thread per tile
+  using G = BwdGeom<K, S, CT>;
+  constexpr int P = G::P, TIH = G::TIH, TIW = G::TIW, RH = G::RH, RW = G::RW, R = G::R;
+  constexpr int NCG = G::NCG;
   constexpr int NT = TAP1 - TAP0;
+  constexpr int KK = K * K;
   constexpr int V8 = CT / 8;
-  constexpr int NVR = RMAX * RMAX * V8;     // 16-byte vectors of one gradient-region tensor
-  constexpr int NVX = TI * TI * V8;         // 16-byte vectors of the input tile
-  constexpr int REG_ELEMS = RMAX * RMAX * CT;
-  constexpr int X_ELEMS = TI * TI * CT;
+  constexpr int PSTEP = 256 / V8;
+  constexpr int NPR = RH * RW;              // pixels of the gradient region
+  constexpr int NPX = TIH * TIW;            // pixels of the input tile
+  constexpr int REG_ELEMS = NPR * CT;
+  constexpr int X_ELEMS = NPX * CT;
   constexpr int BUF_ELEMS = 2 * REG_ELEMS + X_ELEMS;  // one staging buffer: dz | h | x
   extern __shared__ __align__(16) float smem_f[];
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(smem_f);  // [2][BUF_ELEMS]
-  float* s_tab = smem_f + BUF_ELEMS;         // 2 * BUF_ELEMS bf16 == BUF_ELEMS floats
-  float* s_w = s_tab + 7 * p.C;              // [K*K][C]
-  float* s_gw = s_w + K * K * p.C;           // [K*K][C]
-  float* s_part = s_gw + K * K * p.C;        // [2][C]
+  float* s_tab = smem_f + BUF_ELEMS;         // [7][CT]: in_scale, in_shift, ca, cb, cc, mean, invstd
+  float* s_w = s_tab + 7 * CT;               // [K*K][CT]
+  float* s_gw = s_w + KK * CT;               // [K*K][CT]
+  float* s_part = s_gw + KK * CT;            // [2][CT]
   const int tid = threadIdx.x;
-  for (int i = tid; i < p.C; i += 256) {
-    s_tab[i] = p.in_scale ? __ldg(p.in_scale + i) : 1.f;
-    s_tab[p.C + i] = p.in_scale ? __ldg(p.in_shift + i) : 0.f;
-    s_tab[2 * p.C + i] = __ldg(p.ca + i);
-    s_tab[3 * p.C + i] = __ldg(p.cb + i);
-    s_tab[4 * p.C + i] = __ldg(p.cc + i);
-    s_tab[5 * p.C + i] = p.has_bn ? __ldg(p.bn.mean + i) : 0.f;
-    s_tab[6 * p.C + i] = p.has_bn ? __ldg(p.bn.invstd + i) : 0.f;
-  }
-  for (int i = tid; i < K * K * p.C; i += 256) {
-    const int tp = i / p.C, c = i % p.C;
-    s_w[i] = __ldg(p.w + (size_t)c * K * K + tp);
-    s_gw[i] = 0.f;
-  }
-  for (int i = tid; i < 2 * p.C; i += 256) s_part[i] = 0.f;
+  for (int i = tid; i < KK * CT; i += 256) s_gw[i] = 0.f;
+  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.f;
   const int act = p.in_scale ? p.in_act : ACT_NONE;
   const ActParam ap = make_act(act);
   const int cg = tid % NCG;
-  const int pslot = tid / NCG;
+  const int sp = tid / NCG;
+  const int py = (sp / 4) * 2, px = (sp % 4) * 2;   // thread tile origin inside the CTA tile
+  const int g8 = tid % V8, pslot = tid / V8;        // staging / transform role
+  // first region row / column of the thread tile (see tap_hits)
+  const int rr0 = S == 1 ? py : py / 2, rc0 = S == 1 ? px : px / 2;
   float2 gw[NT][2];
   float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -379,24 +389,57 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
   const unsigned tiles_per_img = (unsigned)(p.tiles_h * p.tiles_w);
   const unsigned tiles_per_chunk = (unsigned)p.N * tiles_per_img;
 
+  // registers -> shared (per chunk) -> one global reduction per (tap, channel) / channel
   auto flush = [&](int chunk) {
-    const int pc = chunk * CT + cg * 4;
-    if (pc < p.C) {
 #pragma unroll
-      for (int tp = 0; tp < NT; ++tp) {
-        float* dst = &s_gw[(TAP0 + tp) * p.C + pc];
-        atomicAdd(dst + 0, gw[tp][0].x);
-        atomicAdd(dst + 1, gw[tp][0].y);
-        atomicAdd(dst + 2, gw[tp][1].x);
-        atomicAdd(dst + 3, gw[tp][1].y);
-        gw[tp][0] = gw[tp][1] = make_float2(0.f, 0.f);
-      }
+    for (int tp = 0; tp < NT; ++tp) {
+      float* dst = &s_gw[(TAP0 + tp) * CT + cg * 4];
+      atomicAdd(dst + 0, gw[tp][0].x);
+      atomicAdd(dst + 1, gw[tp][0].y);
+      atomicAdd(dst + 2, gw[tp][1].x);
+      atomicAdd(dst + 3, gw[tp][1].y);
+      gw[tp][0] = gw[tp][1] = make_float2(0.f, 0.f);
+    }
+    if (DGRAD) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        atomicAdd(&s_part[pc + v], ssum[v]);
-        atomicAdd(&s_part[p.C + pc + v], ssq[v]);
+        atomicAdd(&s_part[cg * 4 + v], ssum[v]);
+        atomicAdd(&s_part[CT + cg * 4 + v], ssq[v]);
         ssum[v] = ssq[v] = 0.f;
       }
+    }
+    __syncthreads();
+    const int cbase = chunk * CT;
+    for (int i = tid; i < KK * CT; i += 256) {
+      const int tp = i / CT, c = cbase + i % CT;
+      const float g = s_gw[i];
+      if (c < p.C && g != 0.f) atomicAdd(p.dw + (size_t)c * KK + tp, g);
+      s_gw[i] = 0.f;
+    }
+    if (DGRAD && p.has_bn && tid < 2 * CT) {
+      const int c = cbase + tid % CT;
+      const float v = s_part[tid];
+      if (c < p.C && v != 0.f) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
+      s_part[tid] = 0.f;
+    }
+    __syncthreads();
+  };
+  auto load_tables = [&](int chunk) {
+    const int cbase = chunk * CT;
+    for (int i = tid; i < CT; i += 256) {
+      const int c = cbase + i;
+      const bool ok = c < p.C;
+      s_tab[i] = ok && p.in_scale ? __ldg(p.in_scale + c) : 1.f;
+      s_tab[CT + i] = ok && p.in_scale ? __ldg(p.in_shift + c) : 0.f;
+      s_tab[2 * CT + i] = ok ? __ldg(p.ca + c) : 0.f;
+      s_tab[3 * CT + i] = ok ? __ldg(p.cb + c) : 0.f;
+      s_tab[4 * CT + i] = ok ? __ldg(p.cc + c) : 0.f;
+      s_tab[5 * CT + i] = ok && p.has_bn ? __ldg(p.bn.mean + c) : 0.f;
+      s_tab[6 * CT + i] = ok && p.has_bn ? __ldg(p.bn.invstd + c) : 0.f;
+    }
+    for (int i = tid; i < KK * CT; i += 256) {
+      const int tp = i / CT, c = cbase + i % CT;
+      s_w[i] = c < p.C ? __ldg(p.w + (size_t)c * KK + tp) : 0.f;
     }
   };
   auto decode = [&](unsigned t, int& chunk, int& n, int& ty, int& tx) {
@@ -408,7 +451,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     tx = (int)(r - (unsigned)ty * p.tiles_w);
   };
   auto region_origin = [&](int ty, int tx, int& ry0, int& rx0) {
-    const int y0 = ty * TI, x0 = tx * TI;
+    const int y0 = ty * TIH, x0 = tx * TIW;
     ry0 = S == 1 ? y0 - P : (y0 - P + 1) >> 1;   // ceil((y0-P)/2), also right for < 0
     rx0 = S == 1 ? x0 - P : (x0 - P + 1) >> 1;
   };
@@ -416,31 +459,28 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     int chunk, n, ty, tx, ry0, rx0;
     decode(t, chunk, n, ty, tx);
     region_origin(ty, tx, ry0, rx0);
-    const int cbase = chunk * CT;
-    __nv_bfloat16* b_dz = s_raw + buf * BUF_ELEMS;
+    const int c = chunk * CT + g8 * 8;
+    const bool cok = c < p.C;
+    __nv_bfloat16* b_dz = s_raw + buf * BUF_ELEMS + g8 * 8;
     __nv_bfloat16* b_h = b_dz + REG_ELEMS;
     __nv_bfloat16* b_x = b_h + REG_ELEMS;
-    const size_t img_o = (size_t)n * p.Ho * p.Wo * p.ldc;
+    const size_t img_o = (size_t)n * p.Ho * p.Wo * p.ldc + c;
 #pragma unroll 2
-    for (int idx = tid; idx < NVR; idx += 256) {
-      const int pix = idx / V8, g = idx % V8;
-      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
-      const int c = cbase + g * 8;
-      const bool ok = (unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C;
-      const size_t o = ok ? img_o + (unsigned)((oy * p.Wo + ox) * p.ldc + c) : 0;
-      cp_async16(b_dz + pix * CT + g * 8, p.dz + o, ok ? 16 : 0);
-      cp_async16(b_h + pix * CT + g * 8, p.h + o, ok ? 16 : 0);
+    for (int pix = pslot; pix < NPR; pix += PSTEP) {
+      const int oy = ry0 + pix / RW, ox = rx0 + pix % RW;
+      const bool ok = cok && (unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo;
+      const size_t o = ok ? img_o + (unsigned)((oy * p.Wo + ox) * p.ldc) : 0;
+      cp_async16(b_dz + pix * CT, p.dz + o, ok ? 16 : 0);
+      cp_async16(b_h + pix * CT, p.h + o, ok ? 16 : 0);
     }
-    const size_t img_i = (size_t)n * p.H * p.W * p.ldc;
-    const int y0 = ty * TI, x0 = tx * TI;
+    const size_t img_i = (size_t)n * p.H * p.W * p.ldc + c;
+    const int y0 = ty * TIH, x0 = tx * TIW;
 #pragma unroll 2
-    for (int idx = tid; idx < NVX; idx += 256) {
-      const int pix = idx / V8, g = idx % V8;
-      const int y = y0 + pix / TI, x = x0 + pix % TI;
-      const int c = cbase + g * 8;
-      const bool ok = y < p.H && x < p.W && c < p.C;
-      const size_t o = ok ? img_i + (unsigned)((y * p.W + x) * p.ldc + c) : 0;
-      cp_async16(b_x + pix * CT + g * 8, p.x + o, ok ? 16 : 0);
+    for (int pix = pslot; pix < NPX; pix += PSTEP) {
+      const int y = y0 + pix / TIW, x = x0 + pix % TIW;
+      const bool ok = cok && y < p.H && x < p.W;
+      const size_t o = ok ? img_i + (unsigned)((y * p.W + x) * p.ldc) : 0;
+      cp_async16(b_x + pix * CT, p.x + o, ok ? 16 : 0);
     }
   };
 
@@ -461,8 +501,9 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     if (chunk != cur_chunk) {
       if (cur_chunk >= 0) flush(cur_chunk);
       cur_chunk = chunk;
+      load_tables(chunk);
     }
-    const int y0 = ty * TI, x0 = tx * TI;
+    const int y0 = ty * TIH, x0 = tx * TIW;
     __syncthreads();  // previous tile's compute is done with the buffer the prefetch overwrites
     {
       if (t + 1 < t_end) prefetch(t + 1, buf ^ 1);
@@ -474,119 +515,133 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     const __nv_bfloat16* b_h = b_dz + REG_ELEMS;
     const __nv_bfloat16* b_x = b_h + REG_ELEMS;
     // ---- dh = ca*dz + cb*h + cc in place over the gradient region (0 outside the image) ----
+    if (cbase + g8 * 8 < p.C) {
+      float ca8[8], cb8[8], cc8[8];
+#pragma unroll
+      for (int v = 0; v < 8; v += 4) {
+        *reinterpret_cast<float4*>(ca8 + v) = *reinterpret_cast<const float4*>(s_tab + 2 * CT + g8 * 8 + v);
+        *reinterpret_cast<float4*>(cb8 + v) = *reinterpret_cast<const float4*>(s_tab + 3 * CT + g8 * 8 + v);
+        *reinterpret_cast<float4*>(cc8 + v) = *reinterpret_cast<const float4*>(s_tab + 4 * CT + g8 * 8 + v);
+      }
 #pragma unroll 2
-    for (int idx = tid; idx < NVR; idx += 256) {
-      const int pix = idx / V8, g = idx % V8;
-      const int oy = ry0 + pix / RMAX, ox = rx0 + pix % RMAX;
-      const int c = cbase + g * 8;
-      if ((unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo && c < p.C) {
-        uint4* q = reinterpret_cast<uint4*>(b_dz + pix * CT + g * 8);
-        const uint4 rdz = *q;
-        const uint4 rh = *reinterpret_cast<const uint4*>(b_h + pix * CT + g * 8);
-        const float4 ca0 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c);
-        const float4 ca1 = *reinterpret_cast<const float4*>(s_tab + 2 * p.C + c + 4);
-        const float4 cb0 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c);
-        const float4 cb1 = *reinterpret_cast<const float4*>(s_tab + 3 * p.C + c + 4);
-        const float4 cc0 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c);
-        const float4 cc1 = *reinterpret_cast<const float4*>(s_tab + 4 * p.C + c + 4);
-        const float d0 = fmaf(ca0.x, bf16lo(rdz.x), fmaf(cb0.x, bf16lo(rh.x), cc0.x));
-        const float d1 = fmaf(ca0.y, bf16hi(rdz.x), fmaf(cb0.y, bf16hi(rh.x), cc0.y));
-        const float d2 = fmaf(ca0.z, bf16lo(rdz.y), fmaf(cb0.z, bf16lo(rh.y), cc0.z));
-        const float d3 = fmaf(ca0.w, bf16hi(rdz.y), fmaf(cb0.w, bf16hi(rh.y), cc0.w));
-        const float d4 = fmaf(ca1.x, bf16lo(rdz.z), fmaf(cb1.x, bf16lo(rh.z), cc1.x));
-        const float d5 = fmaf(ca1.y, bf16hi(rdz.z), fmaf(cb1.y, bf16hi(rh.z), cc1.y));
-        const float d6 = fmaf(ca1.z, bf16lo(rdz.w), fmaf(cb1.z, bf16lo(rh.w), cc1.z));
-        const float d7 = fmaf(ca1.w, bf16hi(rdz.w), fmaf(cb1.w, bf16hi(rh.w), cc1.w));
-        *q = make_uint4(pack_bf16(d0, d1), pack_bf16(d2, d3), pack_bf16(d4, d5), pack_bf16(d6, d7));
+      for (int pix = pslot; pix < NPR; pix += PSTEP) {
+        const int oy = ry0 + pix / RW, ox = rx0 + pix % RW;
+        if ((unsigned)oy < (unsigned)p.Ho && (unsigned)ox < (unsigned)p.Wo) {
+          uint4* q = reinterpret_cast<uint4*>(b_dz + pix * CT + g8 * 8);
+          const uint4 rdz = *q;
+          const uint4 rh = *reinterpret_cast<const uint4*>(b_h + pix * CT + g8 * 8);
+          const float d0 = fmaf(ca8[0], bf16lo(rdz.x), fmaf(cb8[0], bf16lo(rh.x), cc8[0]));
+          const float d1 = fmaf(ca8[1], bf16hi(rdz.x), fmaf(cb8[1], bf16hi(rh.x), cc8[1]));
+          const float d2 = fmaf(ca8[2], bf16lo(rdz.y), fmaf(cb8[2], bf16lo(rh.y), cc8[2]));
+          const float d3 = fmaf(ca8[3], bf16hi(rdz.y), fmaf(cb8[3], bf16hi(rh.y), cc8[3]));
+          const float d4 = fmaf(ca8[4], bf16lo(rdz.z), fmaf(cb8[4], bf16lo(rh.z), cc8[4]));
+          const float d5 = fmaf(ca8[5], bf16hi(rdz.z), fmaf(cb8[5], bf16hi(rh.z), cc8[5]));
+          const float d6 = fmaf(ca8[6], bf16lo(rdz.w), fmaf(cb8[6], bf16lo(rh.w), cc8[6]));
+          const float d7 = fmaf(ca8[7], bf16hi(rdz.w), fmaf(cb8[7], bf16hi(rh.w), cc8[7]));
+          *q = make_uint4(pack_bf16(d0, d1), pack_bf16(d2, d3), pack_bf16(d4, d5), pack_bf16(d6, d7));
+        }
       }
     }
     __syncthreads();
-    // ---- per input pixel: dgrad gather + fused wgrad + act'/BN-backward epilogue ----
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 mu = sh, rs = sh;
-    if (cvalid) {
-      sc = *reinterpret_cast<const float4*>(s_tab + c0);
-      sh = *reinterpret_cast<const float4*>(s_tab + p.C + c0);
-      mu = *reinterpret_cast<const float4*>(s_tab + 5 * p.C + c0);
-      rs = *reinterpret_cast<const float4*>(s_tab + 6 * p.C + c0);
+    // ---- 2x2 input pixels per thread: dgrad gather + fused wgrad + act'/BN-backward epilogue ----
+    const float4 sc = *reinterpret_cast<const float4*>(s_tab + cg * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(s_tab + CT + cg * 4);
+    const __nv_bfloat16* xbase = b_x + (py * TIW + px) * CT + cg * 4;
+    float2 a1p[2][2][2];
+    bool valid[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        valid[a][b] = cvalid && (y0 + py + a) < p.H && (x0 + px + b) < p.W;
+        const uint2 xr = *reinterpret_cast<const uint2*>(xbase + (a * TIW + b) * CT);
+        float a1[4] = {fmaf(sc.x, bf16lo(xr.x), sh.x), fmaf(sc.y, bf16hi(xr.x), sh.y),
+                       fmaf(sc.z, bf16lo(xr.y), sh.z), fmaf(sc.w, bf16hi(xr.y), sh.w)};
+        act_vec<4>(a1, ap);
+        if (p.in_scale) {  // the forward convolved the bf16-rounded activation
+#pragma unroll
+          for (int v = 0; v < 4; ++v) a1[v] = round_bf16(a1[v]);
+        }
+        if (!valid[a][b]) a1[0] = a1[1] = a1[2] = a1[3] = 0.f;   // zero padding of the forward
+        a1p[a][b][0] = make_float2(a1[0], a1[1]);
+        a1p[a][b][1] = make_float2(a1[2], a1[3]);
+      }
+    float2 da2[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) da2[a][b][0] = da2[a][b][1] = make_float2(0.f, 0.f);
+    // The staged region is zero outside the image and covers every tap of every pixel of the
+    // tile: no bounds tests; which (pixel, tap) pairs meet at a region offset is compile-time.
+    const __nv_bfloat16* dbase = b_dz + (rr0 * RW + rc0) * CT + cg * 4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < R; ++c) {
+        const uint2 dr = *reinterpret_cast<const uint2*>(dbase + (r * RW + c) * CT);
+        const float2 dlo = make_float2(bf16lo(dr.x), bf16hi(dr.x));
+        const float2 dhi = make_float2(bf16lo(dr.y), bf16hi(dr.y));
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int tp = ky * K + kx;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                if (tap_hits<K, S>(a, ky, r) && tap_hits<K, S>(b, kx, c)) {
+                  if (DGRAD) {
+                    const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * CT + cg * 4);
+                    da2[a][b][0] = ffma2(dlo, make_float2(wv.x, wv.y), da2[a][b][0]);
+                    da2[a][b][1] = ffma2(dhi, make_float2(wv.z, wv.w), da2[a][b][1]);
+                  }
+                  if (tp >= TAP0 && tp < TAP1) {
+                    gw[tp - TAP0][0] = ffma2(dlo, a1p[a][b][0], gw[tp - TAP0][0]);
+                    gw[tp - TAP0][1] = ffma2(dhi, a1p[a][b][1], gw[tp - TAP0][1]);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
     }
-    const size_t img_in = (size_t)n * p.H * p.W * p.ldc + c0;
-#pragma unroll 1
-    for (int it = 0; it < ITEMS; ++it) {
-      const int pix = it * NPIX + pslot;
-      const int y = y0 + pix / TI, x = x0 + pix % TI;
-      if (!(cvalid && y < p.H && x < p.W)) continue;
-      const uint2 xr = *reinterpret_cast<const uint2*>(b_x + pix * CT + cg * 4);
-      const float xv[4] = {bf16lo(xr.x), bf16hi(xr.x), bf16lo(xr.y), bf16hi(xr.y)};
-      const float z[4] = {fmaf(sc.x, xv[0], sh.x), fmaf(sc.y, xv[1], sh.y),
-                          fmaf(sc.z, xv[2], sh.z), fmaf(sc.w, xv[3], sh.w)};
-      float a1[4] = {z[0], z[1], z[2], z[3]};
-      act_vec<4>(a1, ap);
-      if (p.in_scale) {  // the forward convolved the bf16-rounded activation
+    if (DGRAD) {
+      const float4 mu = *reinterpret_cast<const float4*>(s_tab + 5 * CT + cg * 4);
+      const float4 rs = *reinterpret_cast<const float4*>(s_tab + 6 * CT + cg * 4);
+      const size_t img_in = (size_t)n * p.H * p.W * p.ldc + c0;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) a1[v] = round_bf16(a1[v]);
-      }
-      const float2 a1lo = make_float2(a1[0], a1[1]), a1hi = make_float2(a1[2], a1[3]);
-      float2 da2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      // The staged region is zero outside the image and covers every tap of every pixel of the
-      // tile, so no bounds tests are needed: stride 1 is branch-free, stride 2 keeps only the
-      // parity test of the transposed convolution.
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int ky = 0; ky < K; ++ky) {
-        const int yy = y + P - ky;
-        if (S == 2 && (yy & 1)) continue;
-        const int oy = S == 1 ? yy : yy >> 1;
+        for (int b = 0; b < 2; ++b) {
+          if (!valid[a][b]) continue;
+          const uint2 xr = *reinterpret_cast<const uint2*>(xbase + (a * TIW + b) * CT);
+          const float xv[4] = {bf16lo(xr.x), bf16hi(xr.x), bf16lo(xr.y), bf16hi(xr.y)};
+          const float z[4] = {fmaf(sc.x, xv[0], sh.x), fmaf(sc.y, xv[1], sh.y),
+                              fmaf(sc.z, xv[2], sh.z), fmaf(sc.w, xv[3], sh.w)};
+          float da[4] = {da2[a][b][0].x, da2[a][b][0].y, da2[a][b][1].x, da2[a][b][1].y};
+          act_bwd_vec<4>(da, z, ap, act);
+          const size_t off = img_in + (unsigned)(((y0 + py + a) * p.W + x0 + px + b) * p.ldc);
+          if (p.residual) {
+            float rv[4];
+            ld4(p.residual + off, rv);
 #pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-          const int tp = ky * K + kx;  // compile-time after unrolling
-          if (!DGRAD && (tp < TAP0 || tp >= TAP1)) continue;
-          const int xx = x + P - kx;
-          if (S == 2 && (xx & 1)) continue;
-          const int ox = S == 1 ? xx : xx >> 1;
-          const uint2 dr = *reinterpret_cast<const uint2*>(
-              b_dz + ((oy - ry0) * RMAX + (ox - rx0)) * CT + cg * 4);
-          const float2 dlo = make_float2(bf16lo(dr.x), bf16hi(dr.x));
-          const float2 dhi = make_float2(bf16lo(dr.y), bf16hi(dr.y));
-          if (DGRAD) {
-            const float4 wv = *reinterpret_cast<const float4*>(s_w + tp * p.C + c0);
-            da2[0] = ffma2(dlo, make_float2(wv.x, wv.y), da2[0]);
-            da2[1] = ffma2(dhi, make_float2(wv.z, wv.w), da2[1]);
+            for (int v = 0; v < 4; ++v) da[v] += rv[v];
           }
-          if (tp >= TAP0 && tp < TAP1) {
-            gw[tp - TAP0][0] = ffma2(dlo, a1lo, gw[tp - TAP0][0]);
-            gw[tp - TAP0][1] = ffma2(dhi, a1hi, gw[tp - TAP0][1]);
-          }
+          st4_round(p.dx + off, da);
+          ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
+          ssq[0] = fmaf(da[0], (xv[0] - mu.x) * rs.x, ssq[0]);
+          ssq[1] = fmaf(da[1], (xv[1] - mu.y) * rs.y, ssq[1]);
+          ssq[2] = fmaf(da[2], (xv[2] - mu.z) * rs.z, ssq[2]);
+          ssq[3] = fmaf(da[3], (xv[3] - mu.w) * rs.w, ssq[3]);
         }
-      }
-      if (DGRAD) {
-        float da[4] = {da2[0].x, da2[0].y, da2[1].x, da2[1].y};
-        act_bwd_vec<4>(da, z, ap, act);
-        const size_t off = img_in + (unsigned)((y * p.W + x) * p.ldc);
-        if (p.residual) {
-          float rv[4];
-          ld4(p.residual + off, rv);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) da[v] += rv[v];
-        }
-        st4_round(p.dx + off, da);
-        ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
-        ssq[0] = fmaf(da[0], (xv[0] - mu.x) * rs.x, ssq[0]);
-        ssq[1] = fmaf(da[1], (xv[1] - mu.y) * rs.y, ssq[1]);
-        ssq[2] = fmaf(da[2], (xv[2] - mu.z) * rs.z, ssq[2]);
-        ssq[3] = fmaf(da[3], (xv[3] - mu.w) * rs.w, ssq[3]);
-      }
     }
   }
   cp_async_wait<0>();
   if (cur_chunk >= 0) flush(cur_chunk);
-  __syncthreads();
-  for (int i = tid; i < K * K * p.C; i += 256) {
-    const int tp = i / p.C, c = i % p.C;
-    const float g = s_gw[i];
-    if (g != 0.f) atomicAdd(p.dw + (size_t)c * K * K + tp, g);
-  }
   if (p.has_bn && DGRAD) {
-    if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
+    if (arrive_last(p.bn.counter)) {
       bn_bwd_finalize(p.bn, p.C);
       __syncthreads();
       if (threadIdx.x == 0) *p.bn.counter = 0;
@@ -701,10 +756,11 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   p.residual = (const __nv_bfloat16*)a->residual;
   p.has_bn = a->bn ? 1 : 0;
   if (a->bn) p.bn = *a->bn;
-  const int ti = 8;
-  const int rmax = s == 1 ? ti + k - 1 : (ti + k - 1) / 2 + 1;
-  p.tiles_h = (a->H + ti - 1) / ti;
-  p.tiles_w = (a->W + ti - 1) / ti;
+  const int tih = ct == 64 ? 8 : 16, tiw = 8;
+  const int rh = s == 1 ? tih + k - 1 : (tih + k - 1) / 2 + 1;
+  const int rw = s == 1 ? tiw + k - 1 : (tiw + k - 1) / 2 + 1;
+  p.tiles_h = (a->H + tih - 1) / tih;
+  p.tiles_w = (a->W + tiw - 1) / tiw;
   p.chunks = (a->C + ct - 1) / ct;
   {
     long long nt = (long long)p.chunks * a->N * p.tiles_h * p.tiles_w;
@@ -713,7 +769,7 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   }
   // two staging buffers of bf16 {dz, h over the region; x over the tile} + fp32 tables
   const size_t smem =
-      ((size_t)(2 * rmax * rmax + ti * ti) * ct + (size_t)(7 + 2 * k * k + 2) * a->C) * sizeof(float);
+      ((size_t)(2 * rh * rw + tih * tiw) * ct + (size_t)(7 + 2 * k * k + 2) * ct) * sizeof(float);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");
   cudaError_t e;
   if (k == 3 && s == 1 && ct == 64) YAMB_DW_BWD(3, 1, 64, p, smem, p.num_tiles, st);
