@@ -173,9 +173,10 @@ def forward(x, cfg, P, training=True, quant=False):
     chid = sum(cfg.channels)
     M_in = x.shape[0] * x.shape[2] * x.shape[3]
 
-    def bn(h, pfx):
+    def bn(h, pfx, stat_src=None):
         if training:
-            scale, shift, mean, invstd, var = _bn_train(h, P[pfx + "_g"], P[pfx + "_b"], cfg.eps)
+            scale, shift, mean, invstd, var = _bn_train(h if stat_src is None else stat_src,
+                                                        P[pfx + "_g"], P[pfx + "_b"], cfg.eps)
             S[pfx + "_mean"], S[pfx + "_invstd"], S[pfx + "_var"] = mean, invstd, var
         else:
             invstd = torch.rsqrt(P[pfx + "_rv"] + cfg.eps)
@@ -193,9 +194,12 @@ def forward(x, cfg, P, training=True, quant=False):
         # unfused, expand=False: each branch sees the whole input (hidden == inp)
         a1 = x if len(cfg.channels) == 1 else torch.cat([x] * len(cfg.channels), 1)
     S["a1"] = a1
-    h2 = _rnd(_dw(a1, P["w_dw"], cfg.channels, cfg.stride), q)
+    h2_acc = _dw(a1, P["w_dw"], cfg.channels, cfg.stride)
+    h2 = _rnd(h2_acc, q)
     S["h2"] = h2
-    a2 = _rnd(act_fwd(bn(h2, "bn2"), cfg.act), q)  # MMA operand -> bf16
+    # the depthwise kernel takes the BN2 statistics from its fp32 accumulators, not from the
+    # bf16 values it stores (a zero-mean 2^-9 rounding noise apart they are the same numbers)
+    a2 = _rnd(act_fwd(bn(h2, "bn2", h2_acc), cfg.act), q)  # MMA operand -> bf16
     S["a2"] = a2
     if cfg.se_hidden:
         s = a2.mean((2, 3))

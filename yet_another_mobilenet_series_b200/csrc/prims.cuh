@@ -307,6 +307,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// clamp both halves of a bf16x2 word (relu / relu6 after rounding == rounding after the clamp:
+// the bounds are bf16 values and rounding is monotonic)
+__device__ __forceinline__ uint32_t clamp_bf16x2(uint32_t v, uint32_t lo2, uint32_t hi2) {
+  uint32_t d;
+  asm("{\n\t.reg .b32 t;\n\tmax.bf16x2 t, %1, %2;\n\tmin.bf16x2 %0, t, %3;\n\t}"
+      : "=r"(d)
+      : "r"(v), "r"(lo2), "r"(hi2));
+  return d;
+}
 __device__ __forceinline__ float round_bf16(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
