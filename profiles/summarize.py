@@ -35,8 +35,10 @@ def read_ncu_csv(path):
     rows = list(csv.reader(open(path)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     body = rows[hi + 1:]
+    units = None
     if body and body[0] and not body[0][0].strip().isdigit():   # wide format: a units row follows
-        body = body[1:]
+        units, body = body[0], body[1:]
+    read_ncu_csv.units = units
     return rows[hi], body
 
 
@@ -99,9 +101,24 @@ def block(rnd):
     if not os.path.exists(path):
         return
     hdr, body = read_ncu_csv(path)
+    units = read_ncu_csv.units or [""] * len(hdr)
     col = {h: i for i, h in enumerate(hdr)}
-    want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"),
-            ("dram__bytes_write.sum", "dram wr"),
+
+    def cell(r, key):
+        if key not in col:
+            return "-"
+        v, u = r[col[key]], units[col[key]]
+        scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6}
+        if u in scale:  # bytes -> MB
+            return "%.1f" % (float(v.replace(",", "")) * scale[u])
+        if u in ("us", "ns", "ms"):
+            return "%.1f" % (float(v.replace(",", "")) * {"us": 1, "ns": 1e-3, "ms": 1e3}[u])
+        try:
+            return "%.1f" % float(v.replace(",", ""))
+        except ValueError:
+            return v
+    want = [("gpu__time_duration.sum", "time us"), ("dram__bytes_read.sum", "dram rd MB"),
+            ("dram__bytes_write.sum", "dram wr MB"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
             ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
@@ -115,7 +132,7 @@ def block(rnd):
             if len(r) < len(hdr) or "yamb::" not in r[col["Kernel Name"]]:
                 continue
             name = re.sub(r"\(.*", "", r[col["Kernel Name"]].replace("void yamb::", ""))[:44]
-            f.write("| %s | " % name + " | ".join(r[col[w[0]]] if w[0] in col else "-" for w in want) + " |\n")
+            f.write("| %s | " % name + " | ".join(cell(r, w[0]) for w in want) + " |\n")
     print("block summary written")
 
 

@@ -28,6 +28,8 @@
 #include "prims.cuh"
 
 namespace yamb {
+#define MBAR_WAIT(bar, par) do { if (p.dbg & 256) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
+
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;          // 64 bf16 = 128 bytes = one SWIZZLE_128B row
@@ -62,6 +64,7 @@ struct GemmDev {
   long long gate_rps;            // pixels per sample
   int wg2x;                   // 1: warps 8-11 transform (light epilogue), 0: they are epilogue WG 1
   int dbg;                    // YAMB_GEMM_DEBUG bits: 1 skip transform math, 2 skip proxy fence
+  unsigned long long* dbg_buf;  // bit 512: per-phase cycle sums of the epilogue warps
   yamb_bn_fwd bnf;
   int has_bnf;
   const float *h_scale, *h_shift;
@@ -209,7 +212,7 @@ __device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int
   }
 }
 
-template <bool kXform>
+template <bool kXform, int kEpi>
 __global__ void __launch_bounds__(kXform ? 512 : 384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
@@ -231,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.epi != 2) tma_prefetch_desc(&tmD);
+    if (kEpi != 2) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -269,13 +272,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       int stage = 0, phase = 0;
+      long long dbg_prod = 0;
+      const long long dbg_p0 = clock64();
       for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
         const int mn = w / p.ksplit, slab = w % p.ksplit;
         const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
         const int kb0 = slab * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1);
+          const long long tp0 = clock64();
+          MBAR_WAIT(&bars->empty[stage], phase ^ 1);
+          dbg_prod += clock64() - tp0;
           uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
           // count the bytes first, then issue
@@ -335,21 +342,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.dbg & 512) {
+        atomicAdd(p.dbg_buf + 8, (unsigned long long)dbg_prod);
+        atomicAdd(p.dbg_buf + 9, (unsigned long long)(clock64() - dbg_p0));
+      }
     }
    } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
     const uint32_t idesc = umma_idesc_bf16(kBlockM, p.block_n, p.a_mn, p.b_mn);
     int stage = 0, phase = 0, it = 0;
+    long long dbg_mma_full = 0, dbg_mma_empty = 0;
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
       const int slab = w % p.ksplit;
       const int kb0 = slab * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
       const int as = it & 1;
-      mbar_wait(&bars->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      const long long te0 = clock64();
+      MBAR_WAIT(&bars->tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      dbg_mma_empty += clock64() - te0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccStride);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(use_x ? &bars->xdone[stage] : &bars->full[stage], phase);
+        const long long tm0 = clock64();
+        MBAR_WAIT(use_x ? &bars->xdone[stage] : &bars->full[stage], phase);
+        dbg_mma_full += clock64() - tm0;
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -370,6 +386,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
+    if ((p.dbg & 512) && lane == 0) {
+      atomicAdd(p.dbg_buf + 10, (unsigned long long)dbg_mma_full);
+      atomicAdd(p.dbg_buf + 11, (unsigned long long)dbg_mma_empty);
+    }
    }
   } else if (warp < 8 || (warp < 12 && !(kXform && p.wg2x))) {
     // ======================================= epilogue =======================================
@@ -385,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* cz_t = s_coef + p.N;
     const float* cz_m = s_coef + 2 * p.N;
     const float* cz_r = s_coef + 3 * p.N;
-    if (p.epi == 1) {
+    if (kEpi == 1) {
       float* wr = s_coef;
       const int n_epi_thr = (kXform && p.wg2x) ? 128 : 256;
       for (int i = threadIdx.x - 128; i < p.N; i += n_epi_thr) {
@@ -398,8 +418,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const int n_epi_wg = (kXform && p.wg2x) ? 1 : 2;
     uint32_t sub_count = 0;   // running sub-tile counter of this warp -> staging buffer parity
-    const bool side_in = (p.epi == 1) || p.has_residual;
-    const ActParam hap = make_act(p.epi == 1 ? p.h_act : ACT_NONE);
+    const bool side_in = (kEpi == 1) || p.has_residual;
+    const ActParam hap = make_act(kEpi == 1 ? p.h_act : ACT_NONE);
     // Column statistics: with a single n-block every lane owns the same 2 columns of sub-tile j in
     // every tile, so the sums live in registers for the whole kernel (shared-memory float atomics
     // are CAS loops and serialise the 8 epilogue warps); flushed once at the end.
@@ -410,6 +430,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int e = 0; e < 4; ++e) racc[j][e] = 0.f;
     int it = 0;
+    long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
+    const long long dbg_start = clock64();
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
       if (n_epi_wg == 2 && (it & 1) != wg) continue;  // the other warpgroup owns this tile
       const int mn = w / p.ksplit;
@@ -419,11 +441,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = grow < p.M;
       // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
       const int n_sub = min((p.block_n + 63) / 64, (p.N - n_blk * p.block_n + 63) / 64);
-      mbar_wait(&bars->tmem_full[as], (it >> 1) & 1);
+      long long tq0 = clock64();
+      MBAR_WAIT(&bars->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll
-      for (int sub = 0; sub < 4; ++sub) {
-        if (sub >= n_sub) break;
+      dbg_t[0] += clock64() - tq0;
+      // NOT unrolled: one copy of the sub-tile body keeps the epilogue inside the instruction
+      // cache (4 unrolled copies x 3 epilogue kinds were ~20k instructions; "no instruction" was
+      // the top stall reason and a sub-tile took ~4000 cycles)
+#pragma unroll 1
+      for (int sub = 0; sub < n_sub; ++sub) {
         const int col0 = n_blk * p.block_n + sub * 64;  // global column of this sub-tile
         // side operand rows straight from global (each thread owns one row: 8 x 16 B)
         uint4 sv[8];
@@ -439,15 +465,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + sub * 64);
         uint32_t acc[2][32];
+        long long tq1 = clock64();
         tmem_ld_32x32(taddr, acc[0]);
         tmem_ld_32x32(taddr + 32, acc[1]);
         tmem_ld_wait();
+        dbg_t[1] += clock64() - tq1;
+        tq1 = clock64();
         if (sub == n_sub - 1) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           mbar_arrive(&bars->tmem_empty[as]);
         }
-        if (p.epi == 2) {
+        if (kEpi == 2) {
           // split-K partial sums: fp32 atomic accumulate into D[M][ldd]
           if (row_ok) {
             float* drow = reinterpret_cast<float*>(p.D) + (size_t)grow * p.ldd;
@@ -471,6 +500,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else tma_store_wait_read<0>();
         }
         __syncwarp();
+        dbg_t[2] += clock64() - tq1;
+        tq1 = clock64();
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 columns
           const int pc = ch ^ (lane & 7);
@@ -479,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
           if (side_in) {
             const uint32_t sw[4] = {sv[ch].x, sv[ch].y, sv[ch].z, sv[ch].w};
-            if (p.epi == 0) {
+            if (kEpi == 0) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 v[2 * e] += bf16lo(sw[e]);
@@ -512,12 +543,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           o.w = pack_bf16(v[6], v[7]);
           *reinterpret_cast<uint4*>(sO + lane * 128 + (pc << 4)) = o;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tmD, sO, col0, m_blk * kBlockM + q * 32);
-          tma_store_commit();
+        dbg_t[3] += clock64() - tq1;
+        tq1 = clock64();
+        if (p.dbg & 128) {
+          // experiment: coalesced st.global from the staged tile instead of a TMA store
+          __syncwarp();
+          __nv_bfloat16* Dg = reinterpret_cast<__nv_bfloat16*>(p.D);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 3) + 4 * i;
+            const int gr = m_blk * kBlockM + q * 32 + r;
+            const int gc = col0 + (lane & 7) * 8;
+            const uint4 v = *reinterpret_cast<const uint4*>(sO + r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+            if (gr < p.M && gc < p.N && (sub * 64 + (lane & 7) * 8) < p.block_n)
+              *reinterpret_cast<uint4*>(Dg + (size_t)gr * p.ldd + gc) = v;
+          }
+        } else {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 64)) {
+            tma_store_2d(&tmD, sO, col0, m_blk * kBlockM + q * 32);
+            tma_store_commit();
+          }
         }
+        dbg_t[4] += clock64() - tq1;
+        tq1 = clock64();
         // ---- per-column statistics of this warp's 32 rows of the bf16-rounded output ----
         if (p.has_bnf || p.has_bnb) {
           const int c = col0 + 2 * lane;  // column pair owned by this lane
@@ -545,7 +595,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (reg_stats) {
-              racc[sub][0] += s0; racc[sub][1] += s1; racc[sub][2] += q0; racc[sub][3] += q1;
+              switch (sub) {  // constant register indices in every case
+                case 0: racc[0][0] += s0; racc[0][1] += s1; racc[0][2] += q0; racc[0][3] += q1; break;
+                case 1: racc[1][0] += s0; racc[1][1] += s1; racc[1][2] += q0; racc[1][3] += q1; break;
+                case 2: racc[2][0] += s0; racc[2][1] += s1; racc[2][2] += q0; racc[2][3] += q1; break;
+                default: racc[3][0] += s0; racc[3][1] += s1; racc[3][2] += q0; racc[3][3] += q1; break;
+              }
             } else {
               atomicAdd(&s_stats[c], s0);
               atomicAdd(&s_stats[c + 1], s1);
@@ -555,8 +610,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();  // s_h / sO reads done before the next sub-tile overwrites them
         }
+        dbg_t[5] += clock64() - tq1;
         ++sub_count;
       }
+    }
+    if ((p.dbg & 512) && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) atomicAdd(p.dbg_buf + i, (unsigned long long)dbg_t[i]);
+      atomicAdd(p.dbg_buf + 6, (unsigned long long)(clock64() - dbg_start));
+      atomicAdd(p.dbg_buf + 7, 1ull);
     }
     if (reg_stats) {
 #pragma unroll
@@ -570,7 +632,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (lane == 0 && p.epi != 2) tma_store_wait_all<0>();
+    if (lane == 0 && kEpi != 2) tma_store_wait_all<0>();
   } else if (kXform) {
     // ================================== operand transform ==================================
     if (use_x) {
@@ -580,7 +642,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // coefficient tables in smem: A: [scale|shift|scale2] x Ca, then B likewise
       const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
       const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
-      float* xa = s_coef + (p.epi == 1 ? 4 * p.N : 0);
+      float* xa = s_coef + (kEpi == 1 ? 4 * p.N : 0);
       float* xb = xa + 3 * Ca;
       for (int i = t; i < Ca; i += nxt) {
         xa[i] = p.a_scale[i];
@@ -602,7 +664,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb0 = slab * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
+          MBAR_WAIT(&bars->full[stage], phase);
           const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t sB = sA + kABytes;
           // panels of this stage: A (1 K-major / 2 MN-major) then B (ceil(block_n/128) K-major /
@@ -731,6 +793,13 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     return set_error(YAMB_EINVAL, "two-source transform without second tensor");
   p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
   { const char* d = getenv("YAMB_GEMM_DEBUG"); p.dbg = d ? atoi(d) : 0; }
+  p.dbg_buf = nullptr;
+  if (p.dbg & 512) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 16 * sizeof(unsigned long long), stream);
+    p.dbg_buf = dbuf;
+  }
   // transform-heavy / epilogue-light launches give warps 8-11 to the transform
   p.wg2x = ((a->a_xform || a->b_xform) && (a->epi == 2 || (a->epi == 0 && p.block_n <= 192))) ? 1 : 0;
   if (p.dbg & 16) p.wg2x = 0;
@@ -831,19 +900,37 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
 
   const int grid = p.num_work < ctas ? p.num_work : ctas;
   cudaError_t e;
+#define YAMB_GEMM_LAUNCH(XF, EP, THREADS)                                                         \
+  do {                                                                                           \
+    e = cudaFuncSetAttribute(gemm_tc_kernel<XF, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             smem_total);                                                        \
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));  \
+    gemm_tc_kernel<XF, EP><<<grid, THREADS, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p); \
+  } while (0)
   if (xf) {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_total);
-    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
-    gemm_tc_kernel<true><<<grid, 512, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p);
+    if (a->epi == 0) YAMB_GEMM_LAUNCH(true, 0, 512);
+    else if (a->epi == 1) YAMB_GEMM_LAUNCH(true, 1, 512);
+    else YAMB_GEMM_LAUNCH(true, 2, 512);
   } else {
-    e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_total);
-    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));
-    gemm_tc_kernel<false><<<grid, 384, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p);
+    if (a->epi == 0) YAMB_GEMM_LAUNCH(false, 0, 384);
+    else if (a->epi == 1) YAMB_GEMM_LAUNCH(false, 1, 384);
+    else YAMB_GEMM_LAUNCH(false, 2, 384);
   }
+#undef YAMB_GEMM_LAUNCH
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "gemm launch: %s", cudaGetErrorString(e));
+  if (p.dbg & 512) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double n = h[7] ? (double)h[7] : 1.0;
+    fprintf(stderr, "gemm dbg (cycles per epilogue warp): wait_full %.0f tmem_ld %.0f wait_store %.0f "
+            "convert %.0f store %.0f stats %.0f total %.0f warps %.0f\n", h[0] / n, h[1] / n, h[2] / n,
+            h[3] / n, h[4] / n, h[5] / n, h[6] / n, n);
+    fprintf(stderr, "   per CTA: producer wait_empty %.0f of %.0f; mma wait_full %.0f wait_tmem_empty %.0f; "
+            "stages %d out_bufs %d block_n %d\n", h[8] / (double)grid, h[9] / (double)grid,
+            h[10] / (double)grid, h[11] / (double)grid, p.num_stages, p.out_bufs, p.block_n);
+  }
   return 0;
 }
 
