@@ -1,5 +1,4 @@
-"""GPU driver: time output-heavy GEMMs with the store-path experiment bits of YAMB_GEMM_DEBUG
-(64: no store at all, 128: coalesced st.global instead of the TMA store)."""
+"""GPU driver: phase timers (YAMB_GEMM_DEBUG=512) of the GEMM roles on representative shapes."""
 import os
 import sys
 
@@ -9,10 +8,11 @@ import __graft_entry__ as ge  # noqa: E402,F401
 ge.build()
 from gpu_microbench_gemm import run  # noqa: E402
 
-for dbg in (512, 512 + 128, 512 + 64):
+for dbg in [int(a) for a in sys.argv[1:]] or [512]:
     os.environ["YAMB_GEMM_DEBUG"] = str(dbg)
     print("---- YAMB_GEMM_DEBUG=%d" % dbg)
-    run("expand b3 plain", 802816, 144, 24, iters=1)
+    sys.stdout.flush()
     run("expand b3 +stats", 802816, 144, 24, stats=True, iters=1)
-    run("expand b2 plain", 3211264, 96, 16, iters=1)
     run("project b3 +xform+stats", 802816, 24, 144, stats=True, xform=1, iters=1)
+    run("wgrad b3 +xform", 144, 24, 802816, xform=1, a_mn=1, b_mn=1, epi=2, iters=1)
+    run("project b12 +xform+stats", 50176, 96, 576, stats=True, xform=1, iters=1)

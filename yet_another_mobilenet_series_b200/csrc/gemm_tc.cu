@@ -65,6 +65,12 @@ struct GemmDev {
   int wg2x;                   // 1: warps 8-11 transform (light epilogue), 0: they are epilogue WG 1
   int dbg;                    // YAMB_GEMM_DEBUG bits: 1 skip transform math, 2 skip proxy fence
   unsigned long long* dbg_buf;  // bit 512: per-phase cycle sums of the epilogue warps
+  // operand tensors in global memory ([pixels|rows][channels], bf16) for the cp.async loaders
+  const __nv_bfloat16 *gA, *gA2, *gB, *gB2;
+  long long lda, lda2, ldb, ldb2;
+  int lookahead;              // (unused)
+  int a_tma, b_tma;           // wide transformed operand: TMA load + in-place smem transform
+  int lgroup;                 // loader warps that share one stage (1, 2 or 4)
   yamb_bn_fwd bnf;
   int has_bnf;
   const float *h_scale, *h_shift;
@@ -85,6 +91,11 @@ struct Bars {
   uint32_t pad;
 };
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -127,9 +138,9 @@ template <int MODE>
 __device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t rbase2, int row,
                                             int lc, uint32_t tab_s, uint32_t tab_b,
                                             uint32_t tab_s2, int cbase, int C,
-                                            const float* gate_row) {
+                                            const float* gate_row, bool valid) {
   const int c0 = cbase + lc * 8;
-  k.ok = c0 < C;
+  k.ok = valid && c0 < C;
   const uint32_t off = (uint32_t)((lc ^ (row & 7)) << 4);
   k.addr = rbase + off;
   if (k.ok) {
@@ -174,46 +185,155 @@ __device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap
                             pack_bf16(x[6], x[7])));
 }
 
-// In-place transform of one panel (R = 64 or 128 rows x 128 B, SWIZZLE_128B) by 128 threads.
+// In-place transform of one panel (R = 64 or 128 rows x 128 B, SWIZZLE_128B) by `nt` threads.
 //   mode 1: v = act(s[c]*v + b[c])        mode 2: v = s[c]*v + s2[c]*v2 + b[c]
-// `t` in [0,128).  Channel of (logical 16B chunk lc, element e) = cbase + lc*8 + e.
+// `t` in [0,nt).  Chunk i = row*8 + lc; channel of (chunk lc, element e) = cbase + lc*8 + e.
 // All addresses are 32-bit shared-window addresses; tab_* point at fp32 tables indexed by channel.
 // ONE copy of this code exists in the kernel (single call site, runtime R / mode): two chunks'
 // loads are in flight before the first use.
-__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int logR, int t,
+__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int R, int t, int nt,
                                             int mode, const ActParam& ap, uint32_t tab_s,
                                             uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
-                                            int row_limit, const float* gate, long long pixbase,
-                                            long long rps, int lognt) {
-  // lognt = log2(#transform threads) (7 or 8); threads per row = nt / R, chunks per thread = 8R/nt
-  const int row = t & ((1 << logR) - 1);
-  const int part = t >> logR;
-  const int per = 1 << (logR + 3 - lognt);
-  if (row >= row_limit) return;
-  const uint32_t rbase = panel + row * 128;
-  const uint32_t rbase2 = panel2 + row * 128;
-  const float* grow = gate ? gate + ((pixbase + row) / rps) * C : nullptr;
+                                            int row_limit, const float* gate, unsigned pixbase,
+                                            unsigned rps) {
+  const int total = min(R, row_limit) * 8;
 #pragma unroll 1
-  for (int j0 = 0; j0 < per; j0 += 2) {
+  for (int i = t; i < total; i += 2 * nt) {
     XChunk a, b;
+    const int ra = i >> 3, la = i & 7;
+    const int ib = i + nt;
+    const int rb = ib >> 3, lb = ib & 7;
+    const bool vb = ib < total;
+    const uint32_t pa = panel + ra * 128, pa2 = panel2 + ra * 128;
+    const uint32_t pb = panel + rb * 128, pb2 = panel2 + rb * 128;
     if (mode == 2) {
-      xchunk_load<2>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C, nullptr);
-      xchunk_load<2>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C,
-                     nullptr);
+      xchunk_load<2>(a, pa, pa2, ra, la, tab_s, tab_b, tab_s2, cbase, C, nullptr, true);
+      xchunk_load<2>(b, pb, pb2, rb, lb, tab_s, tab_b, tab_s2, cbase, C, nullptr, vb);
       xchunk_apply<2>(a, ap, false);
       xchunk_apply<2>(b, ap, false);
     } else {
-      xchunk_load<1>(a, rbase, rbase2, row, part * per + j0, tab_s, tab_b, tab_s2, cbase, C, grow);
-      xchunk_load<1>(b, rbase, rbase2, row, part * per + j0 + 1, tab_s, tab_b, tab_s2, cbase, C,
-                     grow);
-      xchunk_apply<1>(a, ap, grow != nullptr);
-      xchunk_apply<1>(b, ap, grow != nullptr);
+      const float* ga = gate ? gate + (size_t)((pixbase + ra) / rps) * C : nullptr;
+      const float* gb = gate ? gate + (size_t)((pixbase + rb) / rps) * C : nullptr;
+      xchunk_load<1>(a, pa, pa2, ra, la, tab_s, tab_b, tab_s2, cbase, C, ga, true);
+      xchunk_load<1>(b, pb, pb2, rb, lb, tab_s, tab_b, tab_s2, cbase, C, gb, vb);
+      xchunk_apply<1>(a, ap, gate != nullptr);
+      xchunk_apply<1>(b, ap, gate != nullptr);
     }
   }
 }
 
+// Register-staged load + transform of one operand panel by ONE warp: every lane owns the same
+// 8-channel column (lc = lane & 7) for the whole panel, so its BatchNorm / affine coefficients sit
+// in registers; 8 rows (16-byte vectors) per lane are in flight from global memory at a time, are
+// transformed in registers and stored straight into the SWIZZLE_128B layout (no shared-memory
+// round trip, no cross-warp synchronisation).
+//   mode 1: v = act(s[c]*v + b[c]) [* gate]      mode 2: v = s[c]*v + s2[c]*v2 + b[c]
+// Vectors outside the tensor (row >= rlimit or channel >= C) are stored as zero.
+template <int MODE, bool SMEM>
+__device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, const __nv_bfloat16* g1, long long ld1,
+                                             const __nv_bfloat16* g2, long long ld2, int rbeg, int rows,
+                                             int rlimit, int ln, const ActParam& ap,
+                                             uint32_t tab_s, uint32_t tab_b, uint32_t tab_s2,
+                                             int col0, int C, const float* gate, unsigned pixbase,
+                                             unsigned rps) {
+  constexpr int NB = MODE == 2 ? 4 : 8;   // rows in flight per lane (16 B each, x2 sources in mode 2)
+  const int lc = ln & 7;
+  const int c0 = col0 + lc * 8;
+  const bool cok = c0 < C;
+  float2 sc[4], sh[4], s2[4];
+  {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, t0 = a0, t1 = a0;
+    if (cok) {
+      a0 = lds128f(tab_s + c0 * 4); a1 = lds128f(tab_s + c0 * 4 + 16);
+      b0 = lds128f(tab_b + c0 * 4); b1 = lds128f(tab_b + c0 * 4 + 16);
+      if (MODE == 2) { t0 = lds128f(tab_s2 + c0 * 4); t1 = lds128f(tab_s2 + c0 * 4 + 16); }
+    }
+    sc[0] = make_float2(a0.x, a0.y); sc[1] = make_float2(a0.z, a0.w);
+    sc[2] = make_float2(a1.x, a1.y); sc[3] = make_float2(a1.z, a1.w);
+    sh[0] = make_float2(b0.x, b0.y); sh[1] = make_float2(b0.z, b0.w);
+    sh[2] = make_float2(b1.x, b1.y); sh[3] = make_float2(b1.z, b1.w);
+    s2[0] = make_float2(t0.x, t0.y); s2[1] = make_float2(t0.z, t0.w);
+    s2[2] = make_float2(t1.x, t1.y); s2[3] = make_float2(t1.z, t1.w);
+  }
+  const uint32_t lo2 = pack_bf16(ap.lo, ap.lo), hi2 = pack_bf16(ap.hi, ap.hi);
+  const __nv_bfloat16* p1 = g1 + c0;
+  const __nv_bfloat16* p2 = g2 + c0;
+  auto load_batch = [&](int rb, uint4 (&v)[NB], uint4 (&w)[MODE == 2 ? NB : 1]) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = rb + 4 * j;
+      const bool ok = cok && r < rlimit;
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (MODE == 2) w[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok) {
+        if (SMEM) {   // the TMA producer put the raw tile(s) there: rewrite in place
+          const uint32_t off = (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4));
+          v[j] = lds128(panel + off);
+          if (MODE == 2) w[j] = lds128(panel2 + off);
+        } else {
+          v[j] = __ldg(reinterpret_cast<const uint4*>(p1 + (long long)r * ld1));
+          if (MODE == 2) w[j] = __ldg(reinterpret_cast<const uint4*>(p2 + (long long)r * ld2));
+        }
+      }
+    }
+  };
+  auto proc_batch = [&](int rb, const uint4 (&v)[NB], const uint4 (&w)[MODE == 2 ? NB : 1]) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = rb + 4 * j;
+      if (r >= rows) continue;
+      const bool ok = cok && r < rlimit;
+      const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      uint32_t o[4];
+      if (MODE == 2) {
+        const uint32_t yv[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t1 = ffma2(s2[e], make_float2(bf16lo(yv[e]), bf16hi(yv[e])), sh[e]);
+          const float2 d = ffma2(sc[e], make_float2(bf16lo(xv[e]), bf16hi(xv[e])), t1);
+          o[e] = pack_bf16(d.x, d.y);
+        }
+      } else if (ap.kind == 0 && gate == nullptr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 d = ffma2(sc[e], make_float2(bf16lo(xv[e]), bf16hi(xv[e])), sh[e]);
+          o[e] = clamp_bf16x2(pack_bf16(d.x, d.y), lo2, hi2);
+        }
+      } else {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 d = ffma2(sc[e], make_float2(bf16lo(xv[e]), bf16hi(xv[e])), sh[e]);
+          x[2 * e] = d.x; x[2 * e + 1] = d.y;
+        }
+        act_vec<8>(x, ap);
+        if (gate != nullptr && ok) {
+          // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
+          const float* gr = gate + (size_t)((pixbase + (unsigned)r) / rps) * C + c0;
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(gr));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(gr + 4));
+          const float gq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = round_bf16(x[e]) * gq[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+      }
+      sts128(panel + (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4)),
+             make_uint4(ok ? o[0] : 0u, ok ? o[1] : 0u, ok ? o[2] : 0u, ok ? o[3] : 0u));
+    }
+  };
+  // (narrow operands only: one register batch in flight per lane)
+  uint4 va[NB], wa[MODE == 2 ? NB : 1];
+#pragma unroll 1
+  for (int rb = rbeg + (ln >> 3); rb < rows; rb += 4 * NB) {
+    load_batch(rb, va, wa);
+    proc_batch(rb, va, wa);
+  }
+}
+
 template <bool kXform, int kEpi>
-__global__ void __launch_bounds__(kXform ? 512 : 384, 1)
+__global__ void __launch_bounds__(512, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmDev p) {
@@ -232,14 +352,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // ---- one-time setup ------------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
     if (kEpi != 2) tma_prefetch_desc(&tmD);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(&bars->full[i], 1);
-      mbar_init(&bars->xdone[i], p.wg2x ? 256 : 128);
+      mbar_init(&bars->full[i], p.lgroup);   // the loader warps that own the stage arrive
+      mbar_init(&bars->xdone[i], 1);
       mbar_init(&bars->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -261,90 +379,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  const uint32_t a_tx = (uint32_t)kABytes;
   const bool use_x = kXform && (p.a_xform != 0 || p.b_xform != 0);
 
   // 512-thread variant: every thread starts with 128 registers; the control warpgroup hands its
   // surplus to the two epilogue warpgroups (64*4 + 160*8 + 128*4 warps x 32 lanes = 64 Ki regs).
   if (warp < 4) {
-   if (kXform) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // ============ TMA producer: wide transformed operands only (128-byte box rows) ============
+    if (lane == 0 && (p.a_tma || p.b_tma)) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
       int stage = 0, phase = 0;
-      long long dbg_prod = 0;
-      const long long dbg_p0 = clock64();
       for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
         const int mn = w / p.ksplit, slab = w % p.ksplit;
         const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
         const int kb0 = slab * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
-          const long long tp0 = clock64();
           MBAR_WAIT(&bars->empty[stage], phase ^ 1);
-          dbg_prod += clock64() - tp0;
           uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sB = sA + kABytes;
-          // count the bytes first, then issue
           uint32_t tx = 0;
           const int a_panels = p.a_mn ? 2 : 1;
           int a_issue[2] = {0, 0};
-          if (!p.a_mn) {
-            tx += a_tx;
-          } else {
-            for (int q = 0; q < 2; ++q)
-              if (m_blk * kBlockM + q * 64 < p.M) { a_issue[q] = 1; tx += kPanelBytes64; }
-          }
           const int b_panels = (p.block_n + 63) / 64;
-          if (!p.b_mn) {
-            tx += (uint32_t)p.block_n * 128u;
-          } else {
-            for (int q = 0; q < b_panels; ++q)
-              if (n_blk * p.block_n + q * 64 < p.N) tx += kPanelBytes64;
+          if (p.a_tma) {
+            if (!p.a_mn) {
+              tx += (uint32_t)kABytes;
+            } else {
+              for (int q = 0; q < 2; ++q)
+                if (m_blk * kBlockM + q * 64 < p.M) { a_issue[q] = 1; tx += kPanelBytes64; }
+            }
+            if (p.a_xform == 2) tx += p.a_mn ? (a_issue[0] + a_issue[1]) * kPanelBytes64 : (uint32_t)kABytes;
           }
-          if (p.a_xform == 2) tx += p.a_mn ? (a_issue[0] + a_issue[1]) * kPanelBytes64 : a_tx;
-          if (p.b_xform == 2) {
-            if (!p.b_mn) tx += (uint32_t)p.block_n * 128u;
-            else
+          if (p.b_tma) {
+            uint32_t tb = 0;
+            if (!p.b_mn) {
+              tb = (uint32_t)p.block_n * 128u;
+            } else {
               for (int q = 0; q < b_panels; ++q)
-                if (n_blk * p.block_n + q * 64 < p.N) tx += kPanelBytes64;
+                if (n_blk * p.block_n + q * 64 < p.N) tb += kPanelBytes64;
+            }
+            tx += p.b_xform == 2 ? 2 * tb : tb;
           }
-          mbar_arrive_expect_tx(&bars->full[stage], tx);
-          if (!p.a_mn) {
-            tma_load_2d(&tmA, &bars->full[stage], sA, kb * kBlockK, m_blk * kBlockM);
-            if (p.a_xform == 2)
-              tma_load_2d(&tmA2, &bars->full[stage], sA + p.a2_off, kb * kBlockK, m_blk * kBlockM);
-          } else {
-            for (int q = 0; q < a_panels; ++q)
-              if (a_issue[q]) {
-                tma_load_2d(&tmA, &bars->full[stage], sA + q * kPanelBytes64,
-                            m_blk * kBlockM + q * 64, kb * kBlockK);
-                if (p.a_xform == 2)
-                  tma_load_2d(&tmA2, &bars->full[stage], sA + p.a2_off + q * kPanelBytes64,
+          mbar_arrive_expect_tx(&bars->xdone[stage], tx);
+          if (p.a_tma) {
+            if (!p.a_mn) {
+              tma_load_2d(&tmA, &bars->xdone[stage], sA, kb * kBlockK, m_blk * kBlockM);
+              if (p.a_xform == 2)
+                tma_load_2d(&tmA2, &bars->xdone[stage], sA + p.a2_off, kb * kBlockK, m_blk * kBlockM);
+            } else {
+              for (int q = 0; q < a_panels; ++q)
+                if (a_issue[q]) {
+                  tma_load_2d(&tmA, &bars->xdone[stage], sA + q * kPanelBytes64,
                               m_blk * kBlockM + q * 64, kb * kBlockK);
-              }
+                  if (p.a_xform == 2)
+                    tma_load_2d(&tmA2, &bars->xdone[stage], sA + p.a2_off + q * kPanelBytes64,
+                                m_blk * kBlockM + q * 64, kb * kBlockK);
+                }
+            }
           }
-          if (!p.b_mn) {
-            tma_load_2d(&tmB, &bars->full[stage], sB, kb * kBlockK, n_blk * p.block_n);
-            if (p.b_xform == 2)
-              tma_load_2d(&tmB2, &bars->full[stage], sA + p.b2_off, kb * kBlockK,
-                          n_blk * p.block_n);
-          } else {
-            for (int q = 0; q < b_panels; ++q)
-              if (n_blk * p.block_n + q * 64 < p.N) {
-                tma_load_2d(&tmB, &bars->full[stage], sB + q * kPanelBytes64,
-                            n_blk * p.block_n + q * 64, kb * kBlockK);
-                if (p.b_xform == 2)
-                  tma_load_2d(&tmB2, &bars->full[stage], sA + p.b2_off + q * kPanelBytes64,
+          if (p.b_tma) {
+            if (!p.b_mn) {
+              tma_load_2d(&tmB, &bars->xdone[stage], sB, kb * kBlockK, n_blk * p.block_n);
+              if (p.b_xform == 2)
+                tma_load_2d(&tmB2, &bars->xdone[stage], sA + p.b2_off, kb * kBlockK,
+                            n_blk * p.block_n);
+            } else {
+              for (int q = 0; q < b_panels; ++q)
+                if (n_blk * p.block_n + q * 64 < p.N) {
+                  tma_load_2d(&tmB, &bars->xdone[stage], sB + q * kPanelBytes64,
                               n_blk * p.block_n + q * 64, kb * kBlockK);
-              }
+                  if (p.b_xform == 2)
+                    tma_load_2d(&tmB2, &bars->xdone[stage], sA + p.b2_off + q * kPanelBytes64,
+                                n_blk * p.block_n + q * 64, kb * kBlockK);
+                }
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-      }
-      if (p.dbg & 512) {
-        atomicAdd(p.dbg_buf + 8, (unsigned long long)dbg_prod);
-        atomicAdd(p.dbg_buf + 9, (unsigned long long)(clock64() - dbg_p0));
       }
     }
    } else if (warp == 1) {
@@ -364,7 +478,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccStride);
       for (int kb = kb0; kb < kb1; ++kb) {
         const long long tm0 = clock64();
-        MBAR_WAIT(use_x ? &bars->xdone[stage] : &bars->full[stage], phase);
+        MBAR_WAIT(&bars->full[stage], phase);
         dbg_mma_full += clock64() - tm0;
         tc_fence_after();
         if (lane == 0) {
@@ -393,7 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
    }
   } else if (warp < 8 || (warp < 12 && !(kXform && p.wg2x))) {
     // ======================================= epilogue =======================================
-    if (kXform) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int ew = warp - 4;           // 0..7
     const int wg = ew >> 2;            // epilogue warpgroup = TMEM accumulator stage it serves
     const int q = warp & 3;            // TMEM lane quadrant of this warp
@@ -633,17 +747,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (lane == 0 && kEpi != 2) tma_store_wait_all<0>();
-  } else if (kXform) {
-    // ================================== operand transform ==================================
+  } else {
+    // ============================ operand loaders (+ transform) ============================
+    // Warps 12-15 (t 0..127) plus, when wg2x, warps 8-11 (t 128..255) stream the operand tiles
+    // of `lookahead` k-blocks ahead into shared memory with cp.async (16-byte chunks written
+    // straight into the SWIZZLE_128B layout the UMMA descriptors expect, zero-filled outside the
+    // tensors), then — for transformed operands — rewrite their tile in place, and publish the
+    // stage to the MMA warp.  (TMA tile loads cost ~7-16 cycles per box ROW whatever its width:
+    // with 32-96-byte rows of the narrow operands the TMA unit, not HBM, bounded every GEMM.)
+    // registers: 4 control warps x 56 + (epilogue + loader) warps x 152 = 64 Ki / 32
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    const int nxt = p.wg2x ? 256 : 128;
+    const int t = warp >= 12 ? threadIdx.x - 384 : threadIdx.x - 256 + 128;
+    const int G = p.lgroup;                       // warps sharing a stage (rows split G ways)
+    const int NW = (nxt >> 5) / G, lw = (t >> 5) / G, ls = (t >> 5) % G, ln = t & 31;
+    const int Ca = (kXform && p.a_xform) ? (p.a_mn ? p.M : p.K) : 0;
+    const int Cb = (kXform && p.b_xform) ? (p.b_mn ? p.N : p.K) : 0;
+    float* xa = s_coef + (kEpi == 1 ? 4 * p.N : 0);
+    float* xb = xa + 3 * Ca;
     if (use_x) {
-      // transform threads: warps 12-15 (t 0..127) plus, when wg2x, warps 8-11 (t 128..255)
-      const int nxt = p.wg2x ? 256 : 128;
-      const int t = warp >= 12 ? threadIdx.x - 384 : threadIdx.x - 256 + 128;
       // coefficient tables in smem: A: [scale|shift|scale2] x Ca, then B likewise
-      const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
-      const int Cb = p.b_xform ? (p.b_mn ? p.N : p.K) : 0;
-      float* xa = s_coef + (kEpi == 1 ? 4 * p.N : 0);
-      float* xb = xa + 3 * Ca;
       for (int i = t; i < Ca; i += nxt) {
         xa[i] = p.a_scale[i];
         xa[Ca + i] = p.a_shift[i];
@@ -655,57 +778,178 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         xb[2 * Cb + i] = p.b_xform == 2 ? p.b_scale2[i] : 0.f;
       }
       named_bar_sync(2, nxt);
-      const ActParam apa = make_act(p.a_xform == 1 ? p.a_act : ACT_NONE);
-      const ActParam apb = make_act(p.b_xform == 1 ? p.b_act : ACT_NONE);
-      int stage = 0, phase = 0;
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
-        const int mn = w / p.ksplit, slab = w % p.ksplit;
-        const int m_blk = mn / p.n_blocks, n_blk = mn % p.n_blocks;
-        const int kb0 = slab * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          MBAR_WAIT(&bars->full[stage], phase);
-          const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sB = sA + kABytes;
-          // panels of this stage: A (1 K-major / 2 MN-major) then B (ceil(block_n/128) K-major /
-          // ceil(block_n/64) MN-major); one loop, one call site
-          const int na = p.a_xform ? (p.a_mn ? 2 : 1) : 0;
-          const int nb = p.b_xform ? (p.b_mn ? (p.block_n + 63) / 64 : (p.block_n + 127) / 128) : 0;
+    }
+    long long dbg_l[4] = {0, 0, 0, 0};
+    const ActParam apa = make_act((kXform && p.a_xform == 1) ? p.a_act : ACT_NONE);
+    const ActParam apb = make_act((kXform && p.b_xform == 1) ? p.b_act : ACT_NONE);
+    const int na = p.a_mn ? 2 : 1;                                         // panels of A
+    const int nb = p.b_mn ? (p.block_n + 63) / 64 : (p.block_n + 127) / 128;  // panels of B
+
+    // (tile, k-block) cursor over this CTA's work
+    struct Cur { int w, kb, kb1, m_blk, n_blk; };
+    auto cur_set = [&](Cur& c) {
+      if (c.w < p.num_work) {
+        const int mn = c.w / p.ksplit, slab = c.w % p.ksplit;
+        c.m_blk = mn / p.n_blocks; c.n_blk = mn % p.n_blocks;
+        c.kb = slab * p.kb_per_split;
+        c.kb1 = min(c.kb + p.kb_per_split, p.num_k_blocks);
+      }
+    };
+    auto cur_next = [&](Cur& c) {
+      if (++c.kb >= c.kb1) { c.w += gridDim.x; cur_set(c); }
+    };
+    // geometry of panel pi (A panels first, then B) of the k-block at cursor c
+    struct Pan { uint32_t off; int rows, row0, col0, rlimit, climit, logR, cshift; bool isA, mn; };
+    auto panel_of = [&](const Cur& c, int pi) {
+      Pan g;
+      g.isA = pi < na;
+      const int q = g.isA ? pi : pi - na;
+      g.mn = g.isA ? (p.a_mn != 0) : (p.b_mn != 0);
+      g.off = (g.isA ? 0u : (uint32_t)kABytes) + (uint32_t)q * (g.mn ? kPanelBytes64 : 128 * 128);
+      g.logR = g.mn ? 6 : 7;
+      if (!g.mn) {  // K-major: rows are M (A) or N (B), channels along K
+        g.row0 = g.isA ? c.m_blk * kBlockM : c.n_blk * p.block_n + q * 128;
+        g.col0 = c.kb * kBlockK; g.climit = p.K;
+        g.rlimit = g.isA ? min(128, p.M - g.row0)
+                         : min(128, min(p.block_n - q * 128, p.N - g.row0));
+        g.rows = g.rlimit;     // rows past the limit only feed outputs that are never stored
+      } else {      // MN-major: rows are K (pixels), 64 channels of M/N per panel
+        g.row0 = c.kb * kBlockK;
+        g.col0 = (g.isA ? c.m_blk * kBlockM : c.n_blk * p.block_n) + q * 64;
+        g.climit = g.isA ? p.M : p.N;
+        g.rlimit = g.col0 < g.climit ? min(64, p.K - g.row0) : 0;
+        g.rows = 64;           // rows past K must read as zero: they are accumulated
+      }
+      if (g.rlimit < 0) g.rlimit = 0;
+      if (g.rows < 0) g.rows = 0;
+      // 16-byte chunk slots per row that the MMA can read: narrow operands (K or C <= 32) take
+      // 2 or 4 lanes per row instead of 8
+      int ncs = (g.climit - g.col0 + 7) >> 3;
+      if (!g.mn) ncs = (ncs + 1) & ~1;   // K-steps of 16 columns: the odd chunk must read as zero
+      g.cshift = ncs <= 2 ? 1 : (ncs <= 4 ? 2 : 3);
+      return g;
+    };
+    // cp.async one panel (coalesced: 8 consecutive threads fetch the 128 bytes of one row)
+    auto load_panel = [&](uint32_t dst, const __nv_bfloat16* src, long long ld, const Pan& g) {
+      const int rpw = ((1 << g.logR) / G);          // rows of the panel per warp of the group
+      const int rend = min(g.rows, (ls + 1) * rpw);
+      const int total = rend << g.cshift;
+      const __nv_bfloat16* base = src + (long long)g.row0 * ld + g.col0;
+#pragma unroll 4
+      for (int i = ((ls * rpw) << g.cshift) + ln; i < total; i += 32) {
+        const int r = i >> g.cshift, lc = i & ((1 << g.cshift) - 1);
+        const bool ok = r < g.rlimit && g.col0 + lc * 8 < g.climit;
+        const __nv_bfloat16* sp = ok ? base + (long long)r * ld + lc * 8 : src;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                         dst + (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4))),
+                     "l"(sp), "r"(ok ? 16 : 0)
+                     : "memory");
+      }
+    };
+    auto issue = [&](const Cur& c, int n) {
+      const int stage = n % S;
+      const long long tl0 = clock64();
+      MBAR_WAIT(&bars->empty[stage], ((n / S) & 1) ^ 1);
+      dbg_l[0] += clock64() - tl0;
+      const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
+      for (int pi = 0; pi < na + nb; ++pi) {
+        const Pan g = panel_of(c, pi);
+        if (kXform && (g.isA ? p.a_xform : p.b_xform) != 0) continue;   // register path (consume)
+        load_panel(sA + g.off, g.isA ? p.gA : p.gB, g.isA ? p.lda : p.ldb, g);
+      }
+    };
+    auto consume = [&](const Cur& c, int n) {
+      const int stage = n % S;
+      const long long tl3 = clock64();
+      if (kXform && use_x) {
+        const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        // narrow transformed operands: registers (few bytes per row, latency hidden by the batch)
+#pragma unroll 1
+        for (int pi = 0; pi < na + nb; ++pi) {
+          const Pan g = panel_of(c, pi);
+          const int mode = g.isA ? p.a_xform : p.b_xform;
+          if (mode == 0 || (g.isA ? p.a_tma : p.b_tma)) continue;
+          const ActParam& ap = g.isA ? apa : apb;
+          const float* tab = g.isA ? xa : xb;
+          const int Ct = g.isA ? Ca : Cb;
+          const uint32_t t_s = smem_u32(tab), t_b = smem_u32(tab + Ct), t_s2 = smem_u32(tab + 2 * Ct);
+          const float* gate = (mode == 1 && (g.mn || g.isA)) ? (g.isA ? p.a_gate : p.b_gate) : nullptr;
+          const __nv_bfloat16* g1 = (g.isA ? p.gA : p.gB) + (long long)g.row0 * (g.isA ? p.lda : p.ldb);
+          const __nv_bfloat16* g2 = mode == 2
+              ? (g.isA ? p.gA2 : p.gB2) + (long long)g.row0 * (g.isA ? p.lda2 : p.ldb2) : g1;
+          if (mode == 2)
+            gxform_panel<2, false>(sA + g.off, 0u, g1, g.isA ? p.lda : p.ldb, g2, g.isA ? p.lda2 : p.ldb2,
+                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
+                                   (unsigned)g.row0, (unsigned)p.gate_rps);
+          else
+            gxform_panel<1, false>(sA + g.off, 0u, g1, g.isA ? p.lda : p.ldb, g2, g.isA ? p.lda2 : p.ldb2,
+                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
+                                   (unsigned)g.row0, (unsigned)p.gate_rps);
+        }
+        // wide transformed operands: the TMA producer loaded them; rewrite the tile in place
+        if (p.a_tma || p.b_tma) {
+          const long long tl1 = clock64();
+          MBAR_WAIT(&bars->xdone[stage], (n / S) & 1);
+          dbg_l[1] += clock64() - tl1;
           if (!(p.dbg & 1)) {
 #pragma unroll 1
             for (int pi = 0; pi < na + nb; ++pi) {
-              const bool isA = pi < na;
-              const int q = isA ? pi : pi - na;
-              const bool mn = isA ? p.a_mn : p.b_mn;
-              const uint32_t opbase = isA ? sA : sB;
-              const uint32_t op2 = sA + (isA ? p.a2_off : p.b2_off);
-              const uint32_t poff = (uint32_t)q * (mn ? kPanelBytes64 : 128 * 128);
-              const int mode = isA ? p.a_xform : p.b_xform;
-              const ActParam& ap = isA ? apa : apb;
-              const float* tab = isA ? xa : xb;
-              const int Ct = isA ? Ca : Cb;
+              const Pan g = panel_of(c, pi);
+              const int mode = g.isA ? p.a_xform : p.b_xform;
+              if (mode == 0 || !(g.isA ? p.a_tma : p.b_tma)) continue;
+              const ActParam& ap = g.isA ? apa : apb;
+              const float* tab = g.isA ? xa : xb;
+              const int Ct = g.isA ? Ca : Cb;
               const uint32_t t_s = smem_u32(tab), t_b = smem_u32(tab + Ct), t_s2 = smem_u32(tab + 2 * Ct);
-              int cbase, climit, rlimit;
-              if (!mn) {  // K-major: channels along K, rows are M (A) or N (B)
-                cbase = kb * kBlockK; climit = p.K;
-                rlimit = isA ? p.M - m_blk * kBlockM : min(128, p.block_n - q * 128);
-              } else {    // MN-major: channels along M/N (64 per panel), rows are K (pixels)
-                const int c0p = (isA ? m_blk * kBlockM : n_blk * p.block_n) + q * 64;
-                cbase = c0p; climit = isA ? p.M : p.N;
-                rlimit = (c0p < climit) ? p.K - kb * kBlockK : 0;
-              }
-              // rows of a K-major A tile are pixels m; rows of an MN-major tile are pixels k
-              const long long pixbase = mn ? (long long)kb * kBlockK : (long long)m_blk * kBlockM;
-              const float* gate = (mode == 1 && (mn || isA)) ? (isA ? p.a_gate : p.b_gate) : nullptr;
-              xform_panel(opbase + poff, op2 + poff, mn ? 6 : 7, t, mode, ap, t_s, t_b, t_s2, cbase,
-                          climit, rlimit, gate, pixbase, p.gate_rps, p.wg2x ? 8 : 7);
+              const float* gate = (mode == 1 && (g.mn || g.isA)) ? (g.isA ? p.a_gate : p.b_gate) : nullptr;
+              const uint32_t op2 = sA + (g.isA ? p.a2_off : p.b2_off) +
+                                   (g.off - (g.isA ? 0u : (uint32_t)kABytes));
+              // rows the TMA zero-filled (outside the tensor) must stay zero: limit = rlimit
+              if (mode == 2)
+                gxform_panel<2, true>(sA + g.off, op2, nullptr, 0, nullptr, 0, ls * ((1 << g.logR) / G),
+                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap,
+                                      t_s, t_b, t_s2, g.col0, g.climit, gate, (unsigned)g.row0,
+                                      (unsigned)p.gate_rps);
+              else
+                gxform_panel<1, true>(sA + g.off, op2, nullptr, 0, nullptr, 0, ls * ((1 << g.logR) / G),
+                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap,
+                                      t_s, t_b, t_s2, g.col0, g.climit, gate, (unsigned)g.row0,
+                                      (unsigned)p.gate_rps);
             }
           }
-          if (!(p.dbg & 2)) fence_proxy_async_smem();
-          mbar_arrive(&bars->xdone[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
+      const long long tl2 = clock64();
+      dbg_l[2] += tl2 - tl3;
+      cp_async_wait_n<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (ln == 0) mbar_arrive(&bars->full[stage]);
+      dbg_l[3] += clock64() - tl2;
+    };
+
+    // One loader WARP fills a whole stage, and every stage has ONE owner warp (stage s belongs to
+    // warp s mod NW): the owner walks the rounds of its stage in order, so a parity wait on
+    // empty[s] can never alias a phase two rounds away.  Each warp has a single stage in flight, so
+    // the proxy fence before publishing it (a MEMBAR that waits for ALL of the thread's
+    // outstanding cp.async) never waits for younger copies; the CTA has min(NW, S) stages in flight.
+    Cur c;
+    c.w = blockIdx.x;
+    cur_set(c);
+    const long long dbg_l0 = clock64();
+    for (int n = 0; c.w < p.num_work; cur_next(c), ++n) {
+      if ((n % S) % NW != lw) continue;
+      issue(c, n);
+      cp_async_commit();
+      consume(c, n);
+    }
+    if ((p.dbg & 512) && ln == 0) {
+      atomicAdd(p.dbg_buf + 12, (unsigned long long)dbg_l[0]);
+      atomicAdd(p.dbg_buf + 13, (unsigned long long)dbg_l[1]);
+      atomicAdd(p.dbg_buf + 14, (unsigned long long)dbg_l[2]);
+      atomicAdd(p.dbg_buf + 15, (unsigned long long)dbg_l[3]);
+      atomicAdd(p.dbg_buf + 8, (unsigned long long)(clock64() - dbg_l0));
+      atomicAdd(p.dbg_buf + 9, 1ull);
     }
   }
 
@@ -837,8 +1081,21 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   const int b_panels = (p.block_n + 63) / 64;
   p.b_bytes = p.b_mn ? b_panels * kPanelBytes64 : ((p.block_n * 128 + 1023) / 1024) * 1024;
   int stage = kABytes + p.b_bytes;
-  if (p.a_xform == 2) { p.a2_off = stage; stage += kABytes; }
-  if (p.b_xform == 2) { p.b2_off = stage; stage += p.b_bytes; }
+  // wide transformed operands come in by TMA (128-byte box rows) and are rewritten in place, a
+  // second source needs its own region; narrow ones are combined in registers on their way in
+  p.a_tma = (p.a_xform != 0 && (p.a_mn ? a->M : a->K) >= 64) ? 1 : 0;
+  p.b_tma = (p.b_xform != 0 && (p.b_mn ? a->N : a->K) >= 64) ? 1 : 0;
+  int dbg_env = 0;
+  { const char* d = getenv("YAMB_GEMM_DEBUG"); dbg_env = d ? atoi(d) : 0;
+    if (dbg_env & 1024) p.a_tma = p.b_tma = 0; }
+  // transformed operands: 4 (2) loader warps share a stage so that its transform latency is short;
+  // plain GEMMs are bound by load latency: one warp per stage, as many stages in flight as warps
+  p.lgroup = 1;   // measured: 2 or 4 warps per stage are slower than one warp per stage (b3 project: 0.25 / 0.33 vs 0.23 ms)
+  if (dbg_env & 2048) p.lgroup = 4;
+  if (dbg_env & 4096) p.lgroup = 2;
+  p.a2_off = p.b2_off = 0;
+  if (p.a_tma && p.a_xform == 2) { p.a2_off = stage; stage += kABytes; }
+  if (p.b_tma && p.b_xform == 2) { p.b2_off = stage; stage += p.b_bytes; }
   p.stage_bytes = stage;
   const bool xf = p.a_xform || p.b_xform;
   const int Ca = p.a_xform ? (p.a_mn ? p.M : p.K) : 0;
@@ -870,25 +1127,44 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB, tmA2, tmB2, tmD;
+  memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB));
   memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB2, 0, sizeof(tmB2));
   memset(&tmD, 0, sizeof(tmD));
   int rc;
-  if (!p.a_mn) rc = make_map_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128);
-  else rc = make_map_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64);
-  if (rc) return rc;
-  if (!p.b_mn) rc = make_map_2d(&tmB, a->B, a->K, a->N, a->ldb, 64, p.block_n);
-  else rc = make_map_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, 64);
-  if (rc) return rc;
-  if (p.a_xform == 2) {
-    if (!p.a_mn) rc = make_map_2d(&tmA2, a->A2, a->K, a->M, a->lda2, 64, 128);
-    else rc = make_map_2d(&tmA2, a->A2, a->M, a->K, a->lda2, 64, 64);
+  if (p.a_tma) {
+    if (!p.a_mn) rc = make_map_2d(&tmA, a->A, a->K, a->M, a->lda, 64, 128);
+    else rc = make_map_2d(&tmA, a->A, a->M, a->K, a->lda, 64, 64);
     if (rc) return rc;
+    if (p.a_xform == 2) {
+      if (!p.a_mn) rc = make_map_2d(&tmA2, a->A2, a->K, a->M, a->lda2, 64, 128);
+      else rc = make_map_2d(&tmA2, a->A2, a->M, a->K, a->lda2, 64, 64);
+      if (rc) return rc;
+    }
   }
-  if (p.b_xform == 2) {
-    if (!p.b_mn) rc = make_map_2d(&tmB2, a->B2, a->K, a->N, a->ldb2, 64, p.block_n);
-    else rc = make_map_2d(&tmB2, a->B2, a->N, a->K, a->ldb2, 64, 64);
+  if (p.b_tma) {
+    if (!p.b_mn) rc = make_map_2d(&tmB, a->B, a->K, a->N, a->ldb, 64, p.block_n);
+    else rc = make_map_2d(&tmB, a->B, a->N, a->K, a->ldb, 64, 64);
     if (rc) return rc;
+    if (p.b_xform == 2) {
+      if (!p.b_mn) rc = make_map_2d(&tmB2, a->B2, a->K, a->N, a->ldb2, 64, p.block_n);
+      else rc = make_map_2d(&tmB2, a->B2, a->N, a->K, a->ldb2, 64, 64);
+      if (rc) return rc;
+    }
   }
+  // operands are fetched with 16-byte cp.async: pointers 16-byte aligned, leading dims % 8 == 0
+  {
+    const void* ptrs[4] = {a->A, a->B, p.a_xform == 2 ? a->A2 : a->A, p.b_xform == 2 ? a->B2 : a->B};
+    const long long lds[4] = {a->lda, a->ldb, p.a_xform == 2 ? a->lda2 : a->lda,
+                              p.b_xform == 2 ? a->ldb2 : a->ldb};
+    for (int i = 0; i < 4; ++i)
+      if (!ptrs[i] || (reinterpret_cast<uintptr_t>(ptrs[i]) & 15) || (lds[i] % 8) || lds[i] <= 0)
+        return set_error(YAMB_EINVAL, "GEMM operand %d: pointer must be 16-byte aligned, ld %% 8 == 0", i);
+  }
+  p.gA = (const __nv_bfloat16*)a->A; p.lda = a->lda;
+  p.gB = (const __nv_bfloat16*)a->B; p.ldb = a->ldb;
+  p.gA2 = (const __nv_bfloat16*)(p.a_xform == 2 ? a->A2 : nullptr); p.lda2 = a->lda2;
+  p.gB2 = (const __nv_bfloat16*)(p.b_xform == 2 ? a->B2 : nullptr); p.ldb2 = a->ldb2;
+  p.lookahead = stages - 1 < 3 ? stages - 1 : 3;
   if (a->epi != 2) {
     rc = make_map_2d(&tmD, a->D, a->N, a->M, a->ldd, 64, 32);  // one epilogue warp's rows
     if (rc) return rc;
@@ -912,9 +1188,9 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     else if (a->epi == 1) YAMB_GEMM_LAUNCH(true, 1, 512);
     else YAMB_GEMM_LAUNCH(true, 2, 512);
   } else {
-    if (a->epi == 0) YAMB_GEMM_LAUNCH(false, 0, 384);
-    else if (a->epi == 1) YAMB_GEMM_LAUNCH(false, 1, 384);
-    else YAMB_GEMM_LAUNCH(false, 2, 384);
+    if (a->epi == 0) YAMB_GEMM_LAUNCH(false, 0, 512);
+    else if (a->epi == 1) YAMB_GEMM_LAUNCH(false, 1, 512);
+    else YAMB_GEMM_LAUNCH(false, 2, 512);
   }
 #undef YAMB_GEMM_LAUNCH
   e = cudaGetLastError();
@@ -927,9 +1203,12 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     fprintf(stderr, "gemm dbg (cycles per epilogue warp): wait_full %.0f tmem_ld %.0f wait_store %.0f "
             "convert %.0f store %.0f stats %.0f total %.0f warps %.0f\n", h[0] / n, h[1] / n, h[2] / n,
             h[3] / n, h[4] / n, h[5] / n, h[6] / n, n);
-    fprintf(stderr, "   per CTA: producer wait_empty %.0f of %.0f; mma wait_full %.0f wait_tmem_empty %.0f; "
-            "stages %d out_bufs %d block_n %d\n", h[8] / (double)grid, h[9] / (double)grid,
-            h[10] / (double)grid, h[11] / (double)grid, p.num_stages, p.out_bufs, p.block_n);
+    const double lw_n = h[9] ? (double)h[9] : 1.0;
+    fprintf(stderr, "   per loader warp: wait_empty %.0f wait_tma %.0f xform(incl wait_tma) %.0f publish %.0f total %.0f "
+            "(warps %.0f); per CTA: mma wait_full %.0f wait_tmem_empty %.0f; stages %d out_bufs %d block_n %d "
+            "tma %d%d wg2x %d\n", h[12] / lw_n, h[13] / lw_n, h[14] / lw_n, h[15] / lw_n, h[8] / lw_n, lw_n,
+            h[10] / (double)grid, h[11] / (double)grid, p.num_stages, p.out_bufs, p.block_n, p.a_tma, p.b_tma,
+            p.wg2x);
   }
   return 0;
 }
