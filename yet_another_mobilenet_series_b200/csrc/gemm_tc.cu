@@ -258,48 +258,60 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
   const uint32_t lo2 = pack_bf16(ap.lo, ap.lo), hi2 = pack_bf16(ap.hi, ap.hi);
   const __nv_bfloat16* p1 = g1 + c0;
   const __nv_bfloat16* p2 = g2 + c0;
-  auto load_batch = [&](int rb, uint4 (&v)[NB], uint4 (&w)[MODE == 2 ? NB : 1]) {
+  // Straight-line batches (no per-chunk branches: the NB chunk bodies interleave, one warp has
+  // NB independent dependency chains in flight; with a branch per chunk a loader warp ran at
+  // ~0.1 IPC and the loaders bounded the GEMM).  `lean`: clamp-type activation, no SE gate.
+  const bool lean = ap.kind == 0 && gate == nullptr;
+  const uint32_t swz = (uint32_t)(lc << 4);
+#pragma unroll 1
+  for (int rb = rbeg + (ln >> 3); rb < rows; rb += 4 * NB) {
+    uint4 v[NB], w[MODE == 2 ? NB : 1];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const int r = rb + 4 * j;
       const bool ok = cok && r < rlimit;
-      v[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (MODE == 2) w[j] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok) {
-        if (SMEM) {   // the TMA producer put the raw tile(s) there: rewrite in place
-          const uint32_t off = (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4));
-          v[j] = lds128(panel + off);
-          if (MODE == 2) w[j] = lds128(panel2 + off);
-        } else {
+      if (SMEM) {   // the TMA producer put the raw tile(s) there: rewrite in place
+        const uint32_t off = (uint32_t)(r * 128) + (swz ^ (uint32_t)((r & 7) << 4));
+        const bool in = r < rows;   // (always a valid shared address; value unused otherwise)
+        v[j] = in ? lds128(panel + off) : make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 2) w[j] = in ? lds128(panel2 + off) : make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        v[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 2) w[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) {
           v[j] = __ldg(reinterpret_cast<const uint4*>(p1 + (long long)r * ld1));
           if (MODE == 2) w[j] = __ldg(reinterpret_cast<const uint4*>(p2 + (long long)r * ld2));
         }
       }
     }
-  };
-  auto proc_batch = [&](int rb, const uint4 (&v)[NB], const uint4 (&w)[MODE == 2 ? NB : 1]) {
+    uint32_t o[NB][4];
+    if (MODE == 2) {
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int r = rb + 4 * j;
-      if (r >= rows) continue;
-      const bool ok = cok && r < rlimit;
-      const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-      uint32_t o[4];
-      if (MODE == 2) {
+      for (int j = 0; j < NB; ++j) {
+        const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
         const uint32_t yv[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 t1 = ffma2(s2[e], make_float2(bf16lo(yv[e]), bf16hi(yv[e])), sh[e]);
           const float2 d = ffma2(sc[e], make_float2(bf16lo(xv[e]), bf16hi(xv[e])), t1);
-          o[e] = pack_bf16(d.x, d.y);
+          o[j][e] = pack_bf16(d.x, d.y);
         }
-      } else if (ap.kind == 0 && gate == nullptr) {
+      }
+    } else if (lean) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 d = ffma2(sc[e], make_float2(bf16lo(xv[e]), bf16hi(xv[e])), sh[e]);
-          o[e] = clamp_bf16x2(pack_bf16(d.x, d.y), lo2, hi2);
+          o[j][e] = clamp_bf16x2(pack_bf16(d.x, d.y), lo2, hi2);
         }
-      } else {
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {   // swish / h-swish / SE gate
+        const int r = rb + 4 * j;
+        const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
         float x[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -307,7 +319,7 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
           x[2 * e] = d.x; x[2 * e + 1] = d.y;
         }
         act_vec<8>(x, ap);
-        if (gate != nullptr && ok) {
+        if (gate != nullptr && cok && r < rlimit) {
           // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
           const float* gr = gate + (size_t)((pixbase + (unsigned)r) / rps) * C + c0;
           const float4 q0 = __ldg(reinterpret_cast<const float4*>(gr));
@@ -317,18 +329,17 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
           for (int e = 0; e < 8; ++e) x[e] = round_bf16(x[e]) * gq[e];
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = pack_bf16(x[2 * e], x[2 * e + 1]);
+        for (int e = 0; e < 4; ++e) o[j][e] = pack_bf16(x[2 * e], x[2 * e + 1]);
       }
-      sts128(panel + (uint32_t)(r * 128 + ((lc ^ (r & 7)) << 4)),
-             make_uint4(ok ? o[0] : 0u, ok ? o[1] : 0u, ok ? o[2] : 0u, ok ? o[3] : 0u));
     }
-  };
-  // (narrow operands only: one register batch in flight per lane)
-  uint4 va[NB], wa[MODE == 2 ? NB : 1];
-#pragma unroll 1
-  for (int rb = rbeg + (ln >> 3); rb < rows; rb += 4 * NB) {
-    load_batch(rb, va, wa);
-    proc_batch(rb, va, wa);
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int r = rb + 4 * j;
+      const bool ok = cok && r < rlimit;
+      if (r < rows)
+        sts128(panel + (uint32_t)(r * 128) + (swz ^ (uint32_t)((r & 7) << 4)),
+               make_uint4(ok ? o[j][0] : 0u, ok ? o[j][1] : 0u, ok ? o[j][2] : 0u, ok ? o[j][3] : 0u));
+    }
   }
 }
 
@@ -556,7 +567,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
       const int n_sub = min((p.block_n + 63) / 64, (p.N - n_blk * p.block_n + 63) / 64);
       long long tq0 = clock64();
-      MBAR_WAIT(&bars->tmem_full[as], (it >> 1) & 1);
+      if (p.dbg & 256) mbar_wait_spin(&bars->tmem_full[as], (it >> 1) & 1);
+      else mbar_wait_relaxed(&bars->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
       dbg_t[0] += clock64() - tq0;
       // NOT unrolled: one copy of the sub-tile body keeps the epilogue inside the instruction
@@ -787,12 +799,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     // (tile, k-block) cursor over this CTA's work
     struct Cur { int w, kb, kb1, m_blk, n_blk; };
+    const bool simple_work = p.ksplit == 1 && p.n_blocks == 1;   // one work item = one m-block
     auto cur_set = [&](Cur& c) {
       if (c.w < p.num_work) {
-        const int mn = c.w / p.ksplit, slab = c.w % p.ksplit;
-        c.m_blk = mn / p.n_blocks; c.n_blk = mn % p.n_blocks;
-        c.kb = slab * p.kb_per_split;
-        c.kb1 = min(c.kb + p.kb_per_split, p.num_k_blocks);
+        if (simple_work) {
+          c.m_blk = c.w; c.n_blk = 0; c.kb = 0; c.kb1 = p.num_k_blocks;
+        } else {
+          const int mn = c.w / p.ksplit, slab = c.w % p.ksplit;
+          c.m_blk = mn / p.n_blocks; c.n_blk = mn % p.n_blocks;
+          c.kb = slab * p.kb_per_split;
+          c.kb1 = min(c.kb + p.kb_per_split, p.num_k_blocks);
+        }
       }
     };
     auto cur_next = [&](Cur& c) {
@@ -846,10 +863,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                      : "memory");
       }
     };
-    auto issue = [&](const Cur& c, int n) {
-      const int stage = n % S;
+    auto issue = [&](const Cur& c, int stage, int rnd) {
       const long long tl0 = clock64();
-      MBAR_WAIT(&bars->empty[stage], ((n / S) & 1) ^ 1);
+      MBAR_WAIT(&bars->empty[stage], (rnd & 1) ^ 1);
       dbg_l[0] += clock64() - tl0;
       const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
       for (int pi = 0; pi < na + nb; ++pi) {
@@ -858,8 +874,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         load_panel(sA + g.off, g.isA ? p.gA : p.gB, g.isA ? p.lda : p.ldb, g);
       }
     };
-    auto consume = [&](const Cur& c, int n) {
-      const int stage = n % S;
+    auto consume = [&](const Cur& c, int stage, int rnd) {
       const long long tl3 = clock64();
       if (kXform && use_x) {
         const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -889,7 +904,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // wide transformed operands: the TMA producer loaded them; rewrite the tile in place
         if (p.a_tma || p.b_tma) {
           const long long tl1 = clock64();
-          MBAR_WAIT(&bars->xdone[stage], (n / S) & 1);
+          MBAR_WAIT(&bars->xdone[stage], rnd & 1);
           dbg_l[1] += clock64() - tl1;
           if (!(p.dbg & 1)) {
 #pragma unroll 1
@@ -937,11 +952,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     c.w = blockIdx.x;
     cur_set(c);
     const long long dbg_l0 = clock64();
-    for (int n = 0; c.w < p.num_work; cur_next(c), ++n) {
-      if ((n % S) % NW != lw) continue;
-      issue(c, n);
-      cp_async_commit();
-      consume(c, n);
+    // n = running k-block index, st = n % S, rnd = n / S (no divisions in the loop)
+    int st = 0, rnd = 0;
+    for (; c.w < p.num_work; cur_next(c)) {
+      if (st % NW == lw) {
+        issue(c, st, rnd);
+        cp_async_commit();
+        consume(c, st, rnd);
+      }
+      if (++st == S) { st = 0; ++rnd; }
     }
     if ((p.dbg & 512) && ln == 0) {
       atomicAdd(p.dbg_buf + 12, (unsigned long long)dbg_l[0]);
