@@ -181,7 +181,29 @@ typedef struct yamb_bn_reduce {
   int64_t M; int32_t C; int32_t lddy, ldh;
   const void* dy; const void* h;
   const yamb_bn_bwd* bn;
+  /* optional activation AFTER this BatchNorm (ConvBNReLU tail, models/mobilenet_base.py:181-203):
+   * the statistics are those of dz = dy * act'(z_scale*h + z_shift); NULL = no activation */
+  const float* z_scale; const float* z_shift; int32_t z_act;
 } yamb_bn_reduce;
+
+/* Stand-alone BatchNorm(+activation) of a convolution this library does not run itself (the stem
+ * 3x3 and the 1x1 head ConvBNReLU, reference models/mobilenet_base.py:181-203 via :143-171 of
+ * mobilenet_supernet.py): batch statistics of the raw conv output ... */
+typedef struct yamb_bn_stats {
+  int64_t M; int32_t C; int32_t ldh;
+  const void* h;               /* [M][ldh] bf16 raw conv output */
+  const yamb_bn_fwd* bn;       /* finalize: scale/shift/mean/invstd/running statistics */
+} yamb_bn_stats;
+
+/* ... and its input gradient dh = ca*dz + cb*h + cc with dz = dy * act'(z_scale*h + z_shift)
+ * (ca/cb/cc from yamb_bn_reduce_bwd's finalize). */
+typedef struct yamb_bn_bwd_apply {
+  int64_t M; int32_t C; int32_t lddy, ldh, lddh;
+  const void* dy; const void* h;
+  const float* z_scale; const float* z_shift; int32_t z_act;   /* NULL scale = no activation */
+  const float* ca; const float* cb; const float* cc;
+  void* dh;
+} yamb_bn_bwd_apply;
 
 typedef struct yamb_se_pool {
   int32_t N, HW, C, ldh;
@@ -212,6 +234,8 @@ int yamb_bn_apply_fwd(const yamb_bn_apply* args, yamb_stream_t stream);
 int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* args, yamb_stream_t stream);
 int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* args, yamb_stream_t stream);
 int yamb_bn_reduce_bwd(const yamb_bn_reduce* args, yamb_stream_t stream);
+int yamb_bn_stats_fwd(const yamb_bn_stats* args, yamb_stream_t stream);
+int yamb_bn_bwd_apply_bwd(const yamb_bn_bwd_apply* args, yamb_stream_t stream);
 int yamb_se_pool_fwd(const yamb_se_pool* args, yamb_stream_t stream);
 
 /* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
@@ -241,7 +265,8 @@ int yamb_cast_bf16(const float* src, void* dst, int64_t n, yamb_stream_t stream)
 int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
- * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply) so bindings can self-check */
+ * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply, 11 bn_stats,
+ * 12 bn_bwd_apply) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

@@ -63,6 +63,8 @@ int yamb_struct_size(int which) {
     case 8: return (int)sizeof(yamb_rmsprop);
     case 9: return (int)sizeof(yamb_se_bwd_reduce);
     case 10: return (int)sizeof(yamb_se_bwd_apply);
+    case 11: return (int)sizeof(yamb_bn_stats);
+    case 12: return (int)sizeof(yamb_bn_bwd_apply);
     default: return -1;
   }
 }
@@ -77,6 +79,8 @@ int yamb_depthwise_fwd(const yamb_dw_fwd* a, yamb_stream_t s) { return yamb::dw_
 int yamb_depthwise_bwd(const yamb_dw_bwd* a, yamb_stream_t s) { return yamb::dw_bwd_launch(a, YAMB_ST(s)); }
 int yamb_bn_apply_fwd(const yamb_bn_apply* a, yamb_stream_t s) { return yamb::bn_apply_launch(a, YAMB_ST(s)); }
 int yamb_bn_reduce_bwd(const yamb_bn_reduce* a, yamb_stream_t s) { return yamb::bn_reduce_launch(a, YAMB_ST(s)); }
+int yamb_bn_stats_fwd(const yamb_bn_stats* a, yamb_stream_t s) { return yamb::bn_stats_launch(a, YAMB_ST(s)); }
+int yamb_bn_bwd_apply_bwd(const yamb_bn_bwd_apply* a, yamb_stream_t s) { return yamb::bn_bwd_apply_launch(a, YAMB_ST(s)); }
 int yamb_se_pool_fwd(const yamb_se_pool* a, yamb_stream_t s) { return yamb::se_pool_launch(a, YAMB_ST(s)); }
 int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* a, yamb_stream_t s) { return yamb::se_bwd_reduce_launch(a, YAMB_ST(s)); }
 int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* a, yamb_stream_t s) { return yamb::se_bwd_apply_launch(a, YAMB_ST(s)); }

@@ -76,6 +76,8 @@ struct BnReduceDev {
   const __nv_bfloat16* dy;
   const __nv_bfloat16* h;
   yamb_bn_bwd bn;
+  const float *z_scale, *z_shift;   // optional activation after the BatchNorm: dz = dy*act'(z)
+  int z_act;
 };
 
 // sum(dy), sum(dy * xhat) with xhat = (h - mean) * invstd; thread owns one 8-channel group.
@@ -91,18 +93,27 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ 
     const int px = CG >= 256 ? 0 : threadIdx.x / CG;
     if (cg < CG && px < PX) {
       const int c0 = cg * 8;
-      float mu[8], rs[8], s[8], q[8];
+      float mu[8], rs[8], s[8], q[8], zs[8], zt[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         mu[e] = __ldg(p.bn.mean + c0 + e);
         rs[e] = __ldg(p.bn.invstd + c0 + e);
+        zs[e] = p.z_scale ? __ldg(p.z_scale + c0 + e) : 1.f;
+        zt[e] = p.z_scale ? __ldg(p.z_shift + c0 + e) : 0.f;
         s[e] = q[e] = 0.f;
       }
+      const ActParam zap = make_act(p.z_scale ? p.z_act : ACT_NONE);
       for (long long row = (long long)blockIdx.x * PX + px; row < p.M;
            row += (long long)gridDim.x * PX) {
         float d[8], hv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.lddy + c0)), d);
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
+        if (p.z_scale) {
+          float z[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = fmaf(zs[e], hv[e], zt[e]);
+          act_bwd_vec<8>(d, z, zap, p.z_act);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           s[e] += d[e];
@@ -121,6 +132,88 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ 
     bn_bwd_finalize(p.bn, p.C);
     __syncthreads();
     if (threadIdx.x == 0) *p.bn.counter = 0;
+  }
+}
+
+// Stand-alone BatchNorm of a convolution run elsewhere (stem / head ConvBNReLU): per-channel
+// sum(h), sum(h^2) + BatchNorm forward finalize (last CTA).  Same thread layout as bn_reduce.
+struct BnStatsDev {
+  long long M;
+  int C, ldh;
+  const __nv_bfloat16* h;
+  yamb_bn_fwd bn;
+};
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __grid_constant__ BnStatsDev p) {
+  extern __shared__ float s_part[];  // [2][C]
+  const int CG = p.C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  __syncthreads();
+  for (int cgb = 0; cgb < CG; cgb += 256) {
+    const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
+    const int px = CG >= 256 ? 0 : threadIdx.x / CG;
+    if (cg < CG && px < PX) {
+      const int c0 = cg * 8;
+      float s[8], q[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+      for (long long row = (long long)blockIdx.x * PX + px; row < p.M;
+           row += (long long)gridDim.x * PX) {
+        float hv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          s[e] += hv[e];
+          q[e] = fmaf(hv[e], hv[e], q[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        atomicAdd(&s_part[c0 + e], s[e]);
+        atomicAdd(&s_part[p.C + c0 + e], q[e]);
+      }
+    }
+  }
+  __syncthreads();
+  if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
+    bn_fwd_finalize(p.bn, p.C);
+    __syncthreads();
+    if (threadIdx.x == 0) *p.bn.counter = 0;
+  }
+}
+
+// dh = ca*dz + cb*h + cc,  dz = dy * act'(z_scale*h + z_shift)
+struct BnBwdApplyDev {
+  long long M;
+  int C, lddy, ldh, lddh;
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* h;
+  const float *z_scale, *z_shift;
+  int z_act;
+  const float *ca, *cb, *cc;
+  __nv_bfloat16* dh;
+};
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __grid_constant__ BnBwdApplyDev p) {
+  const int CG = p.C / 8;
+  const long long total = p.M * CG;
+  const ActParam zap = make_act(p.z_scale ? p.z_act : ACT_NONE);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / CG;
+    const int c0 = (int)(i % CG) * 8;
+    float d[8], hv[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.lddy + c0)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
+    if (p.z_scale) {
+      float z[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) z[e] = fmaf(__ldg(p.z_scale + c0 + e), hv[e], __ldg(p.z_shift + c0 + e));
+      act_bwd_vec<8>(d, z, zap, p.z_act);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      d[e] = fmaf(__ldg(p.ca + c0 + e), d[e], fmaf(__ldg(p.cb + c0 + e), hv[e], __ldg(p.cc + c0 + e)));
+    *reinterpret_cast<uint4*>(p.dh + row * p.lddh + c0) = pack8(d);
   }
 }
 
@@ -312,6 +405,8 @@ int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t st) {
   BnReduceDev p;
   p.M = a->M; p.C = a->C; p.lddy = a->lddy; p.ldh = a->ldh;
   p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h; p.bn = *a->bn;
+  p.z_scale = a->z_scale; p.z_shift = a->z_scale ? a->z_shift : nullptr; p.z_act = a->z_act;
+  if (a->z_scale && !a->z_shift) return set_error(YAMB_EINVAL, "bn_reduce: z_scale without z_shift");
   const int CG = a->C / 8;
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
   long long want = (a->M + PX - 1) / PX;
@@ -319,6 +414,42 @@ int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t st) {
   bn_reduce_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_reduce: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int bn_stats_launch(const yamb_bn_stats* a, cudaStream_t st) {
+  if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8) || (a->ldh % 8) || !a->h || !a->bn)
+    return set_error(YAMB_EINVAL, "bn_stats args");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  BnStatsDev p;
+  p.M = a->M; p.C = a->C; p.ldh = a->ldh;
+  p.h = (const __nv_bfloat16*)a->h; p.bn = *a->bn;
+  const int CG = a->C / 8;
+  const int PX = 256 / CG > 0 ? 256 / CG : 1;
+  long long want = (a->M + PX - 1) / PX;
+  int grid = (int)(want < (long long)4 * max_ctas() ? want : 4 * max_ctas());
+  bn_stats_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_stats: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int bn_bwd_apply_launch(const yamb_bn_bwd_apply* a, cudaStream_t st) {
+  if (!a || a->M <= 0 || a->C <= 0 || (a->C % 8) || (a->ldh % 8) || (a->lddy % 8) || (a->lddh % 8) ||
+      !a->dy || !a->h || !a->dh || !a->ca || !a->cb || !a->cc)
+    return set_error(YAMB_EINVAL, "bn_bwd_apply args");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  BnBwdApplyDev p;
+  p.M = a->M; p.C = a->C; p.lddy = a->lddy; p.ldh = a->ldh; p.lddh = a->lddh;
+  p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
+  p.z_scale = a->z_scale; p.z_shift = a->z_shift; p.z_act = a->z_act;
+  p.ca = a->ca; p.cb = a->cb; p.cc = a->cc; p.dh = (__nv_bfloat16*)a->dh;
+  const long long total = a->M * (a->C / 8);
+  long long want = (total + 255) / 256;
+  int grid = (int)(want < (long long)16 * max_ctas() ? want : 16 * max_ctas());
+  bn_bwd_apply_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_bwd_apply: %s", cudaGetErrorString(e));
   return 0;
 }
 

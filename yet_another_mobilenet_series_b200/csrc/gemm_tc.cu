@@ -232,12 +232,14 @@ __device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int
 template <int MODE, bool SMEM>
 __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, const __nv_bfloat16* g1, long long ld1,
                                              const __nv_bfloat16* g2, long long ld2, int rbeg, int rows,
-                                             int rlimit, int ln, const ActParam& ap,
+                                             int rlimit, int ln, int cs, const ActParam& ap,
                                              uint32_t tab_s, uint32_t tab_b, uint32_t tab_s2,
                                              int col0, int C, const float* gate, unsigned pixbase,
                                              unsigned rps) {
   constexpr int NB = MODE == 2 ? 4 : 8;   // rows in flight per lane (16 B each, x2 sources in mode 2)
-  const int lc = ln & 7;
+  // 2^cs lanes per row (8 for 64-channel panels; 4 / 2 for narrow operands so that no lane idles)
+  const int lc = ln & ((1 << cs) - 1);
+  const int RS = 32 >> cs;                // rows covered by one warp-wide access
   const int c0 = col0 + lc * 8;
   const bool cok = c0 < C;
   float2 sc[4], sh[4], s2[4];
@@ -264,11 +266,11 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
   const bool lean = ap.kind == 0 && gate == nullptr;
   const uint32_t swz = (uint32_t)(lc << 4);
 #pragma unroll 1
-  for (int rb = rbeg + (ln >> 3); rb < rows; rb += 4 * NB) {
+  for (int rb = rbeg + (ln >> cs); rb < rows; rb += RS * NB) {
     uint4 v[NB], w[MODE == 2 ? NB : 1];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      const int r = rb + 4 * j;
+      const int r = rb + RS * j;
       const bool ok = cok && r < rlimit;
       if (SMEM) {   // the TMA producer put the raw tile(s) there: rewrite in place
         const uint32_t off = (uint32_t)(r * 128) + (swz ^ (uint32_t)((r & 7) << 4));
@@ -310,7 +312,7 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
     } else {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {   // swish / h-swish / SE gate
-        const int r = rb + 4 * j;
+        const int r = rb + RS * j;
         const uint32_t xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
         float x[8];
 #pragma unroll
@@ -334,7 +336,7 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
-      const int r = rb + 4 * j;
+      const int r = rb + RS * j;
       const bool ok = cok && r < rlimit;
       if (r < rows)
         sts128(panel + (uint32_t)(r * 128) + (swz ^ (uint32_t)((r & 7) << 4)),
@@ -701,24 +703,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
             const int rmax = min(32, p.M - (m_blk * kBlockM + q * 32));
             if (p.has_bnf) {
-              for (int r = 0; r < rmax; ++r) {
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(
-                    sO + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-                const float a = bf16lo(u), b = bf16hi(u);
-                s0 += a; s1 += b;
-                q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+              if (rmax == 32) {
+                // full sub-tile: 4 independent accumulator sets (a 32-deep dependent chain of
+                // LDS -> FADD/FFMA was ~1500 cycles on the epilogue's critical path per sub-tile)
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                auto rowf = [&](int r, float& S0, float& S1, float& Q0, float& Q1) {
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                      sO + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                  const float a = bf16lo(u), b = bf16hi(u);
+                  S0 += a; S1 += b;
+                  Q0 = fmaf(a, a, Q0); Q1 = fmaf(b, b, Q1);
+                };
+#pragma unroll
+                for (int r = 0; r < 32; r += 4) {
+                  rowf(r, a0, b0, c0, d0);
+                  rowf(r + 1, a1, b1, c1, d1);
+                  rowf(r + 2, a2, b2, c2, d2);
+                  rowf(r + 3, a3, b3, c3, d3);
+                }
+                s0 = (a0 + a1) + (a2 + a3); s1 = (b0 + b1) + (b2 + b3);
+                q0 = (c0 + c1) + (c2 + c3); q1 = (d0 + d1) + (d2 + d3);
+              } else {
+                for (int r = 0; r < rmax; ++r) {
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                      sO + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+                  const float a = bf16lo(u), b = bf16hi(u);
+                  s0 += a; s1 += b;
+                  q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+                }
               }
             } else {
               const float m0 = cz_m[c], m1 = cz_m[c + 1], r0 = cz_r[c], r1 = cz_r[c + 1];
-              for (int r = 0; r < rmax; ++r) {
+              float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f, qa = 0.f, qb = 0.f, ra = 0.f, rb2 = 0.f;
+              auto rowacc = [&](int r, float& S0, float& S1, float& Q0, float& Q1) {
                 const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
                 const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + off);
                 const uint32_t hh = *reinterpret_cast<const uint32_t*>(s_h + off);
                 const float a = bf16lo(u), b = bf16hi(u);
-                s0 += a; s1 += b;
-                q0 = fmaf(a, (bf16lo(hh) - m0) * r0, q0);
-                q1 = fmaf(b, (bf16hi(hh) - m1) * r1, q1);
+                S0 += a; S1 += b;
+                Q0 = fmaf(a, (bf16lo(hh) - m0) * r0, Q0);
+                Q1 = fmaf(b, (bf16hi(hh) - m1) * r1, Q1);
+              };
+              int r = 0;
+#pragma unroll 4
+              for (; r + 1 < rmax; r += 2) {   // two independent accumulator sets
+                rowacc(r, sa, ta, qa, ra);
+                rowacc(r + 1, sb, tb, qb, rb2);
               }
+              if (r < rmax) rowacc(r, sa, ta, qa, ra);
+              s0 = sa + sb; s1 = ta + tb; q0 = qa + qb; q1 = ra + rb2;
             }
             if (reg_stats) {
               switch (sub) {  // constant register indices in every case
@@ -894,11 +928,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ? (g.isA ? p.gA2 : p.gB2) + (long long)g.row0 * (g.isA ? p.lda2 : p.ldb2) : g1;
           if (mode == 2)
             gxform_panel<2, false>(sA + g.off, 0u, g1, g.isA ? p.lda : p.ldb, g2, g.isA ? p.lda2 : p.ldb2,
-                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
+                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, g.cshift, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
                                    (unsigned)g.row0, (unsigned)p.gate_rps);
           else
             gxform_panel<1, false>(sA + g.off, 0u, g1, g.isA ? p.lda : p.ldb, g2, g.isA ? p.lda2 : p.ldb2,
-                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
+                                   ls * ((1 << g.logR) / G), min(g.rows, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, g.cshift, ap, t_s, t_b, t_s2, g.col0, g.climit, gate,
                                    (unsigned)g.row0, (unsigned)p.gate_rps);
         }
         // wide transformed operands: the TMA producer loaded them; rewrite the tile in place
@@ -922,12 +956,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // rows the TMA zero-filled (outside the tensor) must stay zero: limit = rlimit
               if (mode == 2)
                 gxform_panel<2, true>(sA + g.off, op2, nullptr, 0, nullptr, 0, ls * ((1 << g.logR) / G),
-                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap,
+                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, 3, ap,
                                       t_s, t_b, t_s2, g.col0, g.climit, gate, (unsigned)g.row0,
                                       (unsigned)p.gate_rps);
               else
                 gxform_panel<1, true>(sA + g.off, op2, nullptr, 0, nullptr, 0, ls * ((1 << g.logR) / G),
-                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, ap,
+                                      min(g.rlimit, (ls + 1) * ((1 << g.logR) / G)), g.rlimit, ln, 3, ap,
                                       t_s, t_b, t_s2, g.col0, g.climit, gate, (unsigned)g.row0,
                                       (unsigned)p.gate_rps);
             }
@@ -1064,7 +1098,11 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     p.dbg_buf = dbuf;
   }
   // transform-heavy / epilogue-light launches give warps 8-11 to the transform
-  p.wg2x = ((a->a_xform || a->b_xform) && (a->epi == 2 || (a->epi == 0 && p.block_n <= 192))) ? 1 : 0;
+  // warps 8-11 load/transform instead of running a second epilogue warpgroup when the epilogue
+  // is light relative to the operand work: split-K wgrad (no store at all) or a forward/dgrad
+  // store of <= 192 columns fed by more than one k-block per tile
+  p.wg2x = ((a->a_xform || a->b_xform) &&
+            (a->epi == 2 || (a->epi == 0 && p.block_n <= 192 && p.num_k_blocks >= 2))) ? 1 : 0;
   if (p.dbg & 16) p.wg2x = 0;
   if (p.dbg & 32) p.wg2x = (a->a_xform || a->b_xform) ? 1 : 0;
   p.a_gate = a->a_xform == 1 ? a->a_gate : nullptr;
@@ -1109,9 +1147,6 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     if (dbg_env & 1024) p.a_tma = p.b_tma = 0; }
   // transformed operands: 4 (2) loader warps share a stage so that its transform latency is short;
   // plain GEMMs are bound by load latency: one warp per stage, as many stages in flight as warps
-  p.lgroup = 1;   // measured: 2 or 4 warps per stage are slower than one warp per stage (b3 project: 0.25 / 0.33 vs 0.23 ms)
-  if (dbg_env & 2048) p.lgroup = 4;
-  if (dbg_env & 4096) p.lgroup = 2;
   p.a2_off = p.b2_off = 0;
   if (p.a_tma && p.a_xform == 2) { p.a2_off = stage; stage += kABytes; }
   if (p.b_tma && p.b_xform == 2) { p.b2_off = stage; stage += p.b_bytes; }
@@ -1136,6 +1171,22 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return set_error(YAMB_EINVAL, "GEMM tile does not fit shared memory");
   p.num_stages = stages;
+  // Throughput-bound launches (many k-blocks per CTA): one loader warp per stage, all warps on
+  // different stages (measured on b3: 2 / 4 warps per stage are 10 / 40 % slower).  Latency-bound
+  // launches (a handful of k-blocks per CTA: 7x7 / 14x14 layers, split-K tails): the spare warps
+  // share a stage so that its load/transform latency, which then IS the kernel time, shrinks.
+  {
+    const int grid_est = p.num_work < ctas ? p.num_work : ctas;
+    const long long iters = ((long long)(p.num_work + grid_est - 1) / grid_est) * p.kb_per_split;
+    const int nlw = p.wg2x ? 8 : 4;
+    p.lgroup = 1;
+    while (p.lgroup < 4 && (long long)(nlw / (p.lgroup * 2)) >= iters) p.lgroup *= 2;
+    // fewer stages than loader warps: the surplus warps would idle — let them share stages
+    while (p.lgroup < 4 && nlw / (p.lgroup * 2) >= stages) p.lgroup *= 2;
+  }
+  if (dbg_env & 2048) p.lgroup = 4;
+  if (dbg_env & 4096) p.lgroup = 2;
+  if (dbg_env & 8192) p.lgroup = 1;
   int off = stages * p.stage_bytes;
   p.off_out = off; off += out_bytes;
   p.off_hside = off; off += side_bytes;

@@ -21,6 +21,8 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t stream);
 int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t stream);
 int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t stream);
 int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t stream);
+int bn_stats_launch(const yamb_bn_stats* a, cudaStream_t stream);
+int bn_bwd_apply_launch(const yamb_bn_bwd_apply* a, cudaStream_t stream);
 int se_pool_launch(const yamb_se_pool* a, cudaStream_t stream);
 int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t stream);
 int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t stream);

@@ -923,6 +923,123 @@ class _PadFn(torch.autograd.Function):
         return (dx, None) + tuple(pgrads)
 
 
+# ------------------------------------------------------------------------------------------------
+# Stand-alone BatchNorm + activation behind a convolution torch runs (stem 3x3 / head 1x1
+# ConvBNReLU, reference models/mobilenet_base.py:181-203): raw conv output h [N,H,W,C] bf16 ->
+# statistics kernel (+ finalize) -> y = act(scale*h + shift); backward: statistics of
+# dz = dy*act'(z) (+ finalize: dgamma, dbeta, ca/cb/cc) -> dh = ca*dz + cb*h + cc.
+# ------------------------------------------------------------------------------------------------
+class _BnActState:
+    def __init__(self, bn, dev):
+        self.bn = _Bn([bn], dev)
+        self.ws = Workspace.get(dev)
+        self.keep = []
+        self.gbuf = None
+
+
+def _bn_act_state(bn, dev):
+    st = bn.__dict__.get("_yamb_bnact")
+    if st is None or st.bn.dev != dev:
+        st = _BnActState(bn, dev)
+        bn.__dict__["_yamb_bnact"] = st
+    return st
+
+
+class _BnActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, bn, act, weight, bias):
+        lib = nat.lib()
+        st = _bn_act_state(bn, h.device)
+        st.keep = []
+        b = st.bn
+        N, Cc, H, W = h.shape
+        M = N * H * W
+        hm = h.permute(0, 2, 3, 1).reshape(M, Cc)        # view of the channels_last storage
+        if b.batch_stats:
+            f = nat.BnFwd()
+            f.partials, f.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+            f.gamma, f.beta = nat.ptr(bn.weight), nat.ptr(bn.bias)
+            f.eps, f.momentum = b.eps, b.momentum_value()
+            if bn.track_running_stats and bn.running_mean is not None:
+                f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+                f.num_batches_tracked = nat.ptr(bn.num_batches_tracked)
+            f.scale, f.shift = b.scale.data_ptr(), b.shift.data_ptr()
+            f.mean, f.invstd = b.mean.data_ptr(), b.invstd.data_ptr()
+            f.count = M
+            s = nat.BnStats()
+            s.M, s.C, s.ldh, s.h, s.bn = M, Cc, Cc, hm.data_ptr(), C.pointer(f)
+            st.keep += [f, s]
+            launch(lib.yamb_bn_stats_fwd, s, "bn_stats", 2 * M * Cc)
+        else:
+            with torch.no_grad():
+                b.eval_coeffs()
+        y = torch.empty_like(h, memory_format=torch.channels_last)
+        a = nat.BnApply()
+        a.M, a.C, a.ldh, a.ldr, a.ldy = M, Cc, Cc, Cc, Cc
+        a.h, a.scale, a.shift, a.act = hm.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), act
+        a.y = y.data_ptr()
+        st.keep.append(a)
+        launch(lib.yamb_bn_apply_fwd, a, "bn_apply", 4 * M * Cc)
+        ctx.bn, ctx.act, ctx.st = bn, act, st
+        ctx.save_for_backward(h)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = nat.lib()
+        (h,) = ctx.saved_tensors
+        bn, act, st = ctx.bn, ctx.act, ctx.st
+        b = st.bn
+        dy = to_nhwc_bf16(dy)
+        N, Cc, H, W = h.shape
+        M = N * H * W
+        hm = h.permute(0, 2, 3, 1).reshape(M, Cc)
+        dym = dy.permute(0, 2, 3, 1).reshape(M, Cc)
+        params = [p for p in (bn.weight, bn.bias) if p is not None]
+        direct = all(getattr(p, "_yamb_direct", False) and p.grad is not None for p in params)
+        if direct:
+            dg, db = bn.weight.grad, bn.bias.grad
+        else:
+            if st.gbuf is None:
+                st.gbuf = (torch.zeros_like(bn.weight), torch.zeros_like(bn.bias))
+            st.gbuf[0].zero_()
+            st.gbuf[1].zero_()
+            dg, db = st.gbuf
+        g = nat.BnBwd()
+        g.partials, g.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+        g.gamma = nat.ptr(bn.weight)
+        g.mean, g.invstd = b.mean.data_ptr(), b.invstd.data_ptr()
+        g.dgamma, g.dbeta = dg.data_ptr(), db.data_ptr()
+        g.ca, g.cb, g.cc = b.ca.data_ptr(), b.cb.data_ptr(), b.cc.data_ptr()
+        g.count = M
+        g.use_batch_stats = 1 if b.batch_stats else 0
+        r = nat.BnReduce()
+        r.M, r.C, r.lddy, r.ldh = M, Cc, Cc, Cc
+        r.dy, r.h, r.bn = dym.data_ptr(), hm.data_ptr(), C.pointer(g)
+        r.z_scale, r.z_shift, r.z_act = b.scale.data_ptr(), b.shift.data_ptr(), act
+        launch(lib.yamb_bn_reduce_bwd, r, "bn_reduce", 4 * M * Cc)
+        dh = torch.empty_like(h, memory_format=torch.channels_last)
+        a = nat.BnBwdApply()
+        a.M, a.C, a.lddy, a.ldh, a.lddh = M, Cc, Cc, Cc, Cc
+        a.dy, a.h = dym.data_ptr(), hm.data_ptr()
+        a.z_scale, a.z_shift, a.z_act = b.scale.data_ptr(), b.shift.data_ptr(), act
+        a.ca, a.cb, a.cc = b.ca.data_ptr(), b.cb.data_ptr(), b.cc.data_ptr()
+        a.dh = dh.data_ptr()
+        st.keep += [g, r, a]
+        launch(lib.yamb_bn_bwd_apply_bwd, a, "bn_bwd_apply", 6 * M * Cc)
+        if direct:
+            return dh, None, None, None, None
+        return dh, None, None, dg.clone(), db.clone()
+
+
+def bn_act_apply(bn, active_fn, h):
+    """y = act(BatchNorm(h)) for a raw convolution output on CUDA (training or eval)."""
+    h = to_nhwc_bf16(h)
+    if h.shape[1] % 8:
+        raise nat.NativeError("bn_act: channel count must be a multiple of 8")
+    return _BnActFn.apply(h, bn, act_code_of(active_fn), bn.weight, bn.bias)
+
+
 def block_apply(block, x):
     """Forward of a reference-compatible block module through the sm_100a path."""
     if not x.is_cuda:

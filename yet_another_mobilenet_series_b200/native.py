@@ -102,6 +102,26 @@ class BnReduce(C.Structure):
         ("M", C.c_int64), ("C", C.c_int32), ("lddy", C.c_int32), ("ldh", C.c_int32),
         ("dy", C.c_void_p), ("h", C.c_void_p),
         ("bn", C.POINTER(BnBwd)),
+        ("z_scale", C.c_void_p), ("z_shift", C.c_void_p), ("z_act", C.c_int32),
+    ]
+
+
+class BnStats(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("C", C.c_int32), ("ldh", C.c_int32),
+        ("h", C.c_void_p),
+        ("bn", C.POINTER(BnFwd)),
+    ]
+
+
+class BnBwdApply(C.Structure):
+    _fields_ = [
+        ("M", C.c_int64), ("C", C.c_int32), ("lddy", C.c_int32), ("ldh", C.c_int32),
+        ("lddh", C.c_int32),
+        ("dy", C.c_void_p), ("h", C.c_void_p),
+        ("z_scale", C.c_void_p), ("z_shift", C.c_void_p), ("z_act", C.c_int32),
+        ("ca", C.c_void_p), ("cb", C.c_void_p), ("cc", C.c_void_p),
+        ("dh", C.c_void_p),
     ]
 
 
@@ -149,11 +169,11 @@ class Rmsprop(C.Structure):
 
 
 _STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
-            8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply}
+            8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply, 11: BnStats, 12: BnBwdApply}
 
 # every symbol include/yamb200.h declares
 SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
-           "yamb_bn_reduce_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_rmsprop_step", "yamb_ema_update",
            "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
            "yamb_version"]
 _lib = None
@@ -183,6 +203,8 @@ def lib():
         l.yamb_depthwise_bwd.argtypes = [C.POINTER(DwBwd), C.c_void_p]
         l.yamb_bn_apply_fwd.argtypes = [C.POINTER(BnApply), C.c_void_p]
         l.yamb_bn_reduce_bwd.argtypes = [C.POINTER(BnReduce), C.c_void_p]
+        l.yamb_bn_stats_fwd.argtypes = [C.POINTER(BnStats), C.c_void_p]
+        l.yamb_bn_bwd_apply_bwd.argtypes = [C.POINTER(BnBwdApply), C.c_void_p]
         l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
         l.yamb_se_bwd_reduce_bwd.argtypes = [C.POINTER(SeBwdReduce), C.c_void_p]
         l.yamb_se_bwd_apply_bwd.argtypes = [C.POINTER(SeBwdApply), C.c_void_p]
