@@ -157,6 +157,7 @@ def profile_kernels(ts, n_steps=2):
     import torch
     from yet_another_mobilenet_series_b200 import engine
     ts_graph, ts.graph, ts.use_graph = ts.graph, None, False
+    ts_world, ts.world = ts.world, 1   # rank 0 profiles alone: no collective in these extra steps
     agg = {}
     total_ms = 0.0
     try:
@@ -179,6 +180,7 @@ def profile_kernels(ts, n_steps=2):
     finally:
         engine.PROFILE = None
         ts.graph, ts.use_graph = ts_graph, True
+        ts.world = ts_world
     for r in agg.values():
         for k in ("ms", "bytes", "flops", "launches"):
             r[k] = r[k] / n_steps
