@@ -24,7 +24,7 @@ def tag_of(name, prev_gemm=[0]):
         return "dw_bwd"
     if "gemm_tc_kernel" in name:
         return "pw_gemm"
-    for k in ("bn_apply", "bn_reduce", "se_pool", "se_bwd_reduce", "se_bwd_apply", "rmsprop",
+    for k in ("bn_bwd_apply", "bn_stats", "bn_apply", "bn_reduce", "se_pool", "se_bwd_reduce", "se_bwd_apply", "rmsprop",
               "ema_kernel", "cast_bf16"):
         if k in name:
             return k
