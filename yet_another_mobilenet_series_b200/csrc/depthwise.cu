@@ -18,6 +18,7 @@
 // then consecutive pixels, so global accesses are contiguous runs of CT*2 bytes per pixel and
 // shared accesses are bank-conflict free.  CTAs are persistent over (channel chunk, image tile).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 
 #include "bn_finalize.cuh"
@@ -764,6 +765,17 @@ static cudaError_t launch_bwd(const Dev& p, size_t smem, long long tiles, cudaSt
 }
 #define YAMB_DW_BWD(KK, SS, CC, ...) e = launch_bwd<KK, SS, CC>(__VA_ARGS__)
 
+// Channels per tile: 64, unless 32-channel tiles waste fewer padded channels (C = 96, 144: the
+// widest early layers would run a quarter of their lanes on padding).  YAMB_DW_CT overrides.
+static int pick_ct(int C) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("YAMB_DW_CT"); forced = e ? atoi(e) : 0; }
+  if (forced == 32 || forced == 64) return forced;
+  if (C <= 32) return 32;
+  const int pad64 = (C + 63) / 64 * 64, pad32 = (C + 31) / 32 * 32;
+  return pad32 < pad64 ? 32 : 64;
+}
+
 int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   if (!a) return set_error(YAMB_EINVAL, "null args");
   int rc = check_common(a->N, a->H, a->W, a->C, a->ldc, a->k, a->stride);
@@ -771,7 +783,7 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
   if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
   if (!a->x || !a->y || !a->w) return set_error(YAMB_EINVAL, "depthwise fwd: null pointer");
   const int k = a->k, s = a->stride, pad = (k - 1) / 2;
-  const int ct = a->C > 32 ? 64 : 32;
+  const int ct = pick_ct(a->C);
   DwFwdDev p;
   p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.ldc = a->ldc;
   p.Ho = (a->H + 2 * pad - k) / s + 1;
@@ -818,7 +830,7 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   if (!a->ca || !a->cb || !a->cc || !a->dz || !a->h || !a->x || !a->dx || !a->dw || !a->w)
     return set_error(YAMB_EINVAL, "depthwise bwd: null pointer");
   const int k = a->k, s = a->stride, pad = (k - 1) / 2;
-  const int ct = a->C > 32 ? 64 : 32;
+  const int ct = pick_ct(a->C);
   DwBwdDev p;
   p.N = a->N; p.H = a->H; p.W = a->W; p.C = a->C; p.ldc = a->ldc;
   p.Ho = (a->H + 2 * pad - k) / s + 1;
