@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from yet_another_mobilenet_series_b200 import native as nat  # noqa: E402
 
 
-def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10):
+def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10, dgrad=False):
     lib = nat.lib()
     dev = "cuda"
     bf = torch.bfloat16
@@ -31,6 +31,32 @@ def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10):
         keep += [sc, sh]
         g.a_xform, g.a_act = 1, 1
         g.a_scale, g.a_shift = sc.data_ptr(), sh.data_ptr()
+    if dgrad:
+        # project-dgrad shape: A = ca*dy + cb*h3 + cc (two sources, K channels), B = W3 MN-major,
+        # epilogue dz = acc * act'(s*h2+t) + BatchNorm-backward statistics
+        nct = lib.yamb_max_ctas()
+        A2 = torch.randn(M, K, device=dev).to(bf)
+        co = [torch.ones(K, device=dev), torch.zeros(K, device=dev), torch.ones(K, device=dev) * 0.1]
+        g.a_xform = 2
+        g.a_scale, g.a_shift, g.a_scale2 = co[0].data_ptr(), co[1].data_ptr(), co[2].data_ptr()
+        g.A2, g.lda2 = A2.data_ptr(), K
+        H = torch.randn(M, N, device=dev).to(bf)
+        hs, ht = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+        mean, invstd, gamma = torch.zeros(N, device=dev), torch.ones(N, device=dev), torch.ones(N, device=dev)
+        bw = nat.BnBwd()
+        parts, cnt = torch.zeros(nct * 2 * N, device=dev), torch.zeros(1, device=dev, dtype=torch.int32)
+        dg, db = torch.zeros(N, device=dev), torch.zeros(N, device=dev)
+        cs = [torch.zeros(N, device=dev) for _ in range(3)]
+        bw.partials, bw.counter = parts.data_ptr(), cnt.data_ptr()
+        bw.gamma, bw.mean, bw.invstd = gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr()
+        bw.dgamma, bw.dbeta = dg.data_ptr(), db.data_ptr()
+        bw.ca, bw.cb, bw.cc = [o.data_ptr() for o in cs]
+        bw.count, bw.use_batch_stats = M, 1
+        g.epi = 1
+        g.H, g.ldh = H.data_ptr(), N
+        g.h_scale, g.h_shift, g.h_act = hs.data_ptr(), ht.data_ptr(), 2
+        g.bn_bwd = C.pointer(bw)
+        keep += [A2, H, hs, ht, mean, invstd, gamma, bw, parts, cnt, dg, db] + co + cs
     if stats:
         nct = lib.yamb_max_ctas()
         f = nat.BnFwd()
@@ -54,6 +80,8 @@ def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     nbytes = 2 * (M * K + N * K) + (4 if epi == 2 else 2) * M * N * (0 if epi == 2 else 1)
+    if dgrad:
+        nbytes += 2 * M * K + 2 * M * N
     print("%-34s M=%7d N=%4d K=%4d  %.3f ms  %7.1f GB/s" % (tag, M, N, K, ms, nbytes / ms / 1e6))
     sys.stdout.flush()
 

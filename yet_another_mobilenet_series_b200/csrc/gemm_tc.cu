@@ -1,7 +1,8 @@
-// Pointwise-convolution GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+// Pointwise-convolution GEMM for sm_100a: operand loaders -> shared memory -> tcgen05.mma -> TMEM ->
+// epilogue.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer (one elected lane)
+// One persistent CTA (512 threads) per SM, warp-specialised:
+//   warp 0      TMA producer for WIDE TRANSFORMED operands only (128-byte box rows)
 //   warp 1      MMA issuer   (one elected lane, tcgen05.mma.cta_group::1.kind::f16, M=128)
 //   warp 2      TMEM allocator / deallocator
 //   warp 3      idle
@@ -10,8 +11,12 @@
 //               tcgen05.ld (its 32 TMEM lanes) -> registers -> fused math -> warp-private swizzled
 //               smem -> its own TMA store (box 64 x 32) -> per-column BatchNorm statistics read back
 //               from the staged tile.  No CTA-wide barrier in the steady state.
-//   warps 12-15 operand transform (BN-apply + activation, or BN-backward affine) applied in place
-//               on the TMA-landed tile before the MMA reads it (only launched when needed)
+//   warps 12-15 (and 8-11 when the epilogue is light) operand loaders: one warp per pipeline stage;
+//               plain operands by cp.async into the swizzled layout, narrow transformed operands
+//               through registers, wide transformed operands rewritten in place after the TMA
+//               landed them (BN-apply + activation, or the two-source BN-backward affine)
+// (TMA tile loads cost 7-16 cycles per box row whatever its width: with the 32-96-byte rows of the
+// narrow operands the TMA unit bounded every GEMM — measured with the YAMB_GEMM_DEBUG=512 timers.)
 //
 // Replaces, behind yamb_pointwise_gemm (include/yamb200.h), the nn.Conv2d(kernel_size=1) forward /
 // dgrad / wgrad library calls of the reference block (models/mobilenet_base.py:391-395, :413,
@@ -68,7 +73,6 @@ struct GemmDev {
   // operand tensors in global memory ([pixels|rows][channels], bf16) for the cp.async loaders
   const __nv_bfloat16 *gA, *gA2, *gB, *gB2;
   long long lda, lda2, ldb, ldb2;
-  int lookahead;              // (unused)
   int a_tma, b_tma;           // wide transformed operand: TMA load + in-place smem transform
   int lgroup;                 // loader warps that share one stage (1, 2 or 4)
   yamb_bn_fwd bnf;
@@ -116,110 +120,6 @@ __device__ __forceinline__ float4 lds128f(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z),
                "r"(v.w) : "memory");
-}
-
-template <int ACT>
-__device__ __forceinline__ float act_c(float z) {
-  if (ACT == ACT_RELU) return fmaxf(z, 0.f);
-  if (ACT == ACT_RELU6) return fminf(fmaxf(z, 0.f), 6.f);
-  if (ACT == ACT_SWISH) return z / (1.f + __expf(-z));
-  if (ACT == ACT_HSWISH) return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
-  return z;
-}
-
-// One 16-byte chunk (8 channels) of one row of a panel: loads first, math later.
-struct XChunk {
-  uint4 v, v2;
-  float4 sa, sb, ba, bb, ta, tb;  // ta/tb: second-source scale (mode 2) or the SE gate (mode 1)
-  uint32_t addr;
-  bool ok;
-};
-template <int MODE>
-__device__ __forceinline__ void xchunk_load(XChunk& k, uint32_t rbase, uint32_t rbase2, int row,
-                                            int lc, uint32_t tab_s, uint32_t tab_b,
-                                            uint32_t tab_s2, int cbase, int C,
-                                            const float* gate_row, bool valid) {
-  const int c0 = cbase + lc * 8;
-  k.ok = valid && c0 < C;
-  const uint32_t off = (uint32_t)((lc ^ (row & 7)) << 4);
-  k.addr = rbase + off;
-  if (k.ok) {
-    k.v = lds128(rbase + off);
-    if (MODE == 2) k.v2 = lds128(rbase2 + off);
-    k.sa = lds128f(tab_s + c0 * 4);
-    k.sb = lds128f(tab_s + c0 * 4 + 16);
-    k.ba = lds128f(tab_b + c0 * 4);
-    k.bb = lds128f(tab_b + c0 * 4 + 16);
-    if (MODE == 2) {
-      k.ta = lds128f(tab_s2 + c0 * 4);
-      k.tb = lds128f(tab_s2 + c0 * 4 + 16);
-    } else if (gate_row != nullptr) {
-      k.ta = __ldg(reinterpret_cast<const float4*>(gate_row + c0));
-      k.tb = __ldg(reinterpret_cast<const float4*>(gate_row + c0 + 4));
-    }
-  }
-}
-template <int MODE>
-__device__ __forceinline__ void xchunk_apply(const XChunk& k, const ActParam& ap, bool gated) {
-  if (!k.ok) return;
-  float x[8] = {bf16lo(k.v.x), bf16hi(k.v.x), bf16lo(k.v.y), bf16hi(k.v.y),
-                bf16lo(k.v.z), bf16hi(k.v.z), bf16lo(k.v.w), bf16hi(k.v.w)};
-  const float sc[8] = {k.sa.x, k.sa.y, k.sa.z, k.sa.w, k.sb.x, k.sb.y, k.sb.z, k.sb.w};
-  const float sh[8] = {k.ba.x, k.ba.y, k.ba.z, k.ba.w, k.bb.x, k.bb.y, k.bb.z, k.bb.w};
-  const float t2[8] = {k.ta.x, k.ta.y, k.ta.z, k.ta.w, k.tb.x, k.tb.y, k.tb.z, k.tb.w};
-  if (MODE == 1) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = fmaf(sc[e], x[e], sh[e]);
-    act_vec<8>(x, ap);
-    if (gated) {  // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = round_bf16(x[e]) * t2[e];
-    }
-  } else {
-    const float y[8] = {bf16lo(k.v2.x), bf16hi(k.v2.x), bf16lo(k.v2.y), bf16hi(k.v2.y),
-                        bf16lo(k.v2.z), bf16hi(k.v2.z), bf16lo(k.v2.w), bf16hi(k.v2.w)};
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = fmaf(sc[e], x[e], fmaf(t2[e], y[e], sh[e]));
-  }
-  sts128(k.addr, make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                            pack_bf16(x[6], x[7])));
-}
-
-// In-place transform of one panel (R = 64 or 128 rows x 128 B, SWIZZLE_128B) by `nt` threads.
-//   mode 1: v = act(s[c]*v + b[c])        mode 2: v = s[c]*v + s2[c]*v2 + b[c]
-// `t` in [0,nt).  Chunk i = row*8 + lc; channel of (chunk lc, element e) = cbase + lc*8 + e.
-// All addresses are 32-bit shared-window addresses; tab_* point at fp32 tables indexed by channel.
-// ONE copy of this code exists in the kernel (single call site, runtime R / mode): two chunks'
-// loads are in flight before the first use.
-__device__ __forceinline__ void xform_panel(uint32_t panel, uint32_t panel2, int R, int t, int nt,
-                                            int mode, const ActParam& ap, uint32_t tab_s,
-                                            uint32_t tab_b, uint32_t tab_s2, int cbase, int C,
-                                            int row_limit, const float* gate, unsigned pixbase,
-                                            unsigned rps) {
-  const int total = min(R, row_limit) * 8;
-#pragma unroll 1
-  for (int i = t; i < total; i += 2 * nt) {
-    XChunk a, b;
-    const int ra = i >> 3, la = i & 7;
-    const int ib = i + nt;
-    const int rb = ib >> 3, lb = ib & 7;
-    const bool vb = ib < total;
-    const uint32_t pa = panel + ra * 128, pa2 = panel2 + ra * 128;
-    const uint32_t pb = panel + rb * 128, pb2 = panel2 + rb * 128;
-    if (mode == 2) {
-      xchunk_load<2>(a, pa, pa2, ra, la, tab_s, tab_b, tab_s2, cbase, C, nullptr, true);
-      xchunk_load<2>(b, pb, pb2, rb, lb, tab_s, tab_b, tab_s2, cbase, C, nullptr, vb);
-      xchunk_apply<2>(a, ap, false);
-      xchunk_apply<2>(b, ap, false);
-    } else {
-      const float* ga = gate ? gate + (size_t)((pixbase + ra) / rps) * C : nullptr;
-      const float* gb = gate ? gate + (size_t)((pixbase + rb) / rps) * C : nullptr;
-      xchunk_load<1>(a, pa, pa2, ra, la, tab_s, tab_b, tab_s2, cbase, C, ga, true);
-      xchunk_load<1>(b, pb, pb2, rb, lb, tab_s, tab_b, tab_s2, cbase, C, gb, vb);
-      xchunk_apply<1>(a, ap, gate != nullptr);
-      xchunk_apply<1>(b, ap, gate != nullptr);
-    }
-  }
 }
 
 // Register-staged load + transform of one operand panel by ONE warp: every lane owns the same
@@ -559,6 +459,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0;
     long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
     const long long dbg_start = clock64();
+    // Side operand (residual / H) rows come straight from global memory (each thread owns one row:
+    // 8 x 16 B per 64-column sub-tile).  They are requested ONE SUB-TILE AHEAD, into the registers
+    // the previous sub-tile has just finished with: issued at the top of a sub-tile their ~2 us
+    // latency was fully exposed (the "convert" phase of the dgrad epilogue was 4000 cycles).
+    uint4 sv[8];
+    auto load_side = [&](int w2, int sub2) {
+      const int mn2 = w2 / p.ksplit;
+      const int m2 = mn2 / p.n_blocks, n2 = mn2 % p.n_blocks;
+      const int grow2 = m2 * kBlockM + row;
+      const int col2 = n2 * p.block_n + sub2 * 64;
+      const __nv_bfloat16* srow = p.side + (size_t)grow2 * p.lds + col2;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        sv[ch] = make_uint4(0u, 0u, 0u, 0u);
+        if (grow2 < p.M && col2 + ch * 8 < p.N)
+          sv[ch] = __ldg(reinterpret_cast<const uint4*>(srow + ch * 8));
+      }
+    };
+    const int w_step = (n_epi_wg == 2 ? 2 : 1) * (int)gridDim.x;
+    if (side_in) {
+      const int w0 = blockIdx.x + ((n_epi_wg == 2 && wg == 1) ? (int)gridDim.x : 0);
+      if (w0 < p.num_work) load_side(w0, 0);
+    }
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++it) {
       if (n_epi_wg == 2 && (it & 1) != wg) continue;  // the other warpgroup owns this tile
       const int mn = w / p.ksplit;
@@ -579,17 +502,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int sub = 0; sub < n_sub; ++sub) {
         const int col0 = n_blk * p.block_n + sub * 64;  // global column of this sub-tile
-        // side operand rows straight from global (each thread owns one row: 8 x 16 B)
-        uint4 sv[8];
-        if (side_in) {
-          const __nv_bfloat16* srow = p.side + (size_t)grow * p.lds + col0;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            sv[ch] = make_uint4(0u, 0u, 0u, 0u);
-            if (row_ok && col0 + ch * 8 < p.N)
-              sv[ch] = __ldg(reinterpret_cast<const uint4*>(srow + ch * 8));
-          }
-        }
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + sub * 64);
         uint32_t acc[2][32];
@@ -630,46 +542,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         dbg_t[2] += clock64() - tq1;
         tq1 = clock64();
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {  // 8 chunks of 8 columns
+        // Straight-line conversion of the 8 chunks (8 columns each): the mode decisions are taken
+        // ONCE per sub-tile, outside the unrolled chunk loop, so the chunk bodies interleave
+        // (with a branch per chunk this phase took ~4700 cycles per sub-tile in the dgrad epilogue).
+        auto stage_chunk = [&](int ch, const float (&v)[8]) {
           const int pc = ch ^ (lane & 7);
-          float v[8];
+          *reinterpret_cast<uint4*>(sO + lane * 128 + (pc << 4)) =
+              make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                         pack_bf16(v[6], v[7]));
+        };
+        if (kEpi == 1) {
+          auto dz_chunks = [&](const bool clampk) {   // inlined twice, `clampk` a constant in each
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
-          if (side_in) {
-            const uint32_t sw[4] = {sv[ch].x, sv[ch].y, sv[ch].z, sv[ch].w};
-            if (kEpi == 0) {
+            for (int ch = 0; ch < 8; ++ch) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
+              const uint32_t sw[4] = {sv[ch].x, sv[ch].y, sv[ch].z, sv[ch].w};
+              // columns past N: read the last valid coefficients (the values are never stored)
+              const int cb = min(col0 + ch * 8, p.N - 8);
+              const float4 s0 = *reinterpret_cast<const float4*>(cz_s + cb);
+              const float4 s1 = *reinterpret_cast<const float4*>(cz_s + cb + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(cz_t + cb);
+              const float4 t1 = *reinterpret_cast<const float4*>(cz_t + cb + 4);
+              const float zs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float zt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+              float zz[8];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                v[2 * e] += bf16lo(sw[e]);
-                v[2 * e + 1] += bf16hi(sw[e]);
+                zz[2 * e] = fmaf(zs[2 * e], bf16lo(sw[e]), zt[2 * e]);
+                zz[2 * e + 1] = fmaf(zs[2 * e + 1], bf16hi(sw[e]), zt[2 * e + 1]);
               }
-            } else {
-              const int cb = col0 + ch * 8;
-              if (cb < p.N) {
-                const float4 s0 = *reinterpret_cast<const float4*>(cz_s + cb);
-                const float4 s1 = *reinterpret_cast<const float4*>(cz_s + cb + 4);
-                const float4 t0 = *reinterpret_cast<const float4*>(cz_t + cb);
-                const float4 t1 = *reinterpret_cast<const float4*>(cz_t + cb + 4);
-                const float zs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float zt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                float zz[8];
+              if (clampk) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  zz[2 * e] = fmaf(zs[2 * e], bf16lo(sw[e]), zt[2 * e]);
-                  zz[2 * e + 1] = fmaf(zs[2 * e + 1], bf16hi(sw[e]), zt[2 * e + 1]);
-                }
-                act_bwd_vec<8>(v, zz, hap, p.h_act);
+                for (int e = 0; e < 8; ++e) v[e] = (zz[e] > hap.lo && zz[e] < hap.hi) ? v[e] : 0.f;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] *= act_bwd(zz[e], p.h_act);
               }
-              *reinterpret_cast<uint4*>(s_h + lane * 128 + (pc << 4)) = sv[ch];
+              *reinterpret_cast<uint4*>(s_h + lane * 128 + ((ch ^ (lane & 7)) << 4)) = sv[ch];
+              stage_chunk(ch, v);
             }
+          };
+          if (hap.kind == 0) dz_chunks(true);
+          else dz_chunks(false);
+        } else if (side_in) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
+            const uint32_t sw[4] = {sv[ch].x, sv[ch].y, sv[ch].z, sv[ch].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] += bf16lo(sw[e]);
+              v[2 * e + 1] += bf16hi(sw[e]);
+            }
+            stage_chunk(ch, v);
           }
-          uint4 o;
-          o.x = pack_bf16(v[0], v[1]);
-          o.y = pack_bf16(v[2], v[3]);
-          o.z = pack_bf16(v[4], v[5]);
-          o.w = pack_bf16(v[6], v[7]);
-          *reinterpret_cast<uint4*>(sO + lane * 128 + (pc << 4)) = o;
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(acc[ch >> 2][(ch & 3) * 8 + e]);
+            stage_chunk(ch, v);
+          }
         }
         dbg_t[3] += clock64() - tq1;
         tq1 = clock64();
@@ -693,6 +631,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmD, sO, col0, m_blk * kBlockM + q * 32);
             tma_store_commit();
           }
+        }
+        if (side_in) {
+          // sv is dead and the store's proxy fence (a MEMBAR that would wait for these loads) is
+          // behind us: request the next sub-tile's side rows now; they land during the
+          // statistics pass and the next accumulator load
+          if (sub + 1 < n_sub) load_side(w, sub + 1);
+          else if (w + w_step < p.num_work) load_side(w + w_step, 0);
         }
         dbg_t[4] += clock64() - tq1;
         tq1 = clock64();
@@ -735,7 +680,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             } else {
               const float m0 = cz_m[c], m1 = cz_m[c + 1], r0 = cz_r[c], r1 = cz_r[c + 1];
-              float sa = 0.f, sb = 0.f, ta = 0.f, tb = 0.f, qa = 0.f, qb = 0.f, ra = 0.f, rb2 = 0.f;
+              float sa = 0.f, sb = 0.f, sc2 = 0.f, sd = 0.f, ta = 0.f, tb = 0.f, tc = 0.f, td = 0.f;
+              float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f, ra = 0.f, rb2 = 0.f, rc = 0.f, rd = 0.f;
               auto rowacc = [&](int r, float& S0, float& S1, float& Q0, float& Q1) {
                 const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
                 const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + off);
@@ -746,13 +692,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 Q1 = fmaf(b, (bf16hi(hh) - m1) * r1, Q1);
               };
               int r = 0;
-#pragma unroll 4
-              for (; r + 1 < rmax; r += 2) {   // two independent accumulator sets
+#pragma unroll 2
+              for (; r + 3 < rmax; r += 4) {   // four independent accumulator sets
                 rowacc(r, sa, ta, qa, ra);
                 rowacc(r + 1, sb, tb, qb, rb2);
+                rowacc(r + 2, sc2, tc, qc, rc);
+                rowacc(r + 3, sd, td, qd, rd);
               }
-              if (r < rmax) rowacc(r, sa, ta, qa, ra);
-              s0 = sa + sb; s1 = ta + tb; q0 = qa + qb; q1 = ra + rb2;
+              for (; r < rmax; ++r) rowacc(r, sa, ta, qa, ra);
+              s0 = (sa + sb) + (sc2 + sd); s1 = (ta + tb) + (tc + td);
+              q0 = (qa + qb) + (qc + qd); q1 = (ra + rb2) + (rc + rd);
             }
             if (reg_stats) {
               switch (sub) {  // constant register indices in every case
@@ -795,11 +744,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && kEpi != 2) tma_store_wait_all<0>();
   } else {
     // ============================ operand loaders (+ transform) ============================
-    // Warps 12-15 (t 0..127) plus, when wg2x, warps 8-11 (t 128..255) stream the operand tiles
-    // of `lookahead` k-blocks ahead into shared memory with cp.async (16-byte chunks written
-    // straight into the SWIZZLE_128B layout the UMMA descriptors expect, zero-filled outside the
-    // tensors), then — for transformed operands — rewrite their tile in place, and publish the
-    // stage to the MMA warp.  (TMA tile loads cost ~7-16 cycles per box ROW whatever its width:
+    // Warps 12-15 (t 0..127) plus, when wg2x, warps 8-11 (t 128..255) bring the operand tiles into
+    // shared memory: plain operands with cp.async (16-byte chunks written straight into the
+    // SWIZZLE_128B layout the UMMA descriptors expect, zero-filled outside the tensors), narrow
+    // transformed operands through registers, wide transformed operands by rewriting the tile the
+    // TMA producer (warp 0) landed; then they publish the stage to the MMA warp.  (TMA tile loads cost ~7-16 cycles per box ROW whatever its width:
     // with 32-96-byte rows of the narrow operands the TMA unit, not HBM, bounded every GEMM.)
     // registers: 4 control warps x 56 + (epilogue + loader) warps x 152 = 64 Ki / 32
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
@@ -1234,7 +1183,6 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   p.gB = (const __nv_bfloat16*)a->B; p.ldb = a->ldb;
   p.gA2 = (const __nv_bfloat16*)(p.a_xform == 2 ? a->A2 : nullptr); p.lda2 = a->lda2;
   p.gB2 = (const __nv_bfloat16*)(p.b_xform == 2 ? a->B2 : nullptr); p.ldb2 = a->ldb2;
-  p.lookahead = stages - 1 < 3 ? stages - 1 : 3;
   if (a->epi != 2) {
     rc = make_map_2d(&tmD, a->D, a->N, a->M, a->ldd, 64, 32);  // one epilogue warp's rows
     if (rc) return rc;
