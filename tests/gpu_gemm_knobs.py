@@ -5,7 +5,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge  # noqa: E402,F401
-ge.build()
+os.environ.setdefault("YAMB_GEMM_TIMERS", "1")
+ge.build(force=True)   # phase timers are a compile-time option
 from gpu_microbench_gemm import run  # noqa: E402
 
 for dbg in [int(a) for a in sys.argv[1:]] or [512]:

@@ -33,6 +33,14 @@
 #include "prims.cuh"
 
 namespace yamb {
+// phase timers of the roles (YAMB_GEMM_DEBUG=512) are compiled in only with -DYAMB_GEMM_TIMERS
+// (YAMB_GEMM_TIMERS=1 python -c 'import __graft_entry__ as g; g.build(force=True)'): the clock
+// reads are scheduling barriers in the hot loops
+#ifdef YAMB_GEMM_TIMERS
+#define YCLK() clock64()
+#else
+#define YCLK() 0LL
+#endif
 #define MBAR_WAIT(bar, par) do { if (p.dbg & 256) mbar_wait_spin(bar, par); else mbar_wait(bar, par); } while (0)
 
 
@@ -384,15 +392,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb0 = slab * p.kb_per_split;
       const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
       const int as = it & 1;
-      const long long te0 = clock64();
+      const long long te0 = YCLK();
       MBAR_WAIT(&bars->tmem_empty[as], ((it >> 1) & 1) ^ 1);
-      dbg_mma_empty += clock64() - te0;
+      dbg_mma_empty += YCLK() - te0;
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccStride);
       for (int kb = kb0; kb < kb1; ++kb) {
-        const long long tm0 = clock64();
+        const long long tm0 = YCLK();
         MBAR_WAIT(&bars->full[stage], phase);
-        dbg_mma_full += clock64() - tm0;
+        dbg_mma_full += YCLK() - tm0;
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -458,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int e = 0; e < 4; ++e) racc[j][e] = 0.f;
     int it = 0;
     long long dbg_t[6] = {0, 0, 0, 0, 0, 0};
-    const long long dbg_start = clock64();
+    const long long dbg_start = YCLK();
     // Side operand (residual / H) rows come straight from global memory (each thread owns one row:
     // 8 x 16 B per 64-column sub-tile).  They are requested ONE SUB-TILE AHEAD, into the registers
     // the previous sub-tile has just finished with: issued at the top of a sub-tile their ~2 us
@@ -491,11 +499,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = grow < p.M;
       // sub-tiles of 64 columns; skip the ones that lie entirely beyond N (last n-block)
       const int n_sub = min((p.block_n + 63) / 64, (p.N - n_blk * p.block_n + 63) / 64);
-      long long tq0 = clock64();
+      long long tq0 = YCLK();
       if (p.dbg & 256) mbar_wait_spin(&bars->tmem_full[as], (it >> 1) & 1);
       else mbar_wait_relaxed(&bars->tmem_full[as], (it >> 1) & 1);
       tc_fence_after();
-      dbg_t[0] += clock64() - tq0;
+      dbg_t[0] += YCLK() - tq0;
       // NOT unrolled: one copy of the sub-tile body keeps the epilogue inside the instruction
       // cache (4 unrolled copies x 3 epilogue kinds were ~20k instructions; "no instruction" was
       // the top stall reason and a sub-tile took ~4000 cycles)
@@ -505,12 +513,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr =
             tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + sub * 64);
         uint32_t acc[2][32];
-        long long tq1 = clock64();
+        long long tq1 = YCLK();
         tmem_ld_32x32(taddr, acc[0]);
         tmem_ld_32x32(taddr + 32, acc[1]);
         tmem_ld_wait();
-        dbg_t[1] += clock64() - tq1;
-        tq1 = clock64();
+        dbg_t[1] += YCLK() - tq1;
+        tq1 = YCLK();
         if (sub == n_sub - 1) {
           // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
@@ -540,8 +548,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else tma_store_wait_read<0>();
         }
         __syncwarp();
-        dbg_t[2] += clock64() - tq1;
-        tq1 = clock64();
+        dbg_t[2] += YCLK() - tq1;
+        tq1 = YCLK();
         // Straight-line conversion of the 8 chunks (8 columns each): the mode decisions are taken
         // ONCE per sub-tile, outside the unrolled chunk loop, so the chunk bodies interleave
         // (with a branch per chunk this phase took ~4700 cycles per sub-tile in the dgrad epilogue).
@@ -609,8 +617,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             stage_chunk(ch, v);
           }
         }
-        dbg_t[3] += clock64() - tq1;
-        tq1 = clock64();
+        dbg_t[3] += YCLK() - tq1;
+        tq1 = YCLK();
         if (p.dbg & 128) {
           // experiment: coalesced st.global from the staged tile instead of a TMA store
           __syncwarp();
@@ -639,8 +647,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (sub + 1 < n_sub) load_side(w, sub + 1);
           else if (w + w_step < p.num_work) load_side(w + w_step, 0);
         }
-        dbg_t[4] += clock64() - tq1;
-        tq1 = clock64();
+        dbg_t[4] += YCLK() - tq1;
+        tq1 = YCLK();
         // ---- per-column statistics of this warp's 32 rows of the bf16-rounded output ----
         if (p.has_bnf || p.has_bnb) {
           const int c = col0 + 2 * lane;  // column pair owned by this lane
@@ -719,14 +727,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();  // s_h / sO reads done before the next sub-tile overwrites them
         }
-        dbg_t[5] += clock64() - tq1;
+        dbg_t[5] += YCLK() - tq1;
         ++sub_count;
       }
     }
     if ((p.dbg & 512) && lane == 0) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) atomicAdd(p.dbg_buf + i, (unsigned long long)dbg_t[i]);
-      atomicAdd(p.dbg_buf + 6, (unsigned long long)(clock64() - dbg_start));
+      atomicAdd(p.dbg_buf + 6, (unsigned long long)(YCLK() - dbg_start));
       atomicAdd(p.dbg_buf + 7, 1ull);
     }
     if (reg_stats) {
@@ -847,9 +855,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     auto issue = [&](const Cur& c, int stage, int rnd) {
-      const long long tl0 = clock64();
+      const long long tl0 = YCLK();
       MBAR_WAIT(&bars->empty[stage], (rnd & 1) ^ 1);
-      dbg_l[0] += clock64() - tl0;
+      dbg_l[0] += YCLK() - tl0;
       const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
       for (int pi = 0; pi < na + nb; ++pi) {
         const Pan g = panel_of(c, pi);
@@ -858,7 +866,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     auto consume = [&](const Cur& c, int stage, int rnd) {
-      const long long tl3 = clock64();
+      const long long tl3 = YCLK();
       if (kXform && use_x) {
         const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
         // narrow transformed operands: registers (few bytes per row, latency hidden by the batch)
@@ -886,9 +894,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // wide transformed operands: the TMA producer loaded them; rewrite the tile in place
         if (p.a_tma || p.b_tma) {
-          const long long tl1 = clock64();
+          const long long tl1 = YCLK();
           MBAR_WAIT(&bars->xdone[stage], rnd & 1);
-          dbg_l[1] += clock64() - tl1;
+          dbg_l[1] += YCLK() - tl1;
           if (!(p.dbg & 1)) {
 #pragma unroll 1
             for (int pi = 0; pi < na + nb; ++pi) {
@@ -917,13 +925,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      const long long tl2 = clock64();
+      const long long tl2 = YCLK();
       dbg_l[2] += tl2 - tl3;
       cp_async_wait_n<0>();
       fence_proxy_async_smem();
       __syncwarp();
       if (ln == 0) mbar_arrive(&bars->full[stage]);
-      dbg_l[3] += clock64() - tl2;
+      dbg_l[3] += YCLK() - tl2;
     };
 
     // One loader WARP fills a whole stage, and every stage has ONE owner warp (stage s belongs to
@@ -934,7 +942,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     Cur c;
     c.w = blockIdx.x;
     cur_set(c);
-    const long long dbg_l0 = clock64();
+    const long long dbg_l0 = YCLK();
     // n = running k-block index, st = n % S, rnd = n / S (no divisions in the loop)
     int st = 0, rnd = 0;
     for (; c.w < p.num_work; cur_next(c)) {
@@ -950,7 +958,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       atomicAdd(p.dbg_buf + 13, (unsigned long long)dbg_l[1]);
       atomicAdd(p.dbg_buf + 14, (unsigned long long)dbg_l[2]);
       atomicAdd(p.dbg_buf + 15, (unsigned long long)dbg_l[3]);
-      atomicAdd(p.dbg_buf + 8, (unsigned long long)(clock64() - dbg_l0));
+      atomicAdd(p.dbg_buf + 8, (unsigned long long)(YCLK() - dbg_l0));
       atomicAdd(p.dbg_buf + 9, 1ull);
     }
   }
