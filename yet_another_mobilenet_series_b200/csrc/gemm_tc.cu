@@ -144,7 +144,9 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
                                              uint32_t tab_s, uint32_t tab_b, uint32_t tab_s2,
                                              int col0, int C, const float* gate, unsigned pixbase,
                                              unsigned rps) {
-  constexpr int NB = MODE == 2 ? 4 : 8;   // rows in flight per lane (16 B each, x2 sources in mode 2)
+  // rows in flight per lane (16 B each, x2 sources in mode 2).  From global memory every batch
+  // exposes one DRAM latency to this warp: keep the batch as large as the registers allow.
+  constexpr int NB = (MODE == 2 && SMEM) ? 4 : 8;
   // 2^cs lanes per row (8 for 64-channel panels; 4 / 2 for narrow operands so that no lane idles)
   const int lc = ln & ((1 << cs) - 1);
   const int RS = 32 >> cs;                // rows covered by one warp-wide access
@@ -826,7 +828,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         g.col0 = (g.isA ? c.m_blk * kBlockM : c.n_blk * p.block_n) + q * 64;
         g.climit = g.isA ? p.M : p.N;
         g.rlimit = g.col0 < g.climit ? min(64, p.K - g.row0) : 0;
-        g.rows = 64;           // rows past K must read as zero: they are accumulated
+        // rows past K must read as zero (they are accumulated); a panel wholly past M / N only
+        // feeds outputs that are never stored: leave it alone
+        g.rows = g.col0 < g.climit ? 64 : 0;
       }
       if (g.rlimit < 0) g.rlimit = 0;
       if (g.rows < 0) g.rows = 0;
