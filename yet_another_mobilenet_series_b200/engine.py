@@ -378,7 +378,8 @@ class BlockPlan:
             sp.pooled = self.pooled.data_ptr()
             self._call(lib.yamb_se_pool_fwd, sp, "se_pool", 2 * self.M_out * self.Chid)
             se = self.se
-            with torch.no_grad():
+            # the two [N, C] fully connected layers stay fp32 even under the caller's autocast
+            with torch.no_grad(), torch.autocast("cuda", enabled=False):
                 self.se_u = torch.addmm(se.se_reduce.bias, self.pooled,
                                         se.se_reduce.weight.flatten(1).t())
                 self.se_v = _torch_act(self.se_u, self.se_act)
@@ -440,7 +441,7 @@ class BlockPlan:
         r.scale, r.shift, r.act = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr(), self.act
         r.dgate = self.dgate.data_ptr()
         self._call(lib.yamb_se_bwd_reduce_bwd, r, "se_bwd_reduce", 4 * self.M_out * self.Chid)
-        with torch.no_grad():
+        with torch.no_grad(), torch.autocast("cuda", enabled=False):
             gate = self.gate
             dt = self.dgate * gate * (1 - gate)
             we = se.se_expand.weight.flatten(1)          # [C, r]
