@@ -16,6 +16,10 @@ ROWS = [[16, 1, 1, [3], [32], False],
 KW = dict(inverted_residual_setting=ROWS, block="InvertedResidualChannelsFused", se_ratio=0.5,
           active_fn="nn.Swish", batch_norm_momentum=0.01, batch_norm_epsilon=1e-3, num_classes=50,
           dropout_ratio=0.0, last_channel=320)
+# the unfused packing (one expand/depthwise/project branch per kernel size, AtomNAS supernet)
+KW_UNFUSED = dict(inverted_residual_setting=ROWS, block="InvertedResidualChannels",
+                  active_fn="nn.ReLU6", batch_norm_momentum=0.01, batch_norm_epsilon=1e-3,
+                  num_classes=50, dropout_ratio=0.0, last_channel=320)
 
 
 def _rel(a, b):
@@ -23,17 +27,18 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-20))
 
 
-def _model(size):
+def _model(size, kw=None):
     from yet_another_mobilenet_series_b200 import mobilenet_base as mb, searched_network as sn
     torch.manual_seed(7)
-    m = sn.Model(**KW, input_size=size)
+    m = sn.Model(**(kw or KW), input_size=size)
     m.apply(mb.init_weights_mnas)
     return m
 
 
-def test_searched_eval_logits(built_lib):
+@pytest.mark.parametrize("kw", [KW, KW_UNFUSED], ids=["fused_se_swish", "unfused_relu6"])
+def test_searched_eval_logits(built_lib, kw):
     from oracle import torch_model as tm
-    m = _model(64)
+    m = _model(64, kw)
     g = torch.Generator().manual_seed(3)
     for mod in m.modules():
         if isinstance(mod, torch.nn.BatchNorm2d):
@@ -47,11 +52,12 @@ def test_searched_eval_logits(built_lib):
     assert _rel(got, want) < 3e-2      # bf16 activations through 6 blocks + SE gates
 
 
-def test_searched_trains(built_lib):
+@pytest.mark.parametrize("kw", [KW, KW_UNFUSED], ids=["fused_se_swish", "unfused_relu6"])
+def test_searched_trains(built_lib, kw):
     from oracle import torch_model as tm
     from yet_another_mobilenet_series_b200.trainer import TrainStep
     B = 16
-    m = _model(64)
+    m = _model(64, kw)
     ref = tm.as_reference(m).train()
     trainer = tm.RefTrainer(ref, B)
     g = torch.Generator().manual_seed(0)
