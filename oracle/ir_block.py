@@ -222,11 +222,13 @@ def forward(x, cfg, P, training=True, quant=False):
     return y, S
 
 
-def _bn_bwd(dz, h, mean, invstd, g, training):
-    """dgamma, dbeta, dh for z = g*xhat + b, xhat = (h-mean)*invstd."""
+def _bn_bwd(dz, h, mean, invstd, g, training, dz_stats=None):
+    """dgamma, dbeta, dh for z = g*xhat + b, xhat = (h-mean)*invstd.  `dz_stats`: the values the
+    sums are taken from when they differ from the (bf16-rounded) dz that is propagated."""
     xhat = (h - mean[None, :, None, None]) * invstd[None, :, None, None]
-    dg = (dz * xhat).sum((0, 2, 3))
-    db = dz.sum((0, 2, 3))
+    ds = dz if dz_stats is None else dz_stats
+    dg = (ds * xhat).sum((0, 2, 3))
+    db = ds.sum((0, 2, 3))
     sc = (g * invstd)[None, :, None, None]
     if training:
         M = dz.shape[0] * dz.shape[2] * dz.shape[3]
@@ -288,9 +290,10 @@ def backward(dy, cfg, P, S, training=True, quant=False):
     if cfg.expand:
         # --- BN1 + act ---
         z1 = S["h1"] * S["bn1_scale"][None, :, None, None] + S["bn1_shift"][None, :, None, None]
-        dz1 = _rnd(da1 * act_bwd(z1, cfg.act), q)  # materialised bf16
+        dz1_acc = da1 * act_bwd(z1, cfg.act)
+        dz1 = _rnd(dz1_acc, q)  # materialised bf16; the depthwise kernel sums its fp32 values
         G["bn1_g"], G["bn1_b"], dh1 = _bn_bwd(dz1, S["h1"], S["bn1_mean"], S["bn1_invstd"],
-                                              P["bn1_g"], training)
+                                              P["bn1_g"], training, dz1_acc)
         dh1 = _rnd(dh1, q)  # MMA operand
         we = _rnd(P["w_exp"], q)
         G["w_exp"] = torch.einsum("nohw,nchw->oc", dh1, x)

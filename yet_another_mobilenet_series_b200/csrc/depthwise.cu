@@ -687,6 +687,7 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
     if (DGRAD) {
       const float4 mu = *reinterpret_cast<const float4*>(s_tab + 5 * CT + cg * 4);
       const float4 rs = *reinterpret_cast<const float4*>(s_tab + 6 * CT + cg * 4);
+      const float4 nmr = make_float4(-mu.x * rs.x, -mu.y * rs.y, -mu.z * rs.z, -mu.w * rs.w);
       const size_t img_in = (size_t)n * p.H * p.W * p.ldc + c0;
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -706,12 +707,14 @@ __global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
 #pragma unroll
             for (int v = 0; v < 4; ++v) da[v] += rv[v];
           }
-          st4_round(p.dx + off, da);
+          *reinterpret_cast<uint2*>(p.dx + off) =
+              make_uint2(pack_bf16(da[0], da[1]), pack_bf16(da[2], da[3]));
+          // statistics of the fp32 values (see the forward kernel); xhat = x*rs - mu*rs
           ssum[0] += da[0]; ssum[1] += da[1]; ssum[2] += da[2]; ssum[3] += da[3];
-          ssq[0] = fmaf(da[0], (xv[0] - mu.x) * rs.x, ssq[0]);
-          ssq[1] = fmaf(da[1], (xv[1] - mu.y) * rs.y, ssq[1]);
-          ssq[2] = fmaf(da[2], (xv[2] - mu.z) * rs.z, ssq[2]);
-          ssq[3] = fmaf(da[3], (xv[3] - mu.w) * rs.w, ssq[3]);
+          ssq[0] = fmaf(da[0], fmaf(xv[0], rs.x, nmr.x), ssq[0]);
+          ssq[1] = fmaf(da[1], fmaf(xv[1], rs.y, nmr.y), ssq[1]);
+          ssq[2] = fmaf(da[2], fmaf(xv[2], rs.z, nmr.z), ssq[2]);
+          ssq[3] = fmaf(da[3], fmaf(xv[3], rs.w, nmr.w), ssq[3]);
         }
     }
   }
