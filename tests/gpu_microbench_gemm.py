@@ -10,7 +10,8 @@ sys.path.insert(0, ROOT)
 from yet_another_mobilenet_series_b200 import native as nat  # noqa: E402
 
 
-def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10, dgrad=False):
+def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10, dgrad=False,
+        wgrad=False):
     lib = nat.lib()
     dev = "cuda"
     bf = torch.bfloat16
@@ -31,6 +32,18 @@ def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10, dgr
         keep += [sc, sh]
         g.a_xform, g.a_act = 1, 1
         g.a_scale, g.a_shift = sc.data_ptr(), sh.data_ptr()
+    if wgrad:
+        # project-wgrad shape: A = ca*dy + cb*h3 + cc (two sources, M channels, MN-major),
+        # B = act(s*h2 + t) (N channels, MN-major), split-K atomic epilogue
+        A2 = torch.randn(K, M, device=dev).to(bf)
+        co = [torch.ones(M, device=dev), torch.zeros(M, device=dev), torch.ones(M, device=dev) * 0.1]
+        cb2 = [torch.ones(N, device=dev), torch.zeros(N, device=dev)]
+        g.a_xform = 2
+        g.a_scale, g.a_shift, g.a_scale2 = co[0].data_ptr(), co[1].data_ptr(), co[2].data_ptr()
+        g.A2, g.lda2 = A2.data_ptr(), M
+        g.b_xform, g.b_act = 1, 2
+        g.b_scale, g.b_shift = cb2[0].data_ptr(), cb2[1].data_ptr()
+        keep += [A2] + co + cb2
     if dgrad:
         # project-dgrad shape: A = ca*dy + cb*h3 + cc (two sources, K channels), B = W3 MN-major,
         # epilogue dz = acc * act'(s*h2+t) + BatchNorm-backward statistics
@@ -82,6 +95,8 @@ def run(tag, M, N, K, stats=False, xform=0, a_mn=0, b_mn=0, epi=0, iters=10, dgr
     nbytes = 2 * (M * K + N * K) + (4 if epi == 2 else 2) * M * N * (0 if epi == 2 else 1)
     if dgrad:
         nbytes += 2 * M * K + 2 * M * N
+    if wgrad:
+        nbytes += 2 * M * K
     print("%-34s M=%7d N=%4d K=%4d  %.3f ms  %7.1f GB/s" % (tag, M, N, K, ms, nbytes / ms / 1e6))
     sys.stdout.flush()
 

@@ -59,6 +59,7 @@ struct GemmDev {
   int block_n, m_blocks, n_blocks, num_k_blocks, ksplit, kb_per_split, num_work;
   int a_mn, b_mn;
   int num_stages;
+  int a_bytes;      // bytes of the A region of one stage (8 KB when an MN-major A has <= 64 rows)
   int b_bytes;      // bytes of the B region of one stage
   int a2_off;       // offset of A2 region inside a stage (0 = none)
   int b2_off;
@@ -322,7 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           MBAR_WAIT(&bars->empty[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * p.stage_bytes;
-          uint8_t* sB = sA + kABytes;
+          uint8_t* sB = sA + p.a_bytes;
           uint32_t tx = 0;
           const int a_panels = p.a_mn ? 2 : 1;
           int a_issue[2] = {0, 0};
@@ -406,7 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sB = sA + kABytes;
+          const uint32_t sB = sA + p.a_bytes;
           const int krem = p.K - kb * kBlockK;
           const int nk = krem >= kBlockK ? 4 : (krem + 15) / 16;
           for (int kk = 0; kk < nk; ++kk) {
@@ -815,7 +816,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       g.isA = pi < na;
       const int q = g.isA ? pi : pi - na;
       g.mn = g.isA ? (p.a_mn != 0) : (p.b_mn != 0);
-      g.off = (g.isA ? 0u : (uint32_t)kABytes) + (uint32_t)q * (g.mn ? kPanelBytes64 : 128 * 128);
+      g.off = (g.isA ? 0u : (uint32_t)p.a_bytes) + (uint32_t)q * (g.mn ? kPanelBytes64 : 128 * 128);
       g.logR = g.mn ? 6 : 7;
       if (!g.mn) {  // K-major: rows are M (A) or N (B), channels along K
         g.row0 = g.isA ? c.m_blk * kBlockM : c.n_blk * p.block_n + q * 128;
@@ -913,7 +914,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const uint32_t t_s = smem_u32(tab), t_b = smem_u32(tab + Ct), t_s2 = smem_u32(tab + 2 * Ct);
               const float* gate = (mode == 1 && (g.mn || g.isA)) ? (g.isA ? p.a_gate : p.b_gate) : nullptr;
               const uint32_t op2 = sA + (g.isA ? p.a2_off : p.b2_off) +
-                                   (g.off - (g.isA ? 0u : (uint32_t)kABytes));
+                                   (g.off - (g.isA ? 0u : (uint32_t)p.a_bytes));
               // rows the TMA zero-filled (outside the tensor) must stay zero: limit = rlimit
               if (mode == 2)
                 gxform_panel<2, true>(sA + g.off, op2, nullptr, 0, nullptr, 0, ls * ((1 << g.logR) / G),
@@ -1098,7 +1099,10 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   // ---- shared memory plan ----
   const int b_panels = (p.block_n + 63) / 64;
   p.b_bytes = p.b_mn ? b_panels * kPanelBytes64 : ((p.block_n * 128 + 1023) / 1024) * 1024;
-  int stage = kABytes + p.b_bytes;
+  // an MN-major A of <= 64 channels has a single live panel: the second one (rows 64..127 of the
+  // MMA, outputs that are never stored) may alias the B region, the stage shrinks by 8 KB
+  p.a_bytes = (p.a_mn && a->M <= 64) ? kPanelBytes64 : kABytes;
+  int stage = p.a_bytes + p.b_bytes;
   // wide transformed operands come in by TMA (128-byte box rows) and are rewritten in place, a
   // second source needs its own region; narrow ones are combined in registers on their way in
   p.a_tma = (p.a_xform != 0 && (p.a_mn ? a->M : a->K) >= 64) ? 1 : 0;
