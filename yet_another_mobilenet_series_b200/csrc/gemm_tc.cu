@@ -1131,6 +1131,10 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
     fixed = out_bytes + side_bytes + ((coef_bytes + 15) & ~15) + ((stats_bytes + 15) & ~15) +
             (int)sizeof(Bars) + 64;
     stages = (budget - fixed) / p.stage_bytes;
+    // one 64-column sub-tile per tile: a warp's next staging use is two tile periods away (the
+    // warpgroups alternate tiles), a single buffer never waits — spend the 32 KB on stages
+    const bool single_sub = p.block_n <= 64 && a->epi != 2;
+    if (single_sub && p.out_bufs == 2 && stages < kMaxStages) continue;
     if (stages >= 3 || p.out_bufs == 1) break;
   }
   if (stages > kMaxStages) stages = kMaxStages;
