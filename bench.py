@@ -3,6 +3,8 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
   python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (port)
+  python bench.py --impl torch_gpu --steps K ...            # context: the reference's stock-torch
+                                                            # graph (cuDNN/ATen) on the same B200
 
 A step = forward + label-smoothed CE + backward + gradient all-reduce + RMSprop (with L2 decay,
 EMA, bf16 repack) on one synthetic batch of 256 images per GPU (BASELINE.json configs[1];
@@ -131,14 +133,108 @@ def cpu_baseline(steps=3, warmup=1, batch=32, threads=None):
                       "warm-up; %.3f s/step" % (steps, batch, warmup, med)}, med
 
 
+def host_cpu():
+    """Model name and logical CPU count of the box's host (BASELINE.md §4 asks for both)."""
+    name = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    name = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"model": name, "logical_cpus": os.cpu_count(),
+            "usable": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None}
+
+
+def torch_gpu_context(batch=256, steps=5, warmup=3, device=None):
+    """CONTEXT ROW: the reference's own module graph on stock
+    PyTorch kernels (cuDNN / ATen, `cudnn.benchmark = True` as train.py:133 sets it) on THIS GPU,
+    the reference step sequence (Python-loop RMSprop / EMA / L2, the two host syncs of
+    common.py:67-80) — fp32 NCHW exactly as the reference runs, and autocast-bf16 channels_last
+    (the fastest stock configuration).  Same synthetic batch, CUDA-event timing, median."""
+    import torch
+    from oracle import torch_model as tm
+    dev = device or torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, 224, 224, generator=g).to(dev)
+    t = torch.randint(0, 1000, (batch,), generator=g).to(dev)
+    out = {}
+    for tag, ac, cl in (("fp32_nchw", None, False), ("autocast_bf16_channels_last",
+                                                     torch.bfloat16, True)):
+        model = tm.as_reference(build_model()).to(dev)
+        xin = x
+        if cl:
+            model = model.to(memory_format=torch.channels_last)
+            xin = x.contiguous(memory_format=torch.channels_last)
+        tr = tm.RefTrainer(model, batch, autocast=ac)
+        for _ in range(warmup):
+            tr.step(xin, t)
+        torch.cuda.synchronize()
+        full, fb = [], []
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tr.step(xin, t)
+            e1.record()
+            torch.cuda.synchronize()
+            full.append(e0.elapsed_time(e1))
+        for _ in range(steps):      # forward + loss + backward only (no Python-loop optimizer)
+            tr.opt.zero_grad()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if ac is not None:
+                with torch.autocast("cuda", dtype=ac):
+                    o = model(xin).float()
+            else:
+                o = model(xin)
+            tm.label_smooth_ce(o, t, 0.1).mean().backward()
+            e1.record()
+            torch.cuda.synchronize()
+            fb.append(e0.elapsed_time(e1))
+        full.sort()
+        fb.sort()
+        out[tag] = {"step_ms": round(full[len(full) // 2], 3),
+                    "img_per_s": round(batch / (full[len(full) // 2] * 1e-3), 1),
+                    "fwd_bwd_only_ms": round(fb[len(fb) // 2], 3)}
+        del tr, model
+        torch.cuda.empty_cache()
+    out["what"] = ("reference module graph on stock PyTorch %s kernels (cuDNN/ATen, "
+                   "cudnn.benchmark), reference step sequence incl. Python-loop RMSprop/EMA/L2 and "
+                   "its 2 host syncs; N=%d; median of %d steps after %d warm-up"
+                   % (torch.__version__, batch, steps, warmup))
+    return out
+
+
+def run_torch_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ctx = torch_gpu_context(args.batch, steps=max(3, min(args.steps, 10)),
+                            warmup=max(3, min(args.warmup, 5)))
+    best = ctx["autocast_bf16_channels_last"]
+    print(json.dumps({
+        "impl": "torch_gpu", "metric": "images/sec", "value": best["img_per_s"], "unit": "img/s",
+        "n_gpus": 1, "ms_per_step": best["step_ms"], "higher_is_better": True, "dtype": "bf16",
+        "data": "synthetic", "gpu_context": ctx, "host_cpu": host_cpu(),
+        "config": {"workload": "MobileNetV2-1.0 224x224 training step, reference graph on stock "
+                               "PyTorch GPU kernels", "per_gpu_batch": args.batch}}))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, med = cpu_baseline(steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 2)))
+    # every requested step is timed (the driver checks steps x ms against its own clock); the CPU
+    # step takes ~1-2 s, so the default 20 + 5 steps stay well under a minute
+    base, med = cpu_baseline(steps=max(1, args.steps), warmup=max(1, args.warmup))
+    base["host_cpu"] = host_cpu()
     line = {
         "impl": "reference", "metric": "images/sec", "value": base["value"], "unit": "img/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, args.warmup),
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MobileNetV2-1.0 224x224 training step, reference CPU path "
@@ -282,6 +378,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     agg, eager_ms = profile_kernels(ts)
+    launches_per_step = ts.launches_per_step
     hbm_peak, tf_peak, peak_kind = load_peaks()
     kernels = []
     tot_k = sum(r["ms"] for r in agg.values()) or 1.0
@@ -309,8 +406,14 @@ def run_ours(args):
             "avg_launch_ms": round(r["ms"] / max(r["launches"], 1), 5),
         }
     base = None
+    gpu_ctx = None
     if world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_baseline()
+        base["host_cpu"] = host_cpu()
+    if world == 1 and not args.no_gpu_context:
+        del ts
+        torch.cuda.empty_cache()
+        gpu_ctx = torch_gpu_context(B, device=dev)
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
     e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
@@ -330,12 +433,13 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "img/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "note": "host pinned bf16 NHWC batch -> TrainStep (copy stream overlaps compute)"},
-        "gpu_launches": (ts.launches_per_step or 0) * args.steps,
-        "gpu_launches_per_step": ts.launches_per_step,
+        "gpu_launches": (launches_per_step or 0) * args.steps,
+        "gpu_launches_per_step": launches_per_step,
         "roofline": roofline,
         "kernels": kernels,
         "eager_profiled_step_ms": round(eager_ms, 3),
         "cpu_baseline": base,
+        "gpu_context": gpu_ctx,
         "loss_first_last": [loss0, loss_end],
     }
     print(json.dumps(line))
@@ -349,12 +453,16 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-context", action="store_true",
+                    help="skip the stock-PyTorch-on-this-GPU context measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

@@ -240,7 +240,8 @@ int yamb_se_pool_fwd(const yamb_se_pool* args, yamb_stream_t stream);
 
 /* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
  * Replaces RMSprop.step (reference utils/rmsprop.py:67-129), the gradient of cal_l2_loss
- * (utils/optim.py:177-200; l2 * p added where wd_mask != 0), the division by world size of
+ * (utils/optim.py:177-200; l2 * p added where bit 0 of wd_mask is set; bit 1 marks a parameter
+ * that received no gradient this step, rmsprop.py:77-78: only its EMA moves), the division by world size of
  * _allreduce_coalesced (utils/distributed.py:136; grad_scale) and ExponentialMovingAverage.forward
  * (utils/optim.py:53-64; ema / ema_m) in ONE launch over flat fp32 arenas of n elements.
  * hyper: optional device array [lr, ema_m] read instead of the host scalars (CUDA-graph replay). */

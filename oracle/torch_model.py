@@ -51,6 +51,10 @@ def as_reference(model):
     """Copy of `model` whose forward is the reference's stock-torch graph."""
     ref = copy.deepcopy(model)
     for m in ref.modules():
+        if isinstance(m, nn.Sequential) and type(m).forward is not nn.Sequential.forward:
+            # ConvBNReLU of the boundary package routes BatchNorm+activation to the sm_100a
+            # kernels on CUDA; the reference's ConvBNReLU (:181-203) is a plain nn.Sequential
+            m.forward = types.MethodType(nn.Sequential.forward, m)
         if hasattr(m, "pw_bn") and hasattr(m, "ops"):
             m.forward = types.MethodType(_unfused_forward, m)
         elif hasattr(m, "project_conv") and hasattr(m, "depth_ops"):
@@ -137,8 +141,11 @@ class RefTrainer:
 
     def __init__(self, model, batch_size_global, base_lr=0.016, base_total_batch=256, alpha=0.9,
                  momentum=0.9, eps=1e-3, weight_decay=1e-5, label_smoothing=0.1,
-                 ema_decay=0.9999, ema_base_batch=4096):
+                 ema_decay=0.9999, ema_base_batch=4096, autocast=None):
         self.model = model
+        # None: the reference as written (fp32).  A dtype: the same stock-torch graph under
+        # torch.autocast — "the reference's own bf16 path", the parity yardstick of SURVEY §8c(ii)
+        self.autocast = autocast
         self.lr = base_lr * batch_size_global / base_total_batch      # common.py:204-205
         self.opt = RefRMSprop(model.parameters(), self.lr, alpha, eps, True, momentum)
         self.wd = weight_decay
@@ -156,7 +163,11 @@ class RefTrainer:
         model = self.model
         model.train()
         self.opt.zero_grad()                                          # train.py:66
-        out = model(x)
+        if self.autocast is not None:
+            with torch.autocast(x.device.type, dtype=self.autocast):
+                out = model(x).float()
+        else:
+            out = model(x)
         loss_vec = label_smooth_ce(out, target, self.smoothing)
         _ = loss_vec.tolist()                                         # common.py:71 host sync #1
         _, pred = out.topk(5)

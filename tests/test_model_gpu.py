@@ -46,32 +46,43 @@ def test_eval_logits_match_reference_graph(built_lib):
 
 def test_train_step_matches_reference_sequence(built_lib):
     """4 iterations of TrainStep (graph replay from the 3rd) vs oracle RefTrainer on CPU fp32 with
-    the same data: loss curve and parameter trajectory agree within the bf16 budget."""
+    the same data on a toy size: first loss, the EMA recurrence (exact) and "it trains".  The
+    trajectory parity at the real configurations, with the autocast yardstick, lives in
+    tests/test_configs_gpu.py."""
     from oracle import torch_model as tm
     from yet_another_mobilenet_series_b200.trainer import TrainStep
     B = 16
     m = _model(64)
     ref = tm.as_reference(m)
     trainer = tm.RefTrainer(ref, B)
+    w0 = m.classifier[1].weight.detach().clone()
     m = m.cuda()
     ts = TrainStep(m, B, image_size=64)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, 3, 64, 64, generator=g)
     t = torch.randint(0, 100, (B,), generator=g)
-    p0 = {k: v.detach().clone() for k, v in ref.named_parameters()}
-    losses_ref, losses = [], []
+    losses_ref, losses, snaps = [], [], []
     for i in range(4):
         l2 = float(tm.l2_loss_mnas(ref, 1e-5))
         losses_ref.append(trainer.step(x, t) - l2)  # TrainStep folds L2 into the update
         losses.append(float(ts(x.to(torch.bfloat16), t)))
+        snaps.append(m.classifier[1].weight.detach().clone())
     torch.cuda.synchronize()
     assert ts.graph is not None
     assert abs(losses[0] - losses_ref[0]) < 2e-2 * abs(losses_ref[0])
-    for a, b in zip(losses, losses_ref):
-        assert abs(a - b) < 1.5e-1 * abs(b), (losses, losses_ref)
-    assert losses[-1] < 0.5 * losses[0]  # it trains
-    # EMA shadow of a weight follows utils/optim.py:56-64 exactly given OUR weights
-    assert ts.opt.ema_shadow(m.classifier[1].weight).shape == m.classifier[1].weight.shape
+    assert losses[-1] < 0.5 * losses[0] and losses_ref[-1] < 0.5 * losses_ref[0]  # both train
+    # EMA shadow of a weight: the recurrence of utils/optim.py:56-64 on OUR weight trajectory,
+    # m = min(decay_adjusted, (1 + t) / (10 + t)) with t the incremented global step (train.py:109)
+    decay = 0.9999 ** (B / 4096)
+    sh = w0.cuda()
+    for step, w in enumerate(snaps, 1):
+        mm = min(decay, (1.0 + step) / (10.0 + step))
+        sh = mm * sh + (1.0 - mm) * w
+    got = ts.opt.ema_shadow(m.classifier[1].weight)
+    assert float((got - sh).abs().max()) < 1e-6 * float(sh.abs().max()) + 1e-9
+    # ... and it is what the reference's EMA holds for ITS trajectory, within the bf16 budget
+    ref_sh = trainer.ema.shadow["classifier.1.weight"]
+    assert _rel(got - w0.cuda(), ref_sh - w0) < 0.2
 
 
 def test_first_step_gradients_match_reference_graph(built_lib):
@@ -124,29 +135,65 @@ def test_first_step_gradients_match_reference_graph(built_lib):
     assert min(o - a for o, a in zip(ours, auto)) > -0.12, report
 
 
+def _state(ts, model):
+    A = ts.opt.arenas()
+    st = {k: A[k].clone() for k in ("p", "sq", "mom", "ema", "bf16") if A.get(k) is not None}
+    st["buf"] = {k: v.clone() for k, v in model.named_buffers()}
+    st["shadow"] = [s.clone() for s in ts.stat_shadow]
+    st["step"] = ts.global_step
+    return st
+
+
+def _restore(ts, model, st):
+    A = ts.opt.arenas()
+    with torch.no_grad():
+        for k in ("p", "sq", "mom", "ema", "bf16"):
+            if k in st:
+                A[k].copy_(st[k])
+        for k, v in model.named_buffers():
+            v.copy_(st["buf"][k])
+        for s, v in zip(ts.stat_shadow, st["shadow"]):
+            s.copy_(v)
+    ts.global_step = st["step"]
+
+
 def test_graph_replay_equals_eager(built_lib):
+    """The SAME iteration (same state, same batch) run eagerly and as a CUDA-graph replay.  The
+    kernels' fp32 reductions (BatchNorm statistics, split-K weight gradients) are order-free
+    atomics, so the two runs agree to reduction-order noise, not bit for bit; one iteration keeps
+    that noise un-amplified: loss to 2e-3, the whole parameter update to 3e-2 rel-L2."""
     from yet_another_mobilenet_series_b200.trainer import TrainStep
-    B = 8
+    B = 32
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(B, 3, 64, 64, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, 3, 96, 96, generator=g).to(torch.bfloat16)
     t = torch.randint(0, 100, (B,), generator=g)
-    out = []
-    for use_graph in (True, False):
-        m = _model(64).cuda()
-        for mod in m.modules():  # the dropout stream differs between capture and eager: switch it off
-            if isinstance(mod, torch.nn.Dropout):
-                mod.p = 0.0
-        ts = TrainStep(m, B, image_size=64, use_graph=use_graph)
-        ls = [float(ts(x, t)) for _ in range(5)]
-        torch.cuda.synchronize()
-        out.append((ls, m.classifier[1].weight.detach().clone()))
-    # Same state, same batch, yet not bit-identical: fp32 reductions (BatchNorm statistics, weight
-    # gradients) are order-free atomics, and a 1e-7 change of a BatchNorm scale flips bf16 roundings
-    # that the 32-sample BatchNorms of this 8-image/64-pixel toy amplify (tests/gpu_determinism.py:
-    # 3e-6 after block 1, a few 1e-2 at the logits, run to run).  So: near-equal first loss, the
-    # same trajectory within that noise, both training.
-    assert abs(out[0][0][0] - out[1][0][0]) < 1e-2 * abs(out[1][0][0]), (out[0][0], out[1][0])
-    for a, b in zip(out[0][0], out[1][0]):
-        assert abs(a - b) < 0.3 * abs(b), (out[0][0], out[1][0])
-    assert out[0][0][-1] < 0.5 * out[0][0][0] and out[1][0][-1] < 0.5 * out[1][0][0]
-    assert _rel(out[0][1], out[1][1]) < 0.3
+    m = _model(96).cuda()
+    for mod in m.modules():  # the dropout stream differs between capture and eager: switch it off
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ts = TrainStep(m, B, image_size=96)
+    for _ in range(2):
+        ts(x, t)                                  # two eager warm-up iterations
+    torch.cuda.synchronize()
+    st = _state(ts, m)
+    ts.use_graph = False
+    loss_e = float(ts(x, t))
+    p_e = ts.opt.arenas()["p"].clone()
+    _restore(ts, m, st)
+    loss_e2 = float(ts(x, t))                     # eager twice: the reduction-order noise itself
+    p_e2 = ts.opt.arenas()["p"].clone()
+    _restore(ts, m, st)
+    ts.use_graph = True
+    loss_g = float(ts(x, t))                      # captures, then replays
+    torch.cuda.synchronize()
+    assert ts.graph is not None
+    p_g = ts.opt.arenas()["p"].clone()
+    noise = _rel(p_e2 - st["p"], p_e - st["p"])
+    diff = _rel(p_g - st["p"], p_e - st["p"])
+    print("eager-vs-eager update rel-L2 %.3e, graph-vs-eager %.3e; losses %r %r %r"
+          % (noise, diff, loss_e, loss_e2, loss_g))
+    assert abs(loss_g - loss_e) < 2e-3 * abs(loss_e)
+    assert diff < max(3e-2, 3 * noise)
+    # replaying again advances the training (the graph is not a frozen snapshot)
+    loss_next = float(ts(x, t))
+    assert loss_next < loss_g

@@ -106,3 +106,58 @@ def test_negative_hyper_raises():
                dict(alpha=-1)):
         with pytest.raises(ValueError):
             RMSprop(p, **kw)
+
+
+def test_stale_bf16_mirror_is_refreshed_after_inplace_weight_write(built_lib):
+    """the block kernels read the optimizer's bf16 weight mirror.  A load_state_dict /
+    broadcast / re-init AFTER the arenas were built writes the fp32 masters in place; the next
+    forward must see the new weights (the mirror is re-cast when `_version` moved)."""
+    from yet_another_mobilenet_series_b200 import mobilenet_base as mb
+    from yet_another_mobilenet_series_b200.fused_rmsprop import RMSprop
+    torch.manual_seed(3)
+    bn = {"momentum": 0.01, "eps": 1e-3}
+
+    def make():
+        b = mb.InvertedResidualChannels(16, 24, 1, [96], [3], True, mb.get_active_fn("nn.ReLU"), bn)
+        b.apply(mb.init_weights_mnas)
+        return b.cuda().eval()
+
+    blk, other = make(), make()
+    opt = RMSprop(blk.parameters(), lr=0.01, momentum=0.9)
+    opt.arenas()                                   # mirrors exist from here on
+    x = torch.randn(4, 16, 12, 12, device="cuda")
+    with torch.no_grad():
+        y0 = blk(x).float()
+        blk.load_state_dict(other.state_dict())    # in-place copy_ into the arena views
+        y1 = blk(x).float()
+        want = other(x).float()
+    assert float((y1 - want).abs().max()) == 0.0   # same kernels, same weights: bit-identical
+    assert float((y1 - y0).abs().max()) > 1e-2     # and it really changed
+    assert opt.sync_mirror() == 0                  # nothing left stale
+
+
+def test_step_uses_grads_that_left_the_arena_and_skips_gradless_params(built_lib):
+    """`model.zero_grad(set_to_none=True)` detaches the `.grad` views; autograd then
+    allocates fresh gradient tensors.  step() must use them (copy into the arena, re-attach), and
+    a parameter without a gradient is skipped like the reference does (utils/rmsprop.py:77-78)."""
+    from yet_another_mobilenet_series_b200.fused_rmsprop import RMSprop
+    torch.manual_seed(0)
+    a = torch.nn.Parameter(torch.randn(37, device="cuda"))
+    b = torch.nn.Parameter(torch.randn(5, 3, device="cuda"))
+    opt = RMSprop([a, b], lr=0.1, alpha=0.9, momentum=0.9, eps=1e-3, eps_inside_sqrt=True)
+    opt.arenas()
+    a0, b0 = a.detach().clone(), b.detach().clone()
+    a.grad = None
+    b.grad = None                                   # what nn.Module.zero_grad() does
+    (a * 2.0).sum().backward()                      # fresh .grad tensor for a, none for b
+    assert a.grad.data_ptr() != opt.arenas()["gptr"][0]
+    opt.step()
+    torch.cuda.synchronize()
+    g = 2.0
+    sq = 0.1 * g * g
+    want = a0 - 0.1 * (g / (sq + 1e-3) ** 0.5)
+    assert torch.allclose(a, want, rtol=1e-6, atol=1e-7)
+    assert torch.equal(b, b0)                       # skipped: no state change at all
+    assert float(opt.state[b]["square_avg"].abs().max()) == 0.0
+    assert opt.state[a]["step"] == 1 and opt.state[b]["step"] == 0
+    assert a.grad.data_ptr() == opt.arenas()["gptr"][0]   # re-attached to the arena

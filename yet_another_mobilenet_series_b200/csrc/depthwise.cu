@@ -743,14 +743,29 @@ static int check_common(int N, int H, int W, int C, int ldc, int k, int stride) 
 
 template <typename Kern, typename Dev>
 static cudaError_t launch_k(Kern kern, const Dev& p, size_t smem, long long tiles, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  // attribute + occupancy are looked up once per (kernel, shared-memory size)
+  struct Ent { const void* k; size_t smem; int per_sm; };
+  static thread_local Ent cache[96];
+  static thread_local int n_cache = 0;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  for (int i = 0; i < n_cache; ++i)
+    if (cache[i].k == (const void*)kern && cache[i].smem == smem) per_sm = cache[i].per_sm;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    if (n_cache < 96) cache[n_cache++] = Ent{(const void*)kern, smem, per_sm};
+  }
   long long cap = (long long)max_ctas() * (per_sm > 4 ? 4 : per_sm);  // partials sized for 4/SM
   int grid = (int)(tiles < cap ? tiles : cap);
+  // Tiles are ordered channel-chunk-major and every CTA walks a contiguous range.  With a grid that
+  // is a multiple of the chunk count, CTA b and CTA b + grid/chunks walk the SAME spatial tiles of
+  // neighbouring channel chunks at the same time, so the 128-byte lines that straddle two chunks
+  // (pixels of 192 / 288 bytes read in 64-byte pieces) and the halo rows are served by L2 instead
+  // of being fetched from DRAM once per chunk (ncu r01: 2.7x the algorithmic reads at C = 144).
+  if (p.chunks > 1 && grid > p.chunks) grid = grid / p.chunks * p.chunks;
   if (grid < 1) grid = 1;
   kern<<<grid, 256, smem, st>>>(p);
   return cudaGetLastError();

@@ -1051,7 +1051,8 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   if ((p.a_xform == 2 && (!a->A2 || !a->a_scale2)) || (p.b_xform == 2 && (!a->B2 || !a->b_scale2)))
     return set_error(YAMB_EINVAL, "two-source transform without second tensor");
   p.has_residual = (a->epi == 0 && a->residual) ? 1 : 0;
-  { const char* d = getenv("YAMB_GEMM_DEBUG"); p.dbg = d ? atoi(d) : 0; }
+  static const int env_dbg = [] { const char* d = getenv("YAMB_GEMM_DEBUG"); return d ? atoi(d) : 0; }();
+  p.dbg = env_dbg;
   p.dbg_buf = nullptr;
   if (p.dbg & 512) {
     static unsigned long long* dbuf = nullptr;
@@ -1107,9 +1108,8 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   // second source needs its own region; narrow ones are combined in registers on their way in
   p.a_tma = (p.a_xform != 0 && (p.a_mn ? a->M : a->K) >= 64) ? 1 : 0;
   p.b_tma = (p.b_xform != 0 && (p.b_mn ? a->N : a->K) >= 64) ? 1 : 0;
-  int dbg_env = 0;
-  { const char* d = getenv("YAMB_GEMM_DEBUG"); dbg_env = d ? atoi(d) : 0;
-    if (dbg_env & 1024) p.a_tma = p.b_tma = 0; }
+  const int dbg_env = env_dbg;
+  if (dbg_env & 1024) p.a_tma = p.b_tma = 0;
   // transformed operands: 4 (2) loader warps share a stage so that its transform latency is short;
   // plain GEMMs are bound by load latency: one warp per stage, as many stages in flight as warps
   p.a2_off = p.b2_off = 0;
@@ -1216,9 +1216,13 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   cudaError_t e;
 #define YAMB_GEMM_LAUNCH(XF, EP, THREADS)                                                         \
   do {                                                                                           \
-    e = cudaFuncSetAttribute(gemm_tc_kernel<XF, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             smem_total);                                                        \
-    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e));  \
+    static thread_local int attr_smem = 0; /* per instantiation: raise the limit only when needed */ \
+    if (attr_smem < smem_total) {                                                                \
+      e = cudaFuncSetAttribute(gemm_tc_kernel<XF, EP>,                                           \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);         \
+      if (e != cudaSuccess) return set_error(YAMB_ECUDA, "smem attr: %s", cudaGetErrorString(e)); \
+      attr_smem = smem_total;                                                                    \
+    }                                                                                            \
     gemm_tc_kernel<XF, EP><<<grid, THREADS, smem_total, stream>>>(tmA, tmB, tmA2, tmB2, tmD, p); \
   } while (0)
   if (xf) {

@@ -20,8 +20,16 @@ struct RmsDev {
   int eps_inside_sqrt;
 };
 
+// mask byte per element: bit 0 = the 'mnas' L2 term applies, bit 1 = the parameter received no
+// gradient this step (reference rmsprop.py:77-78 `if p.grad is None: continue`): only its EMA moves
 __device__ __forceinline__ void rms_one(const RmsDev& a, float lr, float ema_m, float& p, float g,
-                                        float& sq, float* mom, float* gavg, float* ema, bool l2on) {
+                                        float& sq, float* mom, float* gavg, float* ema,
+                                        unsigned mask) {
+  const bool l2on = mask & 1u;
+  if (mask & 2u) {
+    if (ema) *ema = *ema * ema_m + (1.f - ema_m) * p;
+    return;
+  }
   g *= a.grad_scale;
   if (l2on) g = fmaf(a.l2, p, g);                       // d/dp 0.5*wd*p^2 (optim.py:193-200)
   if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);  // rmsprop.py:99-100
@@ -57,13 +65,13 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Rm
     float4 em = a.ema ? reinterpret_cast<float4*>(a.ema)[i] : make_float4(0, 0, 0, 0);
     uchar4 wm = a.wd_mask ? reinterpret_cast<const uchar4*>(a.wd_mask)[i] : make_uchar4(0, 0, 0, 0);
     rms_one(a, lr, ema_m, p.x, g.x, sq.x, a.mom ? &mo.x : nullptr, a.grad_avg ? &ga.x : nullptr,
-            a.ema ? &em.x : nullptr, wm.x != 0);
+            a.ema ? &em.x : nullptr, wm.x);
     rms_one(a, lr, ema_m, p.y, g.y, sq.y, a.mom ? &mo.y : nullptr, a.grad_avg ? &ga.y : nullptr,
-            a.ema ? &em.y : nullptr, wm.y != 0);
+            a.ema ? &em.y : nullptr, wm.y);
     rms_one(a, lr, ema_m, p.z, g.z, sq.z, a.mom ? &mo.z : nullptr, a.grad_avg ? &ga.z : nullptr,
-            a.ema ? &em.z : nullptr, wm.z != 0);
+            a.ema ? &em.z : nullptr, wm.z);
     rms_one(a, lr, ema_m, p.w, g.w, sq.w, a.mom ? &mo.w : nullptr, a.grad_avg ? &ga.w : nullptr,
-            a.ema ? &em.w : nullptr, wm.w != 0);
+            a.ema ? &em.w : nullptr, wm.w);
     reinterpret_cast<float4*>(a.p)[i] = p;
     reinterpret_cast<float4*>(a.sq)[i] = sq;
     if (a.mom) reinterpret_cast<float4*>(a.mom)[i] = mo;
@@ -79,7 +87,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Rm
     float mo = a.mom ? a.mom[i] : 0.f, ga = a.grad_avg ? a.grad_avg[i] : 0.f;
     float em = a.ema ? a.ema[i] : 0.f;
     rms_one(a, lr, ema_m, p, a.g[i], sq, a.mom ? &mo : nullptr, a.grad_avg ? &ga : nullptr,
-            a.ema ? &em : nullptr, a.wd_mask && a.wd_mask[i]);
+            a.ema ? &em : nullptr, a.wd_mask ? a.wd_mask[i] : 0u);
     a.p[i] = p; a.sq[i] = sq;
     if (a.mom) a.mom[i] = mo;
     if (a.grad_avg) a.grad_avg[i] = ga;

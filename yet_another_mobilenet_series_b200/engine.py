@@ -15,6 +15,7 @@ torch.autograd backward.  No tensor between the 1x1 convs is ever normalised in 
 activation are applied by the consumer on load.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -43,6 +44,37 @@ def launch(fn, st, tag="", nbytes=0, flops=0):
     nat.check(fn(C.byref(st), nat.stream_handle()))
     e1.record()
     PROFILE.append((tag, nbytes, flops, e0, e1))
+
+
+# ---- weight-gradient side stream -------------------------------------------------------------------
+# The split-K wgrad GEMMs feed nothing but the optimizer, so they leave the dgrad -> depthwise ->
+# dgrad dependency chain: they are enqueued on a second stream right after the kernel that produces
+# their last input and fill the SMs the chain's under-filled launches (7x7 / 14x14 layers: fewer
+# tiles than SMs) and kernel tails leave idle.  `join_side()` makes the current stream wait for
+# them.  With DEFER_JOIN False (default) every block joins at the end of its backward, so plain
+# `loss.backward(); any_optimizer.step()` code is safe; TrainStep defers the join to the end of the
+# whole backward.  YAMB_SIDE_WGRAD=0 puts everything back on one stream.
+SIDE_WGRAD = os.environ.get("YAMB_SIDE_WGRAD", "1") != "0"
+DEFER_JOIN = False
+_side = {}
+
+
+def _side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side.get(key)
+    if st is None:
+        st = {"stream": torch.cuda.Stream(device=dev), "pending": False}
+        _side[key] = st
+    return st
+
+
+def join_side(dev=None):
+    """Current stream waits for every wgrad launched on the side stream so far."""
+    for key, st in _side.items():
+        if st["pending"] and (dev is None or key == (dev.index if dev.index is not None
+                                                      else torch.cuda.current_device())):
+            torch.cuda.current_stream().wait_stream(st["stream"])
+            st["pending"] = False
 
 
 def act_code_of(active_fn):
@@ -216,6 +248,7 @@ class BlockPlan:
         # ---- bf16 tensor-core operands + fp32 gradient accumulators ----
         self.w_exp_bf = torch.empty(Chid, Cin, device=dev, dtype=bf) if self.expand else None
         self.w_proj_bf = torch.empty(Cout, Chid, device=dev, dtype=bf)
+        self.w_exp_own, self.w_proj_own = self.w_exp_bf, self.w_proj_bf
         self.g_exp = _f32(Chid * Cin, dev).view(Chid, Cin) if self.expand else None
         self.g_proj = _f32(Cout * Chid, dev).view(Cout, Chid)
         self.g_dw = [torch.zeros_like(c.weight, dtype=torch.float32) for c in self.conv_dw]
@@ -287,30 +320,47 @@ class BlockPlan:
         return s
 
     def _refresh_weights(self):
-        """fp32 master -> bf16 tensor-core operands (merged over branches)."""
+        """fp32 master -> bf16 tensor-core operands (merged over branches).
+
+        A single-branch weight uses the fused optimizer's bf16 mirror arena directly.  The mirror
+        is rewritten by `yamb_rmsprop_step` (a raw-pointer write that does not touch the tensor's
+        version counter); any OTHER in-place write to the fp32 master (load_state_dict, a DDP
+        broadcast, re-initialisation, an EMA swap-in) bumps `_version`, which is detected here and
+        the mirror is re-cast before use."""
         with torch.no_grad():
             if self.expand:
                 if len(self.conv_exp) == 1:
-                    w = self.conv_exp[0].weight
-                    mirror = getattr(w, "_yamb_bf16", None)  # kept fresh by the fused optimizer
-                    if mirror is not None:
-                        self.w_exp_bf = mirror.view(self.Chid, self.Cin)
-                    else:
-                        self.w_exp_bf.copy_(w.view(self.Chid, self.Cin))
+                    self.w_exp_bf = _bf16_operand(self.conv_exp[0].weight, self.w_exp_own,
+                                                  (self.Chid, self.Cin))
                 else:
                     self.w_exp_bf.copy_(torch.cat([c.weight.flatten(1) for c in self.conv_exp]))
             if len(self.conv_proj) == 1:
-                w = self.conv_proj[0].weight
-                mirror = getattr(w, "_yamb_bf16", None)
-                if mirror is not None:
-                    self.w_proj_bf = mirror.view(self.Cout, self.Chid)
-                else:
-                    self.w_proj_bf.copy_(w.view(self.Cout, self.Chid))
+                self.w_proj_bf = _bf16_operand(self.conv_proj[0].weight, self.w_proj_own,
+                                               (self.Cout, self.Chid))
             else:
                 self.w_proj_bf.copy_(torch.cat([c.weight.flatten(1) for c in self.conv_proj], 1))
 
     def _call(self, fn, st, tag="", nbytes=0, flops=0):
         launch(fn, st, tag, nbytes, flops)
+
+    def _fork_event(self):
+        if not SIDE_WGRAD or PROFILE is not None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
+
+    def _call_side(self, fn, st, tag, nbytes, flops, ev, tensors):
+        """Launch on the wgrad side stream once `ev` (recorded on the main stream) has passed."""
+        if ev is None:
+            return launch(fn, st, tag, nbytes, flops)
+        side = _side_stream(self.dev)
+        side["stream"].wait_event(ev)
+        with torch.cuda.stream(side["stream"]):
+            launch(fn, st, tag, nbytes, flops)
+        for t in tensors:    # caller-owned storage read by the side stream: keep it alive for it
+            t.record_stream(side["stream"])
+        side["pending"] = True
 
     # -- forward ---------------------------------------------------------------------------------
     def forward(self, x):
@@ -496,6 +546,7 @@ class BlockPlan:
         r.dy, r.h = dym.data_ptr(), self.h3.data_ptr()
         r.bn = C.pointer(self._bn_bwd_struct(self.bn3, self.M_out, grads["bn3"]))
         self._call(lib.yamb_bn_reduce_bwd, r, "bn_reduce", 4 * self.M_out * self.Cout)
+        fork_ev = self._fork_event()
         # 2. project dgrad: da2 = dh3 * W3, dz2 = da2 * act'(z2), BN2-backward statistics
         g = nat.Gemm()
         g.M, g.N, g.K = self.M_out, self.Chid, self.Cout
@@ -554,9 +605,10 @@ class BlockPlan:
             g.b_gate, g.gate_rows_per_sample = self.gate.data_ptr(), self.Ho * self.Wo
         g.D, g.ldd = grads["proj"].data_ptr(), self.Chid
         g.epi = 2
-        self._call(lib.yamb_pointwise_gemm, g, "pw_project_wgrad",
-                   2 * self.M_out * (2 * self.Cout + self.Chid),
-                   2 * self.M_out * self.Chid * self.Cout)
+        # needs only the BN3-backward coefficients (step 1) -> off the critical chain
+        self._call_side(lib.yamb_pointwise_gemm, g, "pw_project_wgrad",
+                        2 * self.M_out * (2 * self.Cout + self.Chid),
+                        2 * self.M_out * self.Chid * self.Cout, fork_ev, (dy,))
         # 4. depthwise backward per branch
         c0 = 0
         for b, (cb, k) in enumerate(zip(self.channels, self.ks)):
@@ -586,6 +638,7 @@ class BlockPlan:
             c0 += cb
         if not self.expand:
             return dx
+        fork2_ev = self._fork_event()   # dz1 and the BN1-backward coefficients exist from here on
         # 5. expand dgrad: dx = dh1 * W1 (+ dy)
         g = nat.Gemm()
         g.M, g.N, g.K = self.M_in, self.Cin, self.Chid
@@ -613,10 +666,23 @@ class BlockPlan:
         g.B, g.ldb = xm.data_ptr(), self.Cin
         g.D, g.ldd = grads["exp"].data_ptr(), self.Cin
         g.epi = 2
-        self._call(lib.yamb_pointwise_gemm, g, "pw_expand_wgrad",
-                   2 * self.M_in * (2 * self.Chid + self.Cin),
-                   2 * self.M_in * self.Chid * self.Cin)
+        self._call_side(lib.yamb_pointwise_gemm, g, "pw_expand_wgrad",
+                        2 * self.M_in * (2 * self.Chid + self.Cin),
+                        2 * self.M_in * self.Chid * self.Cin, fork2_ev, (x,))
         return dx
+
+
+def _bf16_operand(w, own, shape):
+    """bf16 tensor-core operand of an fp32 master weight: the optimizer's mirror when it is
+    provably fresh (same `_version` as when the mirror was last written), else a re-cast."""
+    mirror = getattr(w, "_yamb_bf16", None)
+    if mirror is None:
+        own.copy_(w.view(shape))
+        return own
+    if getattr(w, "_yamb_bf16_version", None) != w._version:
+        mirror.copy_(w)                       # stale: somebody wrote the master in place
+        w._yamb_bf16_version = w._version
+    return mirror.view(shape)
 
 
 def _torch_act(z, code):
@@ -745,6 +811,8 @@ def run_backward(block, plan, x, dy):
         g["bn2"] = bn_targets(plan.bn2, "bn2")
         g["bn3"] = bn_targets(plan.bn3, "bn3")
         dx = plan.backward(x, dy, g)
+        if not (DEFER_JOIN and direct and single_proj and (single_exp or not plan.expand)):
+            join_side(plan.dev)   # the gradient hand-over below reads what the wgrads wrote
         # ---- hand gradients to autograd ----
         gmap = {}
         if plan.expand:
@@ -982,15 +1050,21 @@ class _BnActFn(torch.autograd.Function):
         st.keep.append(a)
         launch(lib.yamb_bn_apply_fwd, a, "bn_apply", 4 * M * Cc)
         ctx.bn, ctx.act, ctx.st = bn, act, st
-        ctx.save_for_backward(h)
+        # per-call copy of [scale, shift, mean, invstd]: another forward through this module before
+        # the backward (eval / calibration pass, gradient accumulation) must not change what the
+        # backward of THIS call sees
+        coef = torch.stack((b.scale, b.shift, b.mean, b.invstd)) if any(ctx.needs_input_grad) \
+            else None
+        ctx.save_for_backward(h, coef)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         lib = nat.lib()
-        (h,) = ctx.saved_tensors
+        h, coef = ctx.saved_tensors
         bn, act, st = ctx.bn, ctx.act, ctx.st
         b = st.bn
+        c_scale, c_shift, c_mean, c_invstd = (coef[i].data_ptr() for i in range(4))
         dy = to_nhwc_bf16(dy)
         N, Cc, H, W = h.shape
         M = N * H * W
@@ -1009,7 +1083,7 @@ class _BnActFn(torch.autograd.Function):
         g = nat.BnBwd()
         g.partials, g.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
         g.gamma = nat.ptr(bn.weight)
-        g.mean, g.invstd = b.mean.data_ptr(), b.invstd.data_ptr()
+        g.mean, g.invstd = c_mean, c_invstd
         g.dgamma, g.dbeta = dg.data_ptr(), db.data_ptr()
         g.ca, g.cb, g.cc = b.ca.data_ptr(), b.cb.data_ptr(), b.cc.data_ptr()
         g.count = M
@@ -1017,13 +1091,13 @@ class _BnActFn(torch.autograd.Function):
         r = nat.BnReduce()
         r.M, r.C, r.lddy, r.ldh = M, Cc, Cc, Cc
         r.dy, r.h, r.bn = dym.data_ptr(), hm.data_ptr(), C.pointer(g)
-        r.z_scale, r.z_shift, r.z_act = b.scale.data_ptr(), b.shift.data_ptr(), act
+        r.z_scale, r.z_shift, r.z_act = c_scale, c_shift, act
         launch(lib.yamb_bn_reduce_bwd, r, "bn_reduce", 4 * M * Cc)
         dh = torch.empty_like(h, memory_format=torch.channels_last)
         a = nat.BnBwdApply()
         a.M, a.C, a.lddy, a.ldh, a.lddh = M, Cc, Cc, Cc, Cc
         a.dy, a.h = dym.data_ptr(), hm.data_ptr()
-        a.z_scale, a.z_shift, a.z_act = b.scale.data_ptr(), b.shift.data_ptr(), act
+        a.z_scale, a.z_shift, a.z_act = c_scale, c_shift, act
         a.ca, a.cb, a.cc = b.ca.data_ptr(), b.cb.data_ptr(), b.cc.data_ptr()
         a.dh = dh.data_ptr()
         st.keep += [g, r, a]

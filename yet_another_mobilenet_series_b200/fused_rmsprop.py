@@ -158,6 +158,10 @@ class RMSprop(Optimizer):
             A["bf16"].copy_(A["p"])
             if A["ema"] is not None:
                 A["ema"].copy_(A["p"])
+        for p in plist:
+            p._yamb_bf16_version = p._version     # the mirror is fresh as of this version
+        A["gptr"] = [A["g"].data_ptr() + 4 * o for o in offs]
+        A["frozen"] = None                        # mask variant used while some p.grad is None
         self._hyper = torch.zeros(2, device=dev, dtype=torch.float32)
         self._arenas = A
         return A
@@ -181,6 +185,46 @@ class RMSprop(Optimizer):
         for p, o in zip(A["plist"], A["offs"]):
             if p.grad is None:
                 p.grad = A["g"][o:o + p.numel()].view(p.shape)
+
+    def sync_mirror(self):
+        """Re-cast the bf16 mirror of every parameter whose fp32 master was written in place by
+        anybody but `step()` (load_state_dict, broadcast, re-init: they bump `_version`).  Cheap
+        host loop; TrainStep calls it before every (graph-replayed) iteration."""
+        A = self.arenas()
+        stale = [p for p in A["plist"] if p._yamb_bf16_version != p._version]
+        with torch.no_grad():
+            for p in stale:
+                p._yamb_bf16.copy_(p)
+                p._yamb_bf16_version = p._version
+        return len(stale)
+
+    def _collect_grads(self, A):
+        """Make the flat gradient arena reflect every `p.grad`: a `.grad` that is no
+        longer the arena view (model.zero_grad(set_to_none=True) followed by autograd allocating a
+        fresh tensor) is copied in and re-attached; a parameter whose grad is None is skipped by
+        the step exactly like the reference does (utils/rmsprop.py:77-78).  Returns the per-element
+        mask to hand to the kernel."""
+        inactive = []
+        for i, p in enumerate(A["plist"]):
+            g = p.grad
+            if g is None or not p.requires_grad:
+                inactive.append(i)
+            elif g.data_ptr() != A["gptr"][i]:
+                o = A["offs"][i]
+                view = A["g"][o:o + p.numel()].view(p.shape)
+                view.copy_(g)
+                p.grad = view
+        if not inactive:
+            return A["mask"], None
+        key = tuple(inactive)
+        if A["frozen"] is None or A["frozen"][0] != key:
+            m = A["mask"].clone() if A["mask"] is not None else \
+                torch.zeros(A["n"], device=A["p"].device, dtype=torch.uint8)
+            for i in inactive:
+                o = A["offs"][i]
+                m[o:o + A["plist"][i].numel()] |= 2
+            A["frozen"] = (key, m)
+        return A["frozen"][1], set(inactive)
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -215,7 +259,8 @@ class RMSprop(Optimizer):
         a.grad_avg = nat.ptr(A["gavg"])
         a.ema = nat.ptr(A["ema"])
         a.p_bf16 = A["bf16"].data_ptr()
-        a.wd_mask = nat.ptr(A["mask"])
+        mask, inactive = self._collect_grads(A)
+        a.wd_mask = nat.ptr(mask)
         a.lr, a.alpha, a.eps = g0["lr"], g0["alpha"], g0["eps"]
         a.momentum, a.weight_decay = g0["momentum"], g0["weight_decay"]
         a.l2 = self._l2
@@ -226,8 +271,9 @@ class RMSprop(Optimizer):
         if use_device_hyper:
             a.hyper = self._hyper.data_ptr()
         nat.check(nat.lib().yamb_rmsprop_step(C.byref(a), nat.stream_handle()))
-        for p in A["plist"]:
-            self.state[p]["step"] += 1
+        for i, p in enumerate(A["plist"]):
+            if inactive is None or i not in inactive:
+                self.state[p]["step"] += 1
         return loss
 
 

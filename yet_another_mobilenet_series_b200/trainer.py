@@ -91,7 +91,12 @@ class TrainStep:
         logits = self.model(self.x)
         per_sample = label_smooth_ce(logits, self.t, self.smoothing)
         loss = per_sample.mean()
-        loss.backward()
+        engine.DEFER_JOIN = True      # wgrad side stream: one join after the whole backward
+        try:
+            loss.backward()
+        finally:
+            engine.DEFER_JOIN = False
+            engine.join_side(self.dev)
         self.loss.copy_(loss.detach())
         self.top1.copy_((logits.argmax(1) == self.t).float().mean())
 
@@ -113,6 +118,7 @@ class TrainStep:
             self.consumed.record(cur)
             self.staged = False
         self.model.train()
+        self.opt.sync_mirror()   # masters written in place since the last step (load_state_dict ...)
         if self.use_graph and self.graph is None and self._warm >= 2:
             torch.cuda.synchronize()
             self._capture()
