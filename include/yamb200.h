@@ -175,6 +175,9 @@ typedef struct yamb_bn_apply {
   const void* h; const float* scale; const float* shift; int32_t act;
   const void* residual; void* y;
   const float* gate; int64_t rows_per_sample;   /* optional [N][C] fp32 gate */
+  const void* residual2; int32_t ldr2;          /* optional second bf16 addend (non-local block:
+                                                 * bn(dw(f)) + l + x, models/mobilenet_base.py:173,
+                                                 * :340-341) */
 } yamb_bn_apply;
 
 typedef struct yamb_bn_reduce {
@@ -238,6 +241,39 @@ int yamb_bn_stats_fwd(const yamb_bn_stats* args, yamb_stream_t stream);
 int yamb_bn_bwd_apply_bwd(const yamb_bn_bwd_apply* args, yamb_stream_t stream);
 int yamb_se_pool_fwd(const yamb_se_pool* args, yamb_stream_t stream);
 
+/* ---- lightweight non-local block (AutoNL) -------------------------------------------------------
+ * Replaces the two einsums of Nonlocal.forward (reference models/mobilenet_base.py:158-173) and
+ * their autograd backward.  All tensors are NHWC bf16 [N][H*W][ld]; `sub` selects the row set:
+ * every pixel (sub = 1) or the pixels of l[:, :, ::sub, ::sub] (:161).
+ *   gram  : G[n][i][j] = alpha * sum_rows X[n,row,i] * Y[n,row,j]      i < I, j < J (fp32, overwritten)
+ *           forward  F = phi^T g  (X = Y = l, I = int(nl_c*C), J = C, rows = subsampled)
+ *           backward dF = (W/H) theta^T df  (X = l, Y = df, rows = all)
+ *   rowmat: out[n,row,o] = {base[n,row,o] | out[n,row,o] | 0} + alpha * sum_k X[n,row,k] * Mat[n](k,o)
+ *           with Mat[n](k,o) = Mat[n*mat_stride + k*sk + o*so], o < O; columns [O, O_copy) of
+ *           `base` are copied through.  forward f = (W/H) theta F; backward dtheta, dphi, dg.
+ * The reference's choice between (theta phi^T) g and theta (phi^T g) (:164-170) is a re-association
+ * of the same sum; the channel matrix is always formed first here. */
+typedef struct yamb_nl_gram {
+  int32_t N, H, W, sub;
+  const void* X; int64_t ldx; int32_t I;
+  const void* Y; int64_t ldy; int32_t J;   /* J, ldy even */
+  float alpha;
+  float* G;                                /* [N][I][J] */
+} yamb_nl_gram;
+
+typedef struct yamb_nl_rowmat {
+  int32_t N, H, W, sub;
+  const void* X; int64_t ldx; int32_t K;
+  const float* Mat; int64_t mat_stride, sk, so; int32_t O;   /* O even */
+  float alpha;
+  const void* base; int64_t ldb; int32_t O_copy;             /* NULL, or bf16 addend + pass-through */
+  int32_t accumulate;                                        /* 1: read-modify-write `out` */
+  void* out; int64_t ldo;
+} yamb_nl_rowmat;
+
+int yamb_nl_gram_fwd(const yamb_nl_gram* args, yamb_stream_t stream);
+int yamb_nl_rowmat_fwd(const yamb_nl_rowmat* args, yamb_stream_t stream);
+
 /* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
  * Replaces RMSprop.step (reference utils/rmsprop.py:67-129), the gradient of cal_l2_loss
  * (utils/optim.py:177-200; l2 * p added where bit 0 of wd_mask is set; bit 1 marks a parameter
@@ -267,7 +303,7 @@ int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
  * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply, 11 bn_stats,
- * 12 bn_bwd_apply) so bindings can self-check */
+ * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

@@ -59,7 +59,8 @@ def as_reference(model):
             m.forward = types.MethodType(_unfused_forward, m)
         elif hasattr(m, "project_conv") and hasattr(m, "depth_ops"):
             m.forward = types.MethodType(_fused_forward, m)
-    ref.forward = types.MethodType(_model_forward, ref)
+    if hasattr(ref, "features") and hasattr(ref, "classifier"):   # a whole network, not a block
+        ref.forward = types.MethodType(_model_forward, ref)
     return ref
 
 

@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "bn_finalize.cuh"
 #include "host_util.h"
 #include "prims.cuh"
@@ -743,20 +745,32 @@ static int check_common(int N, int H, int W, int C, int ldc, int k, int stride) 
 
 template <typename Kern, typename Dev>
 static cudaError_t launch_k(Kern kern, const Dev& p, size_t smem, long long tiles, cudaStream_t st) {
-  // attribute + occupancy are looked up once per (kernel, shared-memory size)
+  // The dynamic-smem limit of a kernel is process-wide state: only ever RAISE it (forward and
+  // backward run on different host threads); occupancy is cached per (kernel, smem size).
   struct Ent { const void* k; size_t smem; int per_sm; };
-  static thread_local Ent cache[96];
-  static thread_local int n_cache = 0;
+  static Ent cache[128];
+  static int n_cache = 0;
+  static std::mutex mu;
   int per_sm = 0;
-  for (int i = 0; i < n_cache; ++i)
-    if (cache[i].k == (const void*)kern && cache[i].smem == smem) per_sm = cache[i].per_sm;
-  if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    if (n_cache < 96) cache[n_cache++] = Ent{(const void*)kern, smem, per_sm};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t limit = 0;
+    for (int i = 0; i < n_cache; ++i)
+      if (cache[i].k == (const void*)kern) {
+        if (cache[i].smem > limit) limit = cache[i].smem;
+        if (cache[i].smem == smem) per_sm = cache[i].per_sm;
+      }
+    if (per_sm == 0) {
+      cudaError_t e;
+      if (smem > limit) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+      }
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+      if (n_cache < 128) cache[n_cache++] = Ent{(const void*)kern, smem, per_sm};
+    }
   }
   long long cap = (long long)max_ctas() * (per_sm > 4 ? 4 : per_sm);  // partials sized for 4/SM
   int grid = (int)(tiles < cap ? tiles : cap);

@@ -34,6 +34,8 @@ struct BnApplyDev {
   // optional per-(sample, channel) gate (SE): y *= gate[n][c], n = row / rows_per_sample
   const float* gate;
   long long rows_per_sample;
+  const __nv_bfloat16* residual2;
+  int ldr2;
 };
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __grid_constant__ BnApplyDev p) {
@@ -63,6 +65,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __grid_constant__ B
     if (p.residual) {
       float r[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + c0)), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    if (p.residual2) {
+      float r[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.residual2 + row * p.ldr2 + c0)), r);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
     }
@@ -415,6 +423,7 @@ int bn_apply_launch(const yamb_bn_apply* a, cudaStream_t st) {
   p.h = (const __nv_bfloat16*)a->h; p.scale = a->scale; p.shift = a->shift; p.act = a->act;
   p.residual = (const __nv_bfloat16*)a->residual; p.y = (__nv_bfloat16*)a->y;
   p.gate = a->gate; p.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
+  p.residual2 = (const __nv_bfloat16*)a->residual2; p.ldr2 = a->ldr2;
   const long long total = a->M * (a->C / 8);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)max_ctas() * 16;

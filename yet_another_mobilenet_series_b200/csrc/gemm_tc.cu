@@ -1216,7 +1216,7 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   cudaError_t e;
 #define YAMB_GEMM_LAUNCH(XF, EP, THREADS)                                                         \
   do {                                                                                           \
-    static thread_local int attr_smem = 0; /* per instantiation: raise the limit only when needed */ \
+    static int attr_smem = 0; /* per instantiation, process-wide: only ever RAISE the limit */     \
     if (attr_smem < smem_total) {                                                                \
       e = cudaFuncSetAttribute(gemm_tc_kernel<XF, EP>,                                           \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);         \

@@ -94,6 +94,7 @@ class BnApply(C.Structure):
         ("h", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int32),
         ("residual", C.c_void_p), ("y", C.c_void_p),
         ("gate", C.c_void_p), ("rows_per_sample", C.c_int64),
+        ("residual2", C.c_void_p), ("ldr2", C.c_int32),
     ]
 
 
@@ -168,12 +169,36 @@ class Rmsprop(C.Structure):
     ]
 
 
+class NlGram(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("sub", C.c_int32),
+        ("X", C.c_void_p), ("ldx", C.c_int64), ("I", C.c_int32),
+        ("Y", C.c_void_p), ("ldy", C.c_int64), ("J", C.c_int32),
+        ("alpha", C.c_float),
+        ("G", C.c_void_p),
+    ]
+
+
+class NlRowmat(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("sub", C.c_int32),
+        ("X", C.c_void_p), ("ldx", C.c_int64), ("K", C.c_int32),
+        ("Mat", C.c_void_p), ("mat_stride", C.c_int64), ("sk", C.c_int64), ("so", C.c_int64),
+        ("O", C.c_int32),
+        ("alpha", C.c_float),
+        ("base", C.c_void_p), ("ldb", C.c_int64), ("O_copy", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+    ]
+
+
 _STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
-            8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply, 11: BnStats, 12: BnBwdApply}
+            8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply, 11: BnStats, 12: BnBwdApply, 13: NlGram,
+            14: NlRowmat}
 
 # every symbol include/yamb200.h declares
 SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
-           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_nl_gram_fwd", "yamb_nl_rowmat_fwd", "yamb_rmsprop_step", "yamb_ema_update",
            "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
            "yamb_version"]
 _lib = None
@@ -208,6 +233,8 @@ def lib():
         l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
         l.yamb_se_bwd_reduce_bwd.argtypes = [C.POINTER(SeBwdReduce), C.c_void_p]
         l.yamb_se_bwd_apply_bwd.argtypes = [C.POINTER(SeBwdApply), C.c_void_p]
+        l.yamb_nl_gram_fwd.argtypes = [C.POINTER(NlGram), C.c_void_p]
+        l.yamb_nl_rowmat_fwd.argtypes = [C.POINTER(NlRowmat), C.c_void_p]
         l.yamb_rmsprop_step.argtypes = [C.POINTER(Rmsprop), C.c_void_p]
         l.yamb_ema_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_float,
                                       C.c_void_p]
