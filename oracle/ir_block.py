@@ -7,6 +7,7 @@ forward AND hand-derived backward:
   InvertedResidualChannelsFused.forward   /root/reference/models/mobilenet_base.py:330-342
   ConvBNReLU                              /root/reference/models/mobilenet_base.py:181-203
   SqueezeAndExcitation.forward            /root/reference/models/mobilenet_base.py:110-113
+  Nonlocal.forward                        /root/reference/models/mobilenet_base.py:158-173
   activations                             /root/reference/models/mobilenet_base.py:70-88, 461-469
 
 The arithmetic of the reference lives in PyTorch (torch.nn.functional conv2d / batch_norm,
@@ -72,7 +73,8 @@ def act_name(active_fn):
 
 
 BlockCfg = collections.namedtuple(
-    "BlockCfg", "inp oup stride channels kernel_sizes expand act eps momentum residual se_hidden")
+    "BlockCfg", "inp oup stride channels kernel_sizes expand act eps momentum residual se_hidden "
+                "nl_c nl_s", defaults=(0, 1))
 
 
 def extract(block):
@@ -108,11 +110,16 @@ def extract(block):
             P["se_br"] = se.se_reduce.bias.detach()
             P["se_we"] = se.se_expand.weight.detach().flatten(1)
             P["se_be"] = se.se_expand.bias.detach()
-        if type(block.nl_op).__name__ != "Identity":
-            raise NotImplementedError("Nonlocal is outside the oracle (SURVEY.md §7.1 step 7)")
+        nl = block.nl_op if type(block.nl_op).__name__ != "Identity" else None
+        if nl is not None:
+            if not isinstance(nl.bn, torch.nn.BatchNorm2d):
+                raise NotImplementedError("oracle: non-local block with a non-BatchNorm nl_norm")
+            P["w_nl"] = nl.depthwise_conv.weight.detach()[:, 0]
+            bn_pack("bn4", [nl.bn])
         bn_any = bn3
     else:
         se = None
+        nl = None
         if block.expand:
             P["w_exp"] = torch.cat([op[0][0].weight.detach().flatten(1) for op in block.ops])
             bn_pack("bn1", [op[0][1] for op in block.ops])
@@ -132,7 +139,8 @@ def extract(block):
                    channels=chans, kernel_sizes=ks, expand=bool(block.expand),
                    act=act_name(block.active_fn), eps=bn_any.eps, momentum=bn_any.momentum,
                    residual=bool(block.use_res_connect),
-                   se_hidden=(P["se_wr"].shape[0] if se is not None else 0))
+                   se_hidden=(P["se_wr"].shape[0] if se is not None else 0),
+                   nl_c=(nl.nl_c if nl is not None else 0), nl_s=(nl.nl_s if nl is not None else 1))
     return cfg, P
 
 
@@ -213,6 +221,20 @@ def forward(x, cfg, P, training=True, quant=False):
     h3 = _rnd(F.conv2d(a2, _rnd(P["w_proj"], q)[:, :, None, None]), q)
     S["h3"] = h3
     y = bn(h3, "bn3")
+    if cfg.nl_c > 0:
+        # Nonlocal.forward (:158-173).  The reference picks (theta phi^T) g or theta (phi^T g) by
+        # a MAC count (:164-170) — one sum, two association orders; the channel-matrix order is
+        # restated here (it is what the CUDA path always uses).
+        l = _rnd(y, q)                                   # BN3 output, materialised bf16
+        n_, C_, H_, W_ = l.shape
+        c, s_ = int(cfg.nl_c * C_), cfg.nl_s
+        lr = l[:, :, ::s_, ::s_]
+        Fm = torch.einsum("nihw,njhw->nij", lr[:, :c], lr)             # phi^T g, fp32
+        f = _rnd(torch.einsum("nij,nihw->njhw", Fm, l[:, :c]) / H_ * W_, q)   # sic: (f/H)*W, :171
+        hn_acc = F.conv2d(f, P["w_nl"][:, None], None, 1, 1, 1, C_)
+        hn = _rnd(hn_acc, q)
+        S.update(nl_l=l, nl_F=Fm, nl_f=f, nl_hn=hn)
+        y = bn(hn, "bn4", hn_acc) + l
     if cfg.residual:
         y = y + x
     y = _rnd(y, q)
@@ -244,6 +266,28 @@ def backward(dy, cfg, P, S, training=True, quant=False):
     G = {}
     dy = _rnd(dy, q)
     x = S["x"]
+    dy_in = dy                                           # what the skip connection carries back
+    if cfg.nl_c > 0:
+        # --- autograd of Nonlocal.forward: bn4 -> depthwise 3x3 -> the two products; `+ l` ---
+        l, Fm, f, hn = S["nl_l"], S["nl_F"], S["nl_f"], S["nl_hn"]
+        n_, C_, H_, W_ = l.shape
+        c, s_ = int(cfg.nl_c * C_), cfg.nl_s
+        sc = float(W_) / float(H_)
+        G["bn4_g"], G["bn4_b"], dhn = _bn_bwd(dy, hn, S["bn4_mean"], S["bn4_invstd"], P["bn4_g"],
+                                              training)
+        dhn = _rnd(dhn, q)                               # staged bf16 by the depthwise backward
+        df = _rnd(torch.nn.grad.conv2d_input(f.shape, P["w_nl"][:, None], dhn, 1, 1, 1, C_), q)
+        G["w_nl"] = torch.nn.grad.conv2d_weight(f, (C_, 1, 3, 3), dhn, 1, 1, 1, C_)[:, 0]
+        dF = torch.einsum("nihw,njhw->nij", l[:, :c], df) * sc
+        dl = dy.clone()
+        dl[:, :c] += torch.einsum("njhw,nij->nihw", df, Fm) * sc           # dtheta
+        dl = _rnd(dl, q)
+        lr = l[:, :, ::s_, ::s_]
+        dl[:, :c, ::s_, ::s_] = _rnd(dl[:, :c, ::s_, ::s_] +
+                                     torch.einsum("njhw,nij->nihw", lr, dF), q)        # dphi
+        dl[:, :, ::s_, ::s_] = _rnd(dl[:, :, ::s_, ::s_] +
+                                    torch.einsum("nihw,nij->njhw", lr[:, :c], dF), q)  # dg
+        dy = dl
     # --- BN3 (no activation) ---
     G["bn3_g"], G["bn3_b"], dh3 = _bn_bwd(dy, S["h3"], S["bn3_mean"], S["bn3_invstd"], P["bn3_g"],
                                           training)
@@ -302,5 +346,5 @@ def backward(dy, cfg, P, S, training=True, quant=False):
         nb = len(cfg.channels)
         dx = da1 if nb == 1 else sum(da1.chunk(nb, 1))
     if cfg.residual:
-        dx = dx + dy
+        dx = dx + dy_in
     return _rnd(dx, q), G

@@ -38,6 +38,75 @@ BLOCK_CASES = [
 ]
 
 
+NL_CASES = [
+    # non-local blocks (Nonlocal, models/mobilenet_base.py:131-178); "A"/"B" = the association
+    # order the reference's MAC test (:164-170) picks for that shape
+    ("nl_B_res", "InvertedResidualChannelsFused", (24, 24, 1, [72], [3], True), "nn.Swish",
+     {"se_ratio": 0.25, "nl_c": 0.25, "nl_s": 1}, (2, 24, 12, 12)),
+    ("nl_A_small_map", "InvertedResidualChannelsFused", (64, 64, 1, [128], [3], True), "nn.Swish",
+     {"nl_c": 0.25, "nl_s": 1}, (2, 64, 4, 4)),
+    ("nl_sub2_odd_map", "InvertedResidualChannelsFused", (40, 40, 1, [120], [5], True), "nn.Swish",
+     {"se_ratio": 0.25, "nl_c": 0.25, "nl_s": 2}, (2, 40, 7, 7)),
+    ("nl_s2_nores", "InvertedResidualChannelsFused", (16, 24, 2, [48], [5], True), "nn.ReLU6",
+     {"nl_c": 0.25, "nl_s": 2}, (2, 16, 12, 12)),
+]
+
+
+def _block_records(mb, cases, bnk):
+    blocks = {}
+    for name, cls, args, act, extra, xshape in cases:
+        torch.manual_seed(1995)
+        blk = getattr(mb, cls)(*args, active_fn=mb.get_active_fn(act), batch_norm_kwargs=bnk,
+                               **extra)
+        blk.apply(mb.init_weights_mnas)
+        g = torch.Generator().manual_seed(7)
+        for m in blk.modules():  # pattern of tests/models/mobilenet_base_test.py:7-10
+            if isinstance(m, torch.nn.BatchNorm2d):   # ZeroInitBN included: gamma != 0
+                m.weight.data.uniform_(0.5, 1.5, generator=g)
+                m.bias.data.normal_(0, 0.3, generator=g)
+                m.running_mean.normal_(0, 0.2, generator=g)
+                m.running_var.uniform_(0.5, 1.5, generator=g)
+        state0 = {k: v.clone() for k, v in blk.state_dict().items()}
+        x = torch.randn(*xshape, generator=g)
+        rec = {"cls": cls, "args": args, "act": act, "extra": extra, "bn": bnk, "state": state0,
+               "x": x}
+        for mode in ("train", "eval"):
+            blk.load_state_dict(state0)
+            blk.train(mode == "train")
+            blk.zero_grad()
+            xi = x.clone().requires_grad_(True)
+            y = blk(xi)
+            dy = torch.randn(y.shape, generator=g)
+            y.backward(dy)
+            rec[mode] = {
+                "y": y.detach().clone(), "dy": dy, "dx": xi.grad.clone(),
+                "grads": {k: p.grad.clone() for k, p in blk.named_parameters()},
+                "state_after": {k: v.clone() for k, v in blk.state_dict().items()},
+            }
+        blocks[name] = rec
+    return blocks
+
+
+def main_nl():
+    """tests/golden/blocks_nl.pt: non-local blocks.  Nonlocal.__init__ imports the reference's
+    FLAGS singleton (models/mobilenet_base.py:151), which parses sys.argv at import
+    (utils/config.py:216): give it the AutoNL yml."""
+    os.environ.setdefault("ARNOLD_OUTPUT", "/tmp/yamb_out")
+    os.environ.setdefault("DATA_LMDB", "/tmp/yamb_lmdb")
+    sys.argv = ["make_golden", "app:" + os.path.join(REF, "apps/searched/autonl/autonl_l.yml")]
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    import logging
+    import models.mobilenet_base as mb
+    logging.disable(logging.CRITICAL)
+    os.chdir(cwd)
+    warnings.simplefilter("ignore")
+    blocks = _block_records(mb, NL_CASES, {"momentum": 0.01, "eps": 1e-3})
+    torch.save(blocks, os.path.join(OUT, "blocks_nl.pt"))
+    print("blocks_nl.pt", os.path.getsize(os.path.join(OUT, "blocks_nl.pt")), "bytes")
+
+
 def main():
     sys.path.insert(0, REF)
     import models.mobilenet_base as mb
@@ -141,4 +210,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--nl" in sys.argv:          # separate process: FLAGS of the reference is a singleton
+        main_nl()
+    else:
+        main()

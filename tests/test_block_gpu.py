@@ -36,8 +36,11 @@ def _build(rec, dev):
 
 
 def _cases():
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blocks.pt")
-    return torch.load(path, weights_only=False)
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    rec = torch.load(os.path.join(d, "blocks.pt"), weights_only=False)
+    # non-local blocks (reference models/mobilenet_base.py:131-178), live-reference fixtures
+    rec.update(torch.load(os.path.join(d, "blocks_nl.pt"), weights_only=False))
+    return rec
 
 
 GOLD = _cases()
@@ -111,6 +114,11 @@ def test_block_vs_golden_and_oracle(built_lib, name, mode):
     assert _rel(torch.cat([d[1].bias.grad for d in dws]), G["bn2_b"]) < 1.5e-2
     assert _rel(bn3.weight.grad, G["bn3_g"]) < 1.5e-2
     assert _rel(bn3.bias.grad, G["bn3_b"]) < 1.5e-2
+    if "w_nl" in G:
+        nl = blk.nl_op
+        assert _rel(nl.depthwise_conv.weight.grad[:, 0], G["w_nl"]) < 1.5e-2
+        assert _rel(nl.bn.weight.grad, G["bn4_g"]) < 1.5e-2
+        assert _rel(nl.bn.bias.grad, G["bn4_b"]) < 1.5e-2
     if "se_wr" in G:
         se = blk.se_op
         assert _rel(se.se_reduce.weight.grad.flatten(1), G["se_wr"]) < 1.5e-2

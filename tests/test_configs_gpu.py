@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [("mobilenet_v2", 32), ("mobilenet_v2", 256), ("proxyless_mobile", 32), ("atomnas_c+", 32),
-         pytest.param("autonl_l", 32, marks=pytest.mark.xfail(reason="Nonlocal kernel lands later this round", strict=False))]
+         ("autonl_l", 32)]
 
 
 def _flat(d, keys):

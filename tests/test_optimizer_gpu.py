@@ -133,6 +133,7 @@ def test_stale_bf16_mirror_is_refreshed_after_inplace_weight_write(built_lib):
         want = other(x).float()
     assert float((y1 - want).abs().max()) == 0.0   # same kernels, same weights: bit-identical
     assert float((y1 - y0).abs().max()) > 1e-2     # and it really changed
+    opt.sync_mirror()                              # the BatchNorm / depthwise masters moved too
     assert opt.sync_mirror() == 0                  # nothing left stale
 
 

@@ -29,12 +29,13 @@ def _build(rec):
 
 CASES = ["v2_s2_relu", "v2_res_relu6", "v2_noexpand", "multi_k357", "fused_se_swish",
          "fused_s2_k5", "fused_plain"]
+NL_CASES = ["nl_B_res", "nl_A_small_map", "nl_sub2_odd_map", "nl_s2_nores"]
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + NL_CASES)
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_oracle_block_matches_reference(golden_dir, name, mode):
-    rec = _gold(golden_dir, "blocks.pt")[name]
+    rec = _gold(golden_dir, "blocks_nl.pt" if name in NL_CASES else "blocks.pt")[name]
     blk = _build(rec)
     cfg, P = ob.extract(blk)
     tr = mode == "train"
@@ -64,6 +65,9 @@ def test_oracle_block_matches_reference(golden_dir, name, mode):
                 tgt = {"se_wr": "se_op.se_reduce.weight", "se_br": "se_op.se_reduce.bias",
                        "se_we": "se_op.se_expand.weight", "se_be": "se_op.se_expand.bias"}[k]
                 got[tgt] = G[k]
+        if "w_nl" in G:   # non-local block: depthwise 3x3 + (ZeroInit)BN, :142-156
+            got["nl_op.depthwise_conv.weight"] = G["w_nl"]
+            got["nl_op.bn.weight"], got["nl_op.bn.bias"] = G["bn4_g"], G["bn4_b"]
     else:
         c0 = 0
         for i, c in enumerate(cfg.channels):
@@ -83,7 +87,10 @@ def test_oracle_block_matches_reference(golden_dir, name, mode):
     for k, g in got.items():
         assert _rel(g.reshape(gold["grads"][k].shape), gold["grads"][k]) < 2e-5, k
     if tr:  # running statistics after one training forward
-        for pfx, key in (("bn3", "pw_bn" if not fused else "project_conv.1"),):
+        pairs = [("bn3", "pw_bn" if not fused else "project_conv.1")]
+        if "w_nl" in G:
+            pairs.append(("bn4", "nl_op.bn"))
+        for pfx, key in pairs:
             rm, rv, _ = ob.bn_running_update(P[pfx + "_rm"], P[pfx + "_rv"], S[pfx + "_mean"],
                                              S[pfx + "_var"], S["count_out"], cfg.momentum, 0)
             assert _rel(rm, gold["state_after"][key + ".running_mean"]) < 1e-5

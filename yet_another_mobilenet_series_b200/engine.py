@@ -77,6 +77,10 @@ def join_side(dev=None):
             st["pending"] = False
 
 
+def lib_fn(name):
+    return getattr(nat.lib(), name)
+
+
 def act_code_of(active_fn):
     """Activation code of the reference's zero-arg activation factory (get_active_fn)."""
     m = active_fn() if callable(active_fn) and not isinstance(active_fn, torch.nn.Module) \
@@ -220,8 +224,7 @@ class BlockPlan:
             self.conv_proj = [block.project_conv[0]]
             bn3 = block.project_conv[1]
             self.se = block.se_op if type(block.se_op).__name__ != "Identity" else None
-            if type(block.nl_op).__name__ != "Identity":
-                raise nat.NativeError("Nonlocal is not yet on the sm_100a path")
+            self.nl = block.nl_op if type(block.nl_op).__name__ != "Identity" else None
         else:
             if self.expand:
                 self.conv_exp = [op[0][0] for op in block.ops]
@@ -235,6 +238,28 @@ class BlockPlan:
             bn3 = block.pw_bn
         if not self.fused:
             self.se = None
+            self.nl = None
+        if self.nl is not None:
+            # non-local block (reference models/mobilenet_base.py:131-178) between BN3 and the skip
+            nl = self.nl
+            if not isinstance(nl.bn, torch.nn.BatchNorm2d):
+                raise nat.NativeError("non-local block: only the BatchNorm nl_norm is on the "
+                                      "sm_100a path (got %s)" % type(nl.bn).__name__)
+            self.nl_cr = int(nl.nl_c * Cout)        # theta / phi channels (:163)
+            self.nl_sub = int(nl.nl_s)
+            if self.nl_cr <= 0 or self.nl_cr % 2 or self.nl_sub < 1:
+                raise nat.NativeError("non-local block: int(nl_c * C) must be a positive even "
+                                      "number (got %d)" % self.nl_cr)
+            self.nl_scale = float(self.Wo) / float(self.Ho)   # sic `f / H * W` (:171)
+            self.nl_l = torch.empty(self.M_out, Cout, device=dev, dtype=bf)
+            self.nl_f = torch.empty(self.M_out, Cout, device=dev, dtype=bf)
+            self.nl_h = torch.empty(self.M_out, Cout, device=dev, dtype=bf)
+            self.nl_F = _f32(N * self.nl_cr * Cout, dev)
+            self.nl_dF = None
+            self.nl_df = None
+            self.nl_dl = None
+            self.bn4 = _Bn([nl.bn], dev)
+            self.g_nl = torch.zeros_like(nl.depthwise_conv.weight, dtype=torch.float32)
         if self.se is not None:
             self.se_act = act_code_of(self.se.active_fn)
             self.pooled = _f32(N * Chid, dev).view(N, Chid)
@@ -459,11 +484,107 @@ class BlockPlan:
         a.h, a.scale, a.shift = self.h3.data_ptr(), self.bn3.scale.data_ptr(), \
             self.bn3.shift.data_ptr()
         a.act = 0
-        a.residual = xm.data_ptr() if self.residual else None
-        a.y = y.data_ptr()
-        self._call(lib.yamb_bn_apply_fwd, a, "bn_apply",
-                   2 * self.M_out * self.Cout * (3 if self.residual else 2))
+        if self.nl is None:
+            a.residual = xm.data_ptr() if self.residual else None
+            a.y = y.data_ptr()
+            self._call(lib.yamb_bn_apply_fwd, a, "bn_apply",
+                       2 * self.M_out * self.Cout * (3 if self.residual else 2))
+            return y
+        a.y = self.nl_l.data_ptr()              # l = BN3(h3): the non-local block's input
+        self._call(lib.yamb_bn_apply_fwd, a, "bn_apply", 4 * self.M_out * self.Cout)
+        self._nl_forward(xm, y)
         return y
+
+    # -- non-local block (reference models/mobilenet_base.py:158-173) ------------------------------
+    def _nl_gram(self, X, I, Y, sub, alpha, G, tag):
+        g = nat.NlGram()
+        g.N, g.H, g.W, g.sub = self.N, self.Ho, self.Wo, sub
+        g.X, g.ldx, g.I = X.data_ptr(), self.Cout, I
+        g.Y, g.ldy, g.J = Y.data_ptr(), self.Cout, self.Cout
+        g.alpha, g.G = alpha, G.data_ptr()
+        self._keep.append(g)
+        self._call(lib_fn("yamb_nl_gram_fwd"), g, tag, 4 * self.M_out * self.Cout // (sub * sub))
+
+    def _nl_rowmat(self, X, K, Mat, sk, so, O, sub, alpha, out, tag, base=None, accumulate=0):
+        r = nat.NlRowmat()
+        r.N, r.H, r.W, r.sub = self.N, self.Ho, self.Wo, sub
+        r.X, r.ldx, r.K = X.data_ptr(), self.Cout, K
+        r.Mat, r.mat_stride, r.sk, r.so, r.O = Mat.data_ptr(), self.nl_cr * self.Cout, sk, so, O
+        r.alpha = alpha
+        if base is not None:
+            r.base, r.ldb, r.O_copy = base.data_ptr(), self.Cout, self.Cout
+        r.accumulate = accumulate
+        r.out, r.ldo = out.data_ptr(), self.Cout
+        self._keep.append(r)
+        self._call(lib_fn("yamb_nl_rowmat_fwd"), r, tag, 4 * self.M_out * self.Cout // (sub * sub))
+
+    def _nl_forward(self, xm, y):
+        lib = self.lib
+        Cc, c = self.Cout, self.nl_cr
+        # F = phi^T g over the sub-sampled pixels; f = (W/H) theta F
+        self._nl_gram(self.nl_l, c, self.nl_l, self.nl_sub, 1.0, self.nl_F, "nl_gram")
+        self._nl_rowmat(self.nl_l, c, self.nl_F, Cc, 1, Cc, 1, self.nl_scale, self.nl_f, "nl_apply")
+        # depthwise 3x3 (no activation before it) + BN4 statistics
+        d = nat.DwFwd()
+        d.N, d.H, d.W, d.C, d.ldc, d.k, d.stride = self.N, self.Ho, self.Wo, Cc, Cc, 3, 1
+        d.x = self.nl_f.data_ptr()
+        d.w = self.nl.depthwise_conv.weight.data_ptr()
+        d.y = self.nl_h.data_ptr()
+        if self.bn4.batch_stats:
+            d.bn = C.pointer(self._bn_fwd_struct(self.bn4, self.M_out))
+        else:
+            self.bn4.eval_coeffs()
+        self._call(lib.yamb_depthwise_fwd, d, "nl_dw_fwd", 4 * Cc * self.M_out,
+                   2 * self.M_out * Cc * 9)
+        # y = BN4(h) + l (+ x)
+        a = nat.BnApply()
+        a.M, a.C = self.M_out, Cc
+        a.ldh = a.ldr = a.ldy = Cc
+        a.h, a.scale, a.shift = self.nl_h.data_ptr(), self.bn4.scale.data_ptr(), \
+            self.bn4.shift.data_ptr()
+        a.act = 0
+        a.residual = self.nl_l.data_ptr()
+        if self.residual:
+            a.residual2, a.ldr2 = xm.data_ptr(), Cc
+        a.y = y.data_ptr()
+        self._keep.append(a)
+        self._call(lib.yamb_bn_apply_fwd, a, "nl_bn_apply",
+                   2 * self.M_out * Cc * (4 if self.residual else 3))
+
+    def _nl_backward(self, dym, grads):
+        """dy -> dl (gradient of the BN3 output): BN4 backward, depthwise 3x3 backward, the two
+        products' backward, plus the `+ l` pass-through."""
+        lib = self.lib
+        Cc, c, bf = self.Cout, self.nl_cr, torch.bfloat16
+        if self.nl_df is None:
+            self.nl_df = torch.empty(self.M_out, Cc, device=self.dev, dtype=bf)
+            self.nl_dl = torch.empty(self.M_out, Cc, device=self.dev, dtype=bf)
+            self.nl_dF = _f32(self.N * c * Cc, self.dev)
+        r = nat.BnReduce()
+        r.M, r.C, r.lddy, r.ldh = self.M_out, Cc, Cc, Cc
+        r.dy, r.h = dym.data_ptr(), self.nl_h.data_ptr()
+        r.bn = C.pointer(self._bn_bwd_struct(self.bn4, self.M_out, grads["bn4"]))
+        self._call(lib.yamb_bn_reduce_bwd, r, "nl_bn_reduce", 4 * self.M_out * Cc)
+        d = nat.DwBwd()
+        d.N, d.H, d.W, d.C, d.ldc, d.k, d.stride = self.N, self.Ho, self.Wo, Cc, Cc, 3, 1
+        d.dz, d.h = dym.data_ptr(), self.nl_h.data_ptr()
+        d.ca, d.cb, d.cc = self.bn4.ca.data_ptr(), self.bn4.cb.data_ptr(), self.bn4.cc.data_ptr()
+        d.w = self.nl.depthwise_conv.weight.data_ptr()
+        d.dw = grads["nl_dw"].data_ptr()
+        d.x = self.nl_f.data_ptr()
+        d.dx = self.nl_df.data_ptr()
+        self._keep.append(d)
+        self._call(lib.yamb_depthwise_bwd, d, "nl_dw_bwd", 8 * Cc * self.M_out,
+                   4 * self.M_out * Cc * 9)
+        # dF = (W/H) theta^T df (all pixels);  dl = dy + [dtheta | 0];  sub-sampled rows += dphi, dg
+        self._nl_gram(self.nl_l, c, self.nl_df, 1, self.nl_scale, self.nl_dF, "nl_gram_bwd")
+        self._nl_rowmat(self.nl_df, Cc, self.nl_F, 1, Cc, c, 1, self.nl_scale, self.nl_dl,
+                        "nl_dtheta", base=dym)
+        self._nl_rowmat(self.nl_l, Cc, self.nl_dF, 1, Cc, c, self.nl_sub, 1.0, self.nl_dl,
+                        "nl_dphi", accumulate=1)
+        self._nl_rowmat(self.nl_l, c, self.nl_dF, Cc, 1, Cc, self.nl_sub, 1.0, self.nl_dl,
+                        "nl_dg", accumulate=1)
+        return self.nl_dl
 
     def _gemm_sliced_stats(self, g, bn, count):
         """Expand GEMM whose output channels belong to several BN modules: one GEMM per module
@@ -538,8 +659,11 @@ class BlockPlan:
                 self.dz1 = torch.empty(self.M_in, self.Chid, device=self.dev, dtype=bf)
         xm = x.permute(0, 2, 3, 1).reshape(self.M_in, self.Cin)
         dym = dy.permute(0, 2, 3, 1).reshape(self.M_out, self.Cout)
+        dym_skip = dym          # what the skip connection carries back to dx
         dx = torch.empty((self.N, self.Cin, self.H, self.W), device=self.dev, dtype=bf,
                          memory_format=torch.channels_last)
+        if self.nl is not None:
+            dym = self._nl_backward(dym, grads)
         # 1. BN3 backward reduction -> ca3, cb3, cc3, dgamma3, dbeta3
         r = nat.BnReduce()
         r.M, r.C, r.lddy, r.ldh = self.M_out, self.Cout, self.Cout, self.Cout
@@ -632,7 +756,7 @@ class BlockPlan:
             else:
                 d.x = xm.data_ptr()
                 d.dx = dx.data_ptr()
-                d.residual = dym.data_ptr() if self.residual else None
+                d.residual = dym_skip.data_ptr() if self.residual else None
             self._call(lib.yamb_depthwise_bwd, d, "dw_bwd", 4 * cb * (self.M_in + self.M_out),
                        4 * self.M_out * cb * k * k)
             c0 += cb
@@ -650,7 +774,7 @@ class BlockPlan:
         g.B, g.ldb, g.b_mn_major = self.w_exp_bf.data_ptr(), self.Cin, 1
         g.D, g.ldd = dx.data_ptr(), self.Cin
         if self.residual:
-            g.residual, g.ldr = dym.data_ptr(), self.Cout
+            g.residual, g.ldr = dym_skip.data_ptr(), self.Cout
         self._call(lib.yamb_pointwise_gemm, g, "pw_expand_dgrad",
                    2 * self.M_in * (2 * self.Chid + self.Cin * (2 if self.residual else 1)),
                    2 * self.M_in * self.Chid * self.Cin)
@@ -810,6 +934,9 @@ def run_backward(block, plan, x, dy):
         g["bn1"] = bn_targets(plan.bn1, "bn1")
         g["bn2"] = bn_targets(plan.bn2, "bn2")
         g["bn3"] = bn_targets(plan.bn3, "bn3")
+        if plan.nl is not None:
+            g["bn4"] = bn_targets(plan.bn4, "bn4")
+            g["nl_dw"] = target(plan.nl.depthwise_conv.weight, plan.g_nl)
         dx = plan.backward(x, dy, g)
         if not (DEFER_JOIN and direct and single_proj and (single_exp or not plan.expand)):
             join_side(plan.dev)   # the gradient hand-over below reads what the wgrads wrote
@@ -839,7 +966,10 @@ def run_backward(block, plan, x, dy):
         if not direct:
             for i, c in enumerate(plan.conv_dw):
                 gmap[id(c.weight)] = plan.g_dw[i]
-            for key, bn in (("bn1", plan.bn1), ("bn2", plan.bn2), ("bn3", plan.bn3)):
+            if plan.nl is not None:
+                gmap[id(plan.nl.depthwise_conv.weight)] = plan.g_nl
+            for key, bn in (("bn1", plan.bn1), ("bn2", plan.bn2), ("bn3", plan.bn3),
+                            ("bn4", getattr(plan, "bn4", None))):
                 if bn is None:
                     continue
                 for i, m in enumerate(bn.mods):

@@ -110,14 +110,26 @@ class ZeroInitBN(nn.BatchNorm2d):
 
 
 class Nonlocal(nn.Module):
-    """Lightweight non-local block (reference :131-178), plain torch ops: AutoNL is outside this
-    round's sm_100a scope but the module exists so its ymls build.
+    """Lightweight non-local block (reference :131-178): parameter holder with the reference's
+    module tree (`depthwise_conv`, `bn`).  Inside a fused block on CUDA its arithmetic runs in the
+    block's kernel sequence (engine.BlockPlan._nl_forward / _nl_backward: yamb_nl_gram,
+    yamb_nl_rowmat, the depthwise and BatchNorm kernels); this `forward` is the stand-alone
+    stock-torch statement of the same function (CPU, oracle, `as_reference`).
 
-    Unlike the reference it does not import a global FLAGS object: `nl_norm` is a keyword."""
+    `nl_norm`: the reference reads it from its global FLAGS inside the constructor (:151, "TODO:
+    as param").  Here it is a keyword; when the reference's `utils.config` is already loaded in
+    the process (its train.py imported this package through `model:`) and defines `nl_norm`, that
+    value is honoured exactly as the reference would."""
 
     def __init__(self, n_feature, nl_c, nl_s, batch_norm_kwargs=None, nl_norm=None):
         super().__init__()
         self.n_feature, self.nl_c, self.nl_s = n_feature, nl_c, nl_s
+        if nl_norm is None:
+            import sys
+            cfg = sys.modules.get("utils.config")     # never trigger its argv-parsing import
+            flags = getattr(cfg, "FLAGS", None) if cfg is not None else None
+            if flags is not None and hasattr(flags, "nl_norm"):
+                nl_norm = flags.nl_norm
         self.depthwise_conv = nn.Conv2d(n_feature, n_feature, 3, 1, 1, groups=n_feature,
                                         bias=False)
         kw = {} if batch_norm_kwargs is None else batch_norm_kwargs
