@@ -233,6 +233,32 @@ typedef struct yamb_se_bwd_apply {
   const yamb_bn_bwd* bn;
 } yamb_se_bwd_apply;
 
+/* The two fully connected layers of the SE branch on the pooled vectors (reference
+ * models/mobilenet_base.py:110-113 se_reduce / active_fn / se_expand / sigmoid) and their backward,
+ * fp32:  u = W_r s + b_r, v = act(u), gate = sigmoid(W_e v + b_e);
+ * backward: dt = dgate*gate*(1-gate), du = (W_e^T dt)*act'(u), dpool = (W_r^T du)*inv_hw, and the
+ * parameter gradients ACCUMULATED (+=) into g_* (sums over the N samples, no atomics). */
+typedef struct yamb_se_fc {
+  int32_t N, C, R; int32_t act;
+  const float* pooled;                     /* [N][C] */
+  const float* w_r; const float* b_r;      /* [R][C], [R]  (se_reduce) */
+  const float* w_e; const float* b_e;      /* [C][R], [C]  (se_expand) */
+  float* u; float* v;                      /* out [N][R]: saved for backward */
+  float* gate;                             /* out [N][C] */
+} yamb_se_fc;
+
+typedef struct yamb_se_fc_grad {
+  int32_t N, C, R; int32_t act; float inv_hw;
+  const float* dgate; const float* gate; const float* u; const float* v; const float* pooled;
+  const float* w_r; const float* w_e;
+  float* dpool;                            /* out [N][C] */
+  float* dt; float* du;                    /* scratch [N][C], [N][R] */
+  float* g_wr; float* g_br; float* g_we; float* g_be;
+} yamb_se_fc_grad;
+
+int yamb_se_fc_fwd(const yamb_se_fc* args, yamb_stream_t stream);
+int yamb_se_fc_bwd(const yamb_se_fc_grad* args, yamb_stream_t stream);
+
 int yamb_bn_apply_fwd(const yamb_bn_apply* args, yamb_stream_t stream);
 int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* args, yamb_stream_t stream);
 int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* args, yamb_stream_t stream);
@@ -303,7 +329,7 @@ int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
  * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply, 11 bn_stats,
- * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat) so bindings can self-check */
+ * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat, 15 se_fc, 16 se_fc_bwd) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

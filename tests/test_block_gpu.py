@@ -79,7 +79,11 @@ def test_block_vs_golden_and_oracle(built_lib, name, mode):
         for k, v in blk.state_dict().items():
             ref = gold["state_after"][k]
             if "running_" in k:
-                assert torch.allclose(v.cpu(), ref, rtol=5e-3, atol=2e-3), k
+                # non-local branch: f sums up to H'W' products per element, O(100) in magnitude;
+                # the bf16 rounding of f and of the depthwise output (2^-9 relative per element)
+                # is then percent-level on the variance the fp32 fixture holds
+                rt = 3e-2 if k.startswith("nl_op") else 5e-3
+                assert torch.allclose(v.cpu(), ref, rtol=rt, atol=2e-3), k
             elif "num_batches_tracked" in k:
                 assert int(v) == int(ref), k
     assert _rel(y, yo) < 3e-3

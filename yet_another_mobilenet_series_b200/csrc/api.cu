@@ -67,6 +67,8 @@ int yamb_struct_size(int which) {
     case 12: return (int)sizeof(yamb_bn_bwd_apply);
     case 13: return (int)sizeof(yamb_nl_gram);
     case 14: return (int)sizeof(yamb_nl_rowmat);
+    case 15: return (int)sizeof(yamb_se_fc);
+    case 16: return (int)sizeof(yamb_se_fc_grad);
     default: return -1;
   }
 }
@@ -86,6 +88,8 @@ int yamb_bn_bwd_apply_bwd(const yamb_bn_bwd_apply* a, yamb_stream_t s) { return 
 int yamb_se_pool_fwd(const yamb_se_pool* a, yamb_stream_t s) { return yamb::se_pool_launch(a, YAMB_ST(s)); }
 int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* a, yamb_stream_t s) { return yamb::se_bwd_reduce_launch(a, YAMB_ST(s)); }
 int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* a, yamb_stream_t s) { return yamb::se_bwd_apply_launch(a, YAMB_ST(s)); }
+int yamb_se_fc_fwd(const yamb_se_fc* a, yamb_stream_t s) { return yamb::se_fc_fwd_launch(a, YAMB_ST(s)); }
+int yamb_se_fc_bwd(const yamb_se_fc_grad* a, yamb_stream_t s) { return yamb::se_fc_bwd_launch(a, YAMB_ST(s)); }
 int yamb_nl_gram_fwd(const yamb_nl_gram* a, yamb_stream_t s) { return yamb::nl_gram_launch(a, YAMB_ST(s)); }
 int yamb_nl_rowmat_fwd(const yamb_nl_rowmat* a, yamb_stream_t s) { return yamb::nl_rowmat_launch(a, YAMB_ST(s)); }
 int yamb_rmsprop_step(const yamb_rmsprop* a, yamb_stream_t s) { return yamb::rmsprop_launch(a, YAMB_ST(s)); }

@@ -26,6 +26,8 @@ int bn_bwd_apply_launch(const yamb_bn_bwd_apply* a, cudaStream_t stream);
 int se_pool_launch(const yamb_se_pool* a, cudaStream_t stream);
 int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t stream);
 int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t stream);
+int se_fc_fwd_launch(const yamb_se_fc* a, cudaStream_t stream);
+int se_fc_bwd_launch(const yamb_se_fc_grad* a, cudaStream_t stream);
 int nl_gram_launch(const yamb_nl_gram* a, cudaStream_t stream);
 int nl_rowmat_launch(const yamb_nl_rowmat* a, cudaStream_t stream);
 int rmsprop_launch(const yamb_rmsprop* a, cudaStream_t stream);

@@ -1,0 +1,142 @@
+// Squeeze-and-Excitation fully connected layers on the pooled [N, C] vectors, sm_100a.
+//
+// Replaces, behind yamb_se_fc_fwd / yamb_se_fc_bwd (include/yamb200.h), the two 1x1 convolutions
+// on [N, C, 1, 1] of SqueezeAndExcitation.forward and the sigmoid
+// (reference models/mobilenet_base.py:110-113: se_reduce -> active_fn -> se_expand -> sigmoid) and
+// their autograd backward, which round 1 left to ~12 ATen/cuBLAS launches per SE block:
+//   forward : u = W_r s + b_r ;  v = act(u) ;  gate = sigmoid(W_e v + b_e)
+//   backward: dt = dgate*gate*(1-gate) ;  du = (W_e^T dt) * act'(u) ;  dpool = (W_r^T du) / HW ;
+//             dW_e += dt^T v, db_e += sum dt, dW_r += du^T s, db_r += sum du   (sums over samples)
+// fp32 throughout (the reference keeps these tiny layers in fp32 too).  One CTA per sample for
+// the per-sample chain; the parameter gradients are owned one-output-per-thread (no atomics:
+// deterministic).  C <= 4096, R <= 1024.
+#include <cuda_runtime.h>
+
+#include "host_util.h"
+#include "prims.cuh"
+
+namespace yamb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) se_fc_fwd_kernel(const __grid_constant__ yamb_se_fc a) {
+  extern __shared__ float sf[];
+  float* s_s = sf;            // [C] pooled row
+  float* s_v = sf + a.C;      // [R]
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < a.C; c += 256) s_s[c] = a.pooled[(size_t)n * a.C + c];
+  __syncthreads();
+  for (int j = warp; j < a.R; j += 8) {          // one warp per squeeze unit: coalesced W_r row
+    const float* w = a.w_r + (size_t)j * a.C;
+    float acc = 0.f;
+    for (int c = lane; c < a.C; c += 32) acc = fmaf(w[c], s_s[c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float u = acc + a.b_r[j];
+      const float v = act_fwd(u, a.act);
+      a.u[(size_t)n * a.R + j] = u;
+      a.v[(size_t)n * a.R + j] = v;
+      s_v[j] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += 256) {
+    const float* w = a.w_e + (size_t)c * a.R;
+    float acc = a.b_e[c];
+    for (int j = 0; j < a.R; ++j) acc = fmaf(w[j], s_v[j], acc);
+    a.gate[(size_t)n * a.C + c] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+// per-sample chain of the backward
+__global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_constant__ yamb_se_fc_grad a) {
+  extern __shared__ float sf[];
+  float* s_dt = sf;           // [C]
+  float* s_du = sf + a.C;     // [R]
+  const int n = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < a.C; c += 256) {
+    const float g = a.gate[(size_t)n * a.C + c];
+    const float dt = a.dgate[(size_t)n * a.C + c] * g * (1.f - g);
+    s_dt[c] = dt;
+    a.dt[(size_t)n * a.C + c] = dt;
+  }
+  __syncthreads();
+  for (int j = tid; j < a.R; j += 256) {         // consecutive threads: consecutive W_e columns
+    float acc = 0.f;
+    for (int c = 0; c < a.C; ++c) acc = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], acc);
+    const float du = acc * act_bwd(a.u[(size_t)n * a.R + j], a.act);
+    s_du[j] = du;
+    a.du[(size_t)n * a.R + j] = du;
+  }
+  __syncthreads();
+  for (int c = tid; c < a.C; c += 256) {
+    float acc = 0.f;
+    for (int j = 0; j < a.R; ++j) acc = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], acc);
+    a.dpool[(size_t)n * a.C + c] = acc * a.inv_hw;
+  }
+}
+
+// parameter gradients: thread (c, j) owns dW_e[c][j] and dW_r[j][c]; the bias sums ride along
+__global__ void __launch_bounds__(256) se_fc_bwd_param_kernel(const __grid_constant__ yamb_se_fc_grad a) {
+  const long long total = (long long)a.C * a.R;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total;
+       i += (long long)gridDim.x * 256) {
+    const int c = (int)(i / a.R), j = (int)(i % a.R);
+    float we = 0.f, wr = 0.f, be = 0.f, br = 0.f;
+    for (int n = 0; n < a.N; ++n) {
+      const float dt = a.dt[(size_t)n * a.C + c], du = a.du[(size_t)n * a.R + j];
+      we = fmaf(dt, a.v[(size_t)n * a.R + j], we);
+      wr = fmaf(du, a.pooled[(size_t)n * a.C + c], wr);
+      be += dt;
+      br += du;
+    }
+    a.g_we[(size_t)c * a.R + j] += we;
+    a.g_wr[(size_t)j * a.C + c] += wr;
+    if (j == 0) a.g_be[c] += be;
+    if (c == 0) a.g_br[j] += br;
+  }
+}
+
+static int se_fc_check(int N, int C, int R) {
+  if (N <= 0 || C <= 0 || R <= 0 || C > 4096 || R > 1024)
+    return set_error(YAMB_EINVAL, "se_fc: N=%d C=%d R=%d", N, C, R);
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  return 0;
+}
+
+int se_fc_fwd_launch(const yamb_se_fc* a, cudaStream_t st) {
+  if (!a) return set_error(YAMB_EINVAL, "null args");
+  int rc = se_fc_check(a->N, a->C, a->R);
+  if (rc) return rc;
+  if (!a->pooled || !a->w_r || !a->b_r || !a->w_e || !a->b_e || !a->u || !a->v || !a->gate)
+    return set_error(YAMB_EINVAL, "se_fc: null pointer");
+  se_fc_fwd_kernel<<<a->N, 256, (a->C + a->R) * sizeof(float), st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_fc fwd: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int se_fc_bwd_launch(const yamb_se_fc_grad* a, cudaStream_t st) {
+  if (!a) return set_error(YAMB_EINVAL, "null args");
+  int rc = se_fc_check(a->N, a->C, a->R);
+  if (rc) return rc;
+  if (!a->dgate || !a->gate || !a->u || !a->v || !a->pooled || !a->w_r || !a->w_e || !a->dpool ||
+      !a->dt || !a->du || !a->g_wr || !a->g_br || !a->g_we || !a->g_be)
+    return set_error(YAMB_EINVAL, "se_fc bwd: null pointer");
+  se_fc_bwd_sample_kernel<<<a->N, 256, (a->C + a->R) * sizeof(float), st>>>(*a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_fc bwd: %s", cudaGetErrorString(e));
+  const long long total = (long long)a->C * a->R;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)max_ctas() * 8;
+  se_fc_bwd_param_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(*a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_fc bwd params: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace yamb

@@ -262,6 +262,14 @@ class BlockPlan:
             self.g_nl = torch.zeros_like(nl.depthwise_conv.weight, dtype=torch.float32)
         if self.se is not None:
             self.se_act = act_code_of(self.se.active_fn)
+            self.se_r = self.se.se_reduce.weight.shape[0]
+            self.se_u = _f32(N * self.se_r, dev).view(N, self.se_r)
+            self.se_v = _f32(N * self.se_r, dev).view(N, self.se_r)
+            self.se_du = _f32(N * self.se_r, dev).view(N, self.se_r)
+            self.se_dt = _f32(N * Chid, dev).view(N, Chid)
+            self.g_se = {k: torch.zeros_like(t, dtype=torch.float32) for k, t in (
+                ("wr", self.se.se_reduce.weight), ("br", self.se.se_reduce.bias),
+                ("we", self.se.se_expand.weight), ("be", self.se.se_expand.bias))}
             self.pooled = _f32(N * Chid, dev).view(N, Chid)
             self.gate = _f32(N * Chid, dev).view(N, Chid)
             self.dgate = _f32(N * Chid, dev).view(N, Chid)
@@ -443,8 +451,8 @@ class BlockPlan:
                        2 * self.M_out * cb * k * k)
             c0 += cb
         # 2b. Squeeze-and-Excitation gate (reference mobilenet_base.py:110-113): spatial mean of
-        #     a2 = act(bn2(h2)) by a kernel, the two tiny FCs on [N, C] by torch, gate applied
-        #     inside the project GEMM's operand transform
+        #     a2 = act(bn2(h2)) by a kernel, the two fully connected layers + sigmoid by another,
+        #     the gate applied inside the project GEMM's operand transform
         if self.se is not None:
             sp = nat.SePool()
             sp.N, sp.HW, sp.C, sp.ldh = self.N, self.Ho * self.Wo, self.Chid, self.Chid
@@ -453,13 +461,17 @@ class BlockPlan:
             sp.pooled = self.pooled.data_ptr()
             self._call(lib.yamb_se_pool_fwd, sp, "se_pool", 2 * self.M_out * self.Chid)
             se = self.se
-            # the two [N, C] fully connected layers stay fp32 even under the caller's autocast
-            with torch.no_grad(), torch.autocast("cuda", enabled=False):
-                self.se_u = torch.addmm(se.se_reduce.bias, self.pooled,
-                                        se.se_reduce.weight.flatten(1).t())
-                self.se_v = _torch_act(self.se_u, self.se_act)
-                t = torch.addmm(se.se_expand.bias, self.se_v, se.se_expand.weight.flatten(1).t())
-                torch.sigmoid(t, out=self.gate)
+            # the two fully connected layers on the pooled [N, C] vectors (fp32, like the reference
+            # keeps them) + sigmoid: one launch (csrc/se_fc.cu)
+            f = nat.SeFc()
+            f.N, f.C, f.R, f.act = self.N, self.Chid, self.se_r, self.se_act
+            f.pooled = self.pooled.data_ptr()
+            f.w_r, f.b_r = se.se_reduce.weight.data_ptr(), se.se_reduce.bias.data_ptr()
+            f.w_e, f.b_e = se.se_expand.weight.data_ptr(), se.se_expand.bias.data_ptr()
+            f.u, f.v, f.gate = self.se_u.data_ptr(), self.se_v.data_ptr(), self.gate.data_ptr()
+            self._keep.append(f)
+            self._call(lib.yamb_se_fc_fwd, f, "se_fc", 4 * self.N * self.Chid * 2,
+                       4 * self.N * self.Chid * self.se_r)
         # 3. project 1x1 (BN2+act as operand transform) + BN3 statistics
         g = nat.Gemm()
         g.M, g.N, g.K = self.M_out, self.Cout, self.Chid
@@ -601,7 +613,8 @@ class BlockPlan:
                        2 * gs.M * gs.K * cb)
 
     def _se_backward(self, grads):
-        """SE backward: dgate by a reduction kernel, the two tiny FCs by torch, then
+        """SE backward: dgate by a reduction kernel, the backward of the two fully connected layers
+        (+ their parameter gradients) by yamb_se_fc_bwd, then
         dz2 = (d(a2*gate)*gate + dpool) * act'(z2) with the BN2-backward statistics."""
         lib = self.lib
         se = self.se
@@ -612,23 +625,17 @@ class BlockPlan:
         r.scale, r.shift, r.act = self.bn2.scale.data_ptr(), self.bn2.shift.data_ptr(), self.act
         r.dgate = self.dgate.data_ptr()
         self._call(lib.yamb_se_bwd_reduce_bwd, r, "se_bwd_reduce", 4 * self.M_out * self.Chid)
-        with torch.no_grad(), torch.autocast("cuda", enabled=False):
-            gate = self.gate
-            dt = self.dgate * gate * (1 - gate)
-            we = se.se_expand.weight.flatten(1)          # [C, r]
-            wr = se.se_reduce.weight.flatten(1)          # [r, C]
-            g_we = dt.t() @ self.se_v
-            g_be = dt.sum(0)
-            du = (dt @ we) * _torch_act_grad(self.se_u, self.se_act)
-            g_wr = du.t() @ self.pooled
-            g_br = du.sum(0)
-            torch.mul(du @ wr, 1.0 / HW, out=self.dpool)
-            grads["se"] = {
-                id(se.se_expand.weight): g_we.view_as(se.se_expand.weight),
-                id(se.se_expand.bias): g_be,
-                id(se.se_reduce.weight): g_wr.view_as(se.se_reduce.weight),
-                id(se.se_reduce.bias): g_br,
-            }
+        b = nat.SeFcBwd()
+        b.N, b.C, b.R, b.act, b.inv_hw = self.N, self.Chid, self.se_r, self.se_act, 1.0 / HW
+        b.dgate, b.gate = self.dgate.data_ptr(), self.gate.data_ptr()
+        b.u, b.v, b.pooled = self.se_u.data_ptr(), self.se_v.data_ptr(), self.pooled.data_ptr()
+        b.w_r, b.w_e = se.se_reduce.weight.data_ptr(), se.se_expand.weight.data_ptr()
+        b.dpool, b.dt, b.du = self.dpool.data_ptr(), self.se_dt.data_ptr(), self.se_du.data_ptr()
+        tg = grads["se"]
+        b.g_wr, b.g_br, b.g_we, b.g_be = (tg[k].data_ptr() for k in ("wr", "br", "we", "be"))
+        self._keep.append(b)
+        self._call(lib.yamb_se_fc_bwd, b, "se_fc_bwd", 4 * self.N * self.Chid * 4,
+                   8 * self.N * self.Chid * self.se_r)
         for (c0, cb) in self.bn2.slices:
             a = nat.SeBwdApply()
             a.M, a.C, a.ldd, a.ldh, a.ldz = self.M_out, cb, self.Chid, self.Chid, self.Chid
@@ -809,32 +816,6 @@ def _bf16_operand(w, own, shape):
     return mirror.view(shape)
 
 
-def _torch_act(z, code):
-    if code == 1:
-        return torch.relu(z)
-    if code == 2:
-        return torch.clamp(z, 0.0, 6.0)
-    if code == 3:
-        return z * torch.sigmoid(z)
-    if code == 4:
-        return z * torch.clamp(z + 3.0, 0.0, 6.0) / 6.0
-    return z
-
-
-def _torch_act_grad(z, code):
-    if code == 1:
-        return (z > 0).to(z.dtype)
-    if code == 2:
-        return ((z > 0) & (z < 6)).to(z.dtype)
-    if code == 3:
-        sg = torch.sigmoid(z)
-        return sg * (1 + z * (1 - sg))
-    if code == 4:
-        return torch.where(z <= -3, torch.zeros_like(z),
-                           torch.where(z >= 3, torch.ones_like(z), (2 * z + 3) / 6))
-    return torch.ones_like(z)
-
-
 def _plan_for(block, x):
     plans = block.__dict__.setdefault("_yamb_plans", {})
     key = (tuple(x.shape), x.device.index)
@@ -934,6 +915,12 @@ def run_backward(block, plan, x, dy):
         g["bn1"] = bn_targets(plan.bn1, "bn1")
         g["bn2"] = bn_targets(plan.bn2, "bn2")
         g["bn3"] = bn_targets(plan.bn3, "bn3")
+        if plan.se is not None:
+            se = plan.se
+            g["se"] = {"wr": target(se.se_reduce.weight, plan.g_se["wr"]),
+                       "br": target(se.se_reduce.bias, plan.g_se["br"]),
+                       "we": target(se.se_expand.weight, plan.g_se["we"]),
+                       "be": target(se.se_expand.bias, plan.g_se["be"])}
         if plan.nl is not None:
             g["bn4"] = bn_targets(plan.bn4, "bn4")
             g["nl_dw"] = target(plan.nl.depthwise_conv.weight, plan.g_nl)
@@ -976,12 +963,11 @@ def run_backward(block, plan, x, dy):
                     dg, db = g[key][i]
                     gmap[id(m.weight)] = dg
                     gmap[id(m.bias)] = db
-        for pid, t in g.get("se", {}).items():
-            if direct:
-                pmap = {id(p): p for p in params}
-                pmap[pid].grad.add_(t)
-            else:
-                gmap[pid] = t
+        if plan.se is not None and not direct:
+            se = plan.se
+            for k, prm in (("wr", se.se_reduce.weight), ("br", se.se_reduce.bias),
+                           ("we", se.se_expand.weight), ("be", se.se_expand.bias)):
+                gmap[id(prm)] = plan.g_se[k]
         return dx, gmap
 
 

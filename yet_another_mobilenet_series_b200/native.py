@@ -171,6 +171,26 @@ class Rmsprop(C.Structure):
     ]
 
 
+class SeFc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("C", C.c_int32), ("R", C.c_int32), ("act", C.c_int32),
+        ("pooled", C.c_void_p),
+        ("w_r", C.c_void_p), ("b_r", C.c_void_p), ("w_e", C.c_void_p), ("b_e", C.c_void_p),
+        ("u", C.c_void_p), ("v", C.c_void_p), ("gate", C.c_void_p),
+    ]
+
+
+class SeFcBwd(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("C", C.c_int32), ("R", C.c_int32), ("act", C.c_int32),
+        ("inv_hw", C.c_float),
+        ("dgate", C.c_void_p), ("gate", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+        ("pooled", C.c_void_p), ("w_r", C.c_void_p), ("w_e", C.c_void_p),
+        ("dpool", C.c_void_p), ("dt", C.c_void_p), ("du", C.c_void_p),
+        ("g_wr", C.c_void_p), ("g_br", C.c_void_p), ("g_we", C.c_void_p), ("g_be", C.c_void_p),
+    ]
+
+
 class NlGram(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("sub", C.c_int32),
@@ -196,11 +216,11 @@ class NlRowmat(C.Structure):
 
 _STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
             8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply, 11: BnStats, 12: BnBwdApply, 13: NlGram,
-            14: NlRowmat}
+            14: NlRowmat, 15: SeFc, 16: SeFcBwd}
 
 # every symbol include/yamb200.h declares
 SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
-           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_nl_gram_fwd", "yamb_nl_rowmat_fwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_nl_gram_fwd", "yamb_nl_rowmat_fwd", "yamb_se_fc_fwd", "yamb_se_fc_bwd", "yamb_rmsprop_step", "yamb_ema_update",
            "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
            "yamb_version"]
 _lib = None
@@ -235,6 +255,8 @@ def lib():
         l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
         l.yamb_se_bwd_reduce_bwd.argtypes = [C.POINTER(SeBwdReduce), C.c_void_p]
         l.yamb_se_bwd_apply_bwd.argtypes = [C.POINTER(SeBwdApply), C.c_void_p]
+        l.yamb_se_fc_fwd.argtypes = [C.POINTER(SeFc), C.c_void_p]
+        l.yamb_se_fc_bwd.argtypes = [C.POINTER(SeFcBwd), C.c_void_p]
         l.yamb_nl_gram_fwd.argtypes = [C.POINTER(NlGram), C.c_void_p]
         l.yamb_nl_rowmat_fwd.argtypes = [C.POINTER(NlRowmat), C.c_void_p]
         l.yamb_rmsprop_step.argtypes = [C.POINTER(Rmsprop), C.c_void_p]
