@@ -300,6 +300,56 @@ typedef struct yamb_nl_rowmat {
 int yamb_nl_gram_fwd(const yamb_nl_gram* args, yamb_stream_t stream);
 int yamb_nl_rowmat_fwd(const yamb_nl_rowmat* args, yamb_stream_t stream);
 
+/* ---- stem convolution -----------------------------------------------------------------------------
+ * 3x3, stride 2, pad 1, 3 input channels -> Cout (multiple of 8, <= 64) on NHWC bf16: the first
+ * layer of the network (reference models/mobilenet_supernet.py:124-130; its BatchNorm + activation
+ * follow through yamb_bn_stats_fwd / yamb_bn_apply_fwd).  Weights fp32 in the parameter's own
+ * [Cout][3][3][3] layout.  fwd writes y; wgrad ACCUMULATES dw += sum dh * x (no input gradient). */
+typedef struct yamb_stem_conv {
+  int32_t N, H, W, Cout;
+  const void* x;        /* bf16 [N][H][W][3] */
+  const float* w;       /* [Cout][3][3][3]            (fwd) */
+  void* y;              /* bf16 [N][Ho][Wo][Cout]     (fwd) */
+  const void* dh;       /* bf16 [N][Ho][Wo][Cout]     (wgrad) */
+  float* dw;            /* [Cout][3][3][3] +=         (wgrad) */
+} yamb_stem_conv;
+
+int yamb_stem_conv_fwd(const yamb_stem_conv* args, yamb_stream_t stream);
+int yamb_stem_conv_wgrad(const yamb_stem_conv* args, yamb_stream_t stream);
+
+/* ---- label-smoothed softmax cross entropy + top-k -------------------------------------------------
+ * Replaces CrossEntropyLabelSmooth(reduction='none') (reference utils/optim.py:150-158), the
+ * top-1 / top-5 `correct_k` bookkeeping of forward_loss (common.py:73-79) and their backward.
+ *   forward : loss[n] = sum_c -t[n][c] log_softmax(logits)[n][c], t = (1-eps) onehot + eps/C;
+ *             correct1/5[n] in {0,1} (ties like torch.topk: lower index wins);
+ *             G[n][c] = softmax - t (bf16), what the backward needs
+ *   backward: dlogits[n][c] = G[n][c] * dloss[n];  dbias[c] += sum_n dlogits[n][c] (classifier
+ *             bias gradient, optional) */
+typedef struct yamb_softmax_ce {
+  int32_t N, C; int64_t ld;
+  const void* logits;          /* bf16 [N][ld] */
+  const int64_t* target;       /* [N] */
+  float smoothing;
+  float* loss;                 /* [N] */
+  float* correct1; float* correct5;   /* [N] or NULL */
+  void* G; int64_t ldg;        /* bf16 [N][ldg] or NULL (no backward wanted) */
+} yamb_softmax_ce;
+
+typedef struct yamb_softmax_ce_grad {
+  int32_t N, C;
+  const void* G; int64_t ldg;
+  const float* dloss;          /* [N] */
+  void* dlogits; int64_t ldd;  /* bf16 [N][ldd] */
+  float* dbias;                /* [C] += or NULL */
+} yamb_softmax_ce_grad;
+
+int yamb_softmax_ce_fwd(const yamb_softmax_ce* args, yamb_stream_t stream);
+int yamb_softmax_ce_bwd(const yamb_softmax_ce_grad* args, yamb_stream_t stream);
+/* out[c] += sum_rows X[row][c] over a bf16 [M][ld] matrix (bias gradient of the classifier,
+ * reference models/mobilenet_supernet.py:163-167) */
+int yamb_colsum_bf16(const void* X, int64_t M, int32_t C, int64_t ld, float* out,
+                     yamb_stream_t stream);
+
 /* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
  * Replaces RMSprop.step (reference utils/rmsprop.py:67-129), the gradient of cal_l2_loss
  * (utils/optim.py:177-200; l2 * p added where bit 0 of wd_mask is set; bit 1 marks a parameter
@@ -329,7 +379,8 @@ int yamb_max_ctas(void);
 
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
  * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply, 11 bn_stats,
- * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat, 15 se_fc, 16 se_fc_bwd) so bindings can self-check */
+ * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat, 15 se_fc, 16 se_fc_grad, 17 softmax_ce,
+ * 18 softmax_ce_grad, 19 stem_conv) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

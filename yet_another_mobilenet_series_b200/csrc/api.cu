@@ -69,6 +69,9 @@ int yamb_struct_size(int which) {
     case 14: return (int)sizeof(yamb_nl_rowmat);
     case 15: return (int)sizeof(yamb_se_fc);
     case 16: return (int)sizeof(yamb_se_fc_grad);
+    case 17: return (int)sizeof(yamb_softmax_ce);
+    case 18: return (int)sizeof(yamb_softmax_ce_grad);
+    case 19: return (int)sizeof(yamb_stem_conv);
     default: return -1;
   }
 }
@@ -90,6 +93,13 @@ int yamb_se_bwd_reduce_bwd(const yamb_se_bwd_reduce* a, yamb_stream_t s) { retur
 int yamb_se_bwd_apply_bwd(const yamb_se_bwd_apply* a, yamb_stream_t s) { return yamb::se_bwd_apply_launch(a, YAMB_ST(s)); }
 int yamb_se_fc_fwd(const yamb_se_fc* a, yamb_stream_t s) { return yamb::se_fc_fwd_launch(a, YAMB_ST(s)); }
 int yamb_se_fc_bwd(const yamb_se_fc_grad* a, yamb_stream_t s) { return yamb::se_fc_bwd_launch(a, YAMB_ST(s)); }
+int yamb_softmax_ce_fwd(const yamb_softmax_ce* a, yamb_stream_t s) { return yamb::softmax_ce_fwd_launch(a, YAMB_ST(s)); }
+int yamb_softmax_ce_bwd(const yamb_softmax_ce_grad* a, yamb_stream_t s) { return yamb::softmax_ce_bwd_launch(a, YAMB_ST(s)); }
+int yamb_colsum_bf16(const void* X, int64_t M, int32_t C, int64_t ld, float* out, yamb_stream_t s) {
+  return yamb::colsum_bf16_launch(X, M, C, ld, out, YAMB_ST(s));
+}
+int yamb_stem_conv_fwd(const yamb_stem_conv* a, yamb_stream_t s) { return yamb::stem_conv_fwd_launch(a, YAMB_ST(s)); }
+int yamb_stem_conv_wgrad(const yamb_stem_conv* a, yamb_stream_t s) { return yamb::stem_conv_wgrad_launch(a, YAMB_ST(s)); }
 int yamb_nl_gram_fwd(const yamb_nl_gram* a, yamb_stream_t s) { return yamb::nl_gram_launch(a, YAMB_ST(s)); }
 int yamb_nl_rowmat_fwd(const yamb_nl_rowmat* a, yamb_stream_t s) { return yamb::nl_rowmat_launch(a, YAMB_ST(s)); }
 int yamb_rmsprop_step(const yamb_rmsprop* a, yamb_stream_t s) { return yamb::rmsprop_launch(a, YAMB_ST(s)); }

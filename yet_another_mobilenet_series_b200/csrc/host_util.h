@@ -28,6 +28,12 @@ int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t stream);
 int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t stream);
 int se_fc_fwd_launch(const yamb_se_fc* a, cudaStream_t stream);
 int se_fc_bwd_launch(const yamb_se_fc_grad* a, cudaStream_t stream);
+int softmax_ce_fwd_launch(const yamb_softmax_ce* a, cudaStream_t stream);
+int softmax_ce_bwd_launch(const yamb_softmax_ce_grad* a, cudaStream_t stream);
+int colsum_bf16_launch(const void* X, long long M, int C, long long ld, float* out,
+                       cudaStream_t stream);
+int stem_conv_fwd_launch(const yamb_stem_conv* a, cudaStream_t stream);
+int stem_conv_wgrad_launch(const yamb_stem_conv* a, cudaStream_t stream);
 int nl_gram_launch(const yamb_nl_gram* a, cudaStream_t stream);
 int nl_rowmat_launch(const yamb_nl_rowmat* a, cudaStream_t stream);
 int rmsprop_launch(const yamb_rmsprop* a, cudaStream_t stream);

@@ -171,10 +171,17 @@ class ConvBNReLU(nn.Sequential):
             active_fn())
 
     def forward(self, x):
-        # CUDA: the convolution stays a library call (stem/head are "next"), its
-        # BatchNorm + activation run on this repo's kernels (torch's channels_last BatchNorm
-        # kernels were 3 ms of a 21 ms step).  CPU / odd widths: the plain torch modules.
+        # CUDA: a 1x1 convolution (the head 320 -> 1280) is the blocks' tcgen05 GEMM with the
+        # BatchNorm statistics in its epilogue (tail_ops.pw_conv_bn_act); the 3x3 stride-2 stem
+        # runs the direct kernels of tail_ops.stem_conv_bn_act; any other convolution stays a
+        # library call with BatchNorm + activation on this repo's kernels.  CPU / odd widths: the
+        # plain torch modules.
         conv, bn, act = self[0], self[1], self[2]
+        from . import tail_ops
+        if tail_ops.pw_conv_supported(self, x):
+            return tail_ops.pw_conv_bn_act(self, x)
+        if tail_ops.stem_supported(self, x):
+            return tail_ops.stem_conv_bn_act(self, x)
         if (x.is_cuda and conv.groups == 1 and bn.num_features % 8 == 0 and bn.affine
                 and type(act).__name__ in ("ReLU", "ReLU6", "Swish", "HSwish", "Identity")):
             return engine.bn_act_apply(bn, act, conv(x))

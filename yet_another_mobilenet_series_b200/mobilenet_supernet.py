@@ -63,11 +63,23 @@ def run_features(model, x):
                 else:
                     x = layer(x)
             x = x.flatten(1)
-            x = model.classifier(x)
+            x = run_classifier(model.classifier, x)
         return x.float()
     # CPU: stem/head/classifier are plain torch, but the blocks have no CPU path and will raise
     x = model.features(x)
     return model.classifier(x.squeeze(3).squeeze(2))
+
+
+def run_classifier(classifier, x):
+    """Dropout -> Linear (reference :163-167); the Linear runs on the tcgen05 GEMM when its
+    widths allow (tail_ops.linear_apply), else as the torch module."""
+    from . import tail_ops
+    for layer in classifier:
+        if isinstance(layer, nn.Linear) and tail_ops.linear_supported(layer, x):
+            x = tail_ops.linear_apply(layer, x)
+        else:
+            x = layer(x)
+    return x
 
 
 class MobileNetV2(nn.Module):

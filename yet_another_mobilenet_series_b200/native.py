@@ -191,6 +191,34 @@ class SeFcBwd(C.Structure):
     ]
 
 
+class SoftmaxCe(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("C", C.c_int32), ("ld", C.c_int64),
+        ("logits", C.c_void_p), ("target", C.c_void_p),
+        ("smoothing", C.c_float),
+        ("loss", C.c_void_p), ("correct1", C.c_void_p), ("correct5", C.c_void_p),
+        ("G", C.c_void_p), ("ldg", C.c_int64),
+    ]
+
+
+class SoftmaxCeGrad(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("C", C.c_int32),
+        ("G", C.c_void_p), ("ldg", C.c_int64),
+        ("dloss", C.c_void_p),
+        ("dlogits", C.c_void_p), ("ldd", C.c_int64),
+        ("dbias", C.c_void_p),
+    ]
+
+
+class StemConv(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cout", C.c_int32),
+        ("x", C.c_void_p), ("w", C.c_void_p), ("y", C.c_void_p),
+        ("dh", C.c_void_p), ("dw", C.c_void_p),
+    ]
+
+
 class NlGram(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("sub", C.c_int32),
@@ -216,11 +244,12 @@ class NlRowmat(C.Structure):
 
 _STRUCTS = {0: BnFwd, 1: BnBwd, 2: Gemm, 3: DwFwd, 4: DwBwd, 5: BnApply, 6: BnReduce, 7: SePool,
             8: Rmsprop, 9: SeBwdReduce, 10: SeBwdApply, 11: BnStats, 12: BnBwdApply, 13: NlGram,
-            14: NlRowmat, 15: SeFc, 16: SeFcBwd}
+            14: NlRowmat, 15: SeFc, 16: SeFcBwd, 17: SoftmaxCe, 18: SoftmaxCeGrad,
+            19: StemConv}
 
 # every symbol include/yamb200.h declares
 SYMBOLS = ["yamb_pointwise_gemm", "yamb_depthwise_fwd", "yamb_depthwise_bwd", "yamb_bn_apply_fwd",
-           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_nl_gram_fwd", "yamb_nl_rowmat_fwd", "yamb_se_fc_fwd", "yamb_se_fc_bwd", "yamb_rmsprop_step", "yamb_ema_update",
+           "yamb_bn_reduce_bwd", "yamb_bn_stats_fwd", "yamb_bn_bwd_apply_bwd", "yamb_se_pool_fwd", "yamb_se_bwd_reduce_bwd", "yamb_se_bwd_apply_bwd", "yamb_nl_gram_fwd", "yamb_nl_rowmat_fwd", "yamb_se_fc_fwd", "yamb_se_fc_bwd", "yamb_softmax_ce_fwd", "yamb_softmax_ce_bwd", "yamb_colsum_bf16", "yamb_stem_conv_fwd", "yamb_stem_conv_wgrad", "yamb_rmsprop_step", "yamb_ema_update",
            "yamb_cast_bf16", "yamb_max_ctas", "yamb_struct_size", "yamb_last_error",
            "yamb_version"]
 _lib = None
@@ -255,6 +284,12 @@ def lib():
         l.yamb_se_pool_fwd.argtypes = [C.POINTER(SePool), C.c_void_p]
         l.yamb_se_bwd_reduce_bwd.argtypes = [C.POINTER(SeBwdReduce), C.c_void_p]
         l.yamb_se_bwd_apply_bwd.argtypes = [C.POINTER(SeBwdApply), C.c_void_p]
+        l.yamb_softmax_ce_fwd.argtypes = [C.POINTER(SoftmaxCe), C.c_void_p]
+        l.yamb_softmax_ce_bwd.argtypes = [C.POINTER(SoftmaxCeGrad), C.c_void_p]
+        l.yamb_colsum_bf16.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p,
+                                       C.c_void_p]
+        l.yamb_stem_conv_fwd.argtypes = [C.POINTER(StemConv), C.c_void_p]
+        l.yamb_stem_conv_wgrad.argtypes = [C.POINTER(StemConv), C.c_void_p]
         l.yamb_se_fc_fwd.argtypes = [C.POINTER(SeFc), C.c_void_p]
         l.yamb_se_fc_bwd.argtypes = [C.POINTER(SeFcBwd), C.c_void_p]
         l.yamb_nl_gram_fwd.argtypes = [C.POINTER(NlGram), C.c_void_p]

@@ -17,6 +17,7 @@ import torch.distributed as dist
 
 from . import distributed as udist
 from . import engine
+from . import tail_ops
 from .fused_rmsprop import RMSprop
 
 
@@ -64,7 +65,8 @@ class TrainStep:
         self.t_stage = torch.zeros_like(self.t)
         self.staged = False
         self.loss = torch.zeros((), device=dev)
-        self.top1 = torch.zeros((), device=dev)
+        self.top1 = torch.zeros((), device=dev)   # fraction correct@1 / @5 of the last batch
+        self.top5 = torch.zeros((), device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.copied = torch.cuda.Event()
         self.consumed = torch.cuda.Event()
@@ -89,7 +91,8 @@ class TrainStep:
     def _fwd_bwd(self):
         self.opt.zero_grad()
         logits = self.model(self.x)
-        per_sample = label_smooth_ce(logits, self.t, self.smoothing)
+        # label-smoothed CE + top-1 / top-5 in one kernel, no host sync (common.py:67-80)
+        per_sample, c1, c5 = tail_ops.softmax_ce(logits, self.t, self.smoothing)
         loss = per_sample.mean()
         engine.DEFER_JOIN = True      # wgrad side stream: one join after the whole backward
         try:
@@ -98,7 +101,8 @@ class TrainStep:
             engine.DEFER_JOIN = False
             engine.join_side(self.dev)
         self.loss.copy_(loss.detach())
-        self.top1.copy_((logits.argmax(1) == self.t).float().mean())
+        self.top1.copy_(c1.mean())
+        self.top5.copy_(c5.mean())
 
     def _capture(self):
         g = torch.cuda.CUDAGraph()
