@@ -96,8 +96,13 @@ def step(rnd):
     print("step:", len(lines), "launches", round(tot / 1e3, 2), "ms")
 
 
-def block(rnd):
-    path = os.path.join(SRC, rnd + "_ncu_b3_raw.csv")
+BLOCK_DESC = {"b1": "b1 (32->16, no expand, 112x112)", "b3": "b3 (24->144->24, 56x56)",
+              "b8": "b8 (64->384->64, 14x14)", "b15": "b15 (160->960->160, 7x7)",
+              "b2": "b2 (16->96->24, 112x112 -> 56x56)"}
+
+
+def block(rnd, name="b3"):
+    path = os.path.join(SRC, "%s_ncu_%s_raw.csv" % (rnd, name))
     if not os.path.exists(path):
         return
     hdr, body = read_ncu_csv(path)
@@ -123,10 +128,17 @@ def block(rnd):
             ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
             ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
+            ("sm__warps_active.avg.per_cycle_active", "warps/cycle"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb"),
+            ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+            ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_sb"),
             ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
             ("lts__t_sector_hit_rate.pct", "L2 hit %")]
-    with open(os.path.join(OUT, rnd + "_ncu_b3_summary.md"), "w") as f:
-        f.write("# %s — ncu --set full, block b3 (24->144->24, 56x56, N=256) forward+backward\n\n" % rnd)
+    with open(os.path.join(OUT, "%s_ncu_%s_summary.md" % (rnd, name)), "w") as f:
+        f.write("# %s — ncu --set full, block %s, N=256, forward+backward\n\n" %
+                (rnd, BLOCK_DESC.get(name, name)))
+        f.write("(stall columns: warps stalled per issue-active cycle, ncu's "
+                "`smsp__average_warps_issue_stalled_*_per_issue_active.ratio`)\n\n")
         f.write("| kernel | " + " | ".join(w[1] for w in want) + " |\n|---|" + "---|" * len(want) + "\n")
         for r in body:
             if len(r) < len(hdr) or "yamb::" not in r[col["Kernel Name"]]:
@@ -139,4 +151,5 @@ def block(rnd):
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     step(rnd)
-    block(rnd)
+    for b in ("b1", "b2", "b3", "b8", "b15"):
+        block(rnd, b)

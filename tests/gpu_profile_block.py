@@ -11,8 +11,9 @@ sys.path.insert(0, ROOT)
 from yet_another_mobilenet_series_b200 import mobilenet_base as mb  # noqa: E402
 
 # (inp, oup, stride, hidden, H)
-SHAPES = {"b2": (16, 24, 2, 96, 112), "b3": (24, 24, 1, 144, 56), "b6": (32, 32, 1, 192, 28),
-          "b9": (64, 64, 1, 384, 14), "b13": (96, 96, 1, 576, 14), "b16": (160, 160, 1, 960, 7)}
+SHAPES = {"b1": (32, 16, 1, 32, 112), "b2": (16, 24, 2, 96, 112), "b3": (24, 24, 1, 144, 56),
+          "b6": (32, 32, 1, 192, 28), "b8": (64, 64, 1, 384, 14), "b9": (64, 64, 1, 384, 14),
+          "b13": (96, 96, 1, 576, 14), "b15": (160, 160, 1, 960, 7), "b16": (160, 160, 1, 960, 7)}
 
 
 def main():
@@ -24,7 +25,7 @@ def main():
     for n in names:
         inp, oup, s, hid, H = SHAPES[n]
         torch.manual_seed(0)
-        blk = mb.InvertedResidualChannels(inp, oup, s, [hid], [3], True,
+        blk = mb.InvertedResidualChannels(inp, oup, s, [hid], [3], hid != inp,
                                           mb.get_active_fn("nn.ReLU"), bn).to(dev).train()
         blk.apply(mb.init_weights_mnas)
         x = torch.randn(N, inp, H, H, device=dev).to(torch.bfloat16).contiguous(

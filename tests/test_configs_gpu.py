@@ -108,18 +108,30 @@ def test_three_train_steps_vs_fp32_reference(built_lib, name, B):
         bt = dict(ref32.model.named_buffers())
         ba = dict(ref16.model.named_buffers())
         bo = dict(model.named_buffers())
+        # per buffer (a global flatten is dominated by the few BatchNorms with O(100) statistics,
+        # e.g. the non-local branch, whose value after three updates is itself chaotic): the
+        # mean and the 90th percentile of the per-buffer errors against the autocast yardstick's
         for kind in ("running_mean", "running_var"):
             ks = [k for k in bt if k.endswith(kind)]
-            eo, ea = _rel(_flat(bo, ks), _flat(bt, ks)), _rel(_flat(ba, ks), _flat(bt, ks))
-            rows.append("%s rel-L2: ours %.2e autocast %.2e" % (kind, eo, ea))
-            assert eo <= 1.5 * ea + 2e-3, rows
+            eo = sorted(_rel(bo[k].double().cpu(), bt[k].double().cpu()) for k in ks)
+            ea = sorted(_rel(ba[k].double().cpu(), bt[k].double().cpu()) for k in ks)
+            mo, ma = sum(eo) / len(eo), sum(ea) / len(ea)
+            po, pa = eo[int(0.9 * (len(eo) - 1))], ea[int(0.9 * (len(ea) - 1))]
+            rows.append("%s per-buffer rel-L2: mean ours %.2e autocast %.2e; p90 ours %.2e "
+                        "autocast %.2e; max ours %.2e autocast %.2e" % (kind, mo, ma, po, pa,
+                                                                        eo[-1], ea[-1]))
+            assert mo <= 1.5 * ma + 2e-3, rows
+            assert po <= 1.5 * pa + 2e-3, rows
         nbt = [k for k in bt if k.endswith("num_batches_tracked")]
         assert all(int(bo[k]) == int(bt[k]) == 3 for k in nbt)
         sk = [n for n, b in model.named_buffers() if "running_mean" in n or "running_var" in n]
-        got = torch.cat([s.detach().double().flatten().cpu() for s in ts.stat_shadow])
-        want = _flat(ref32.ema.shadow, sk)
-        rows.append("stat-shadow rel-L2 %.2e" % _rel(got, want))
-        assert _rel(got, want) < 5e-3, rows
+        eo = [_rel(s.detach().double().cpu(), ref32.ema.shadow[k].double().cpu())
+              for s, k in zip(ts.stat_shadow, sk)]
+        ea = [_rel(ref16.ema.shadow[k].double().cpu(), ref32.ema.shadow[k].double().cpu())
+              for k in sk]
+        mo, ma = sum(eo) / len(eo), sum(ea) / len(ea)
+        rows.append("stat-shadow per-buffer mean rel-L2: ours %.2e autocast %.2e" % (mo, ma))
+        assert mo <= 1.5 * ma + 2e-3, rows
     finally:
         out = os.path.join(ROOT, "gpurun_out")
         os.makedirs(out, exist_ok=True)

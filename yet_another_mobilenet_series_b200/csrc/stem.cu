@@ -35,37 +35,69 @@ struct StemDev {
   int tiles_h, tiles_w, num_tiles;
 };
 
-// stage the input tile of output tile (n, ty, tx) as bf16 [IH][IW][3] (zero outside the image)
+// The staged input tile starts ONE pixel left of the halo (column ix0 - 1) so that, with the tile
+// origin at an even pixel, every row segment begins on a 4-byte boundary and is copied as 32-bit
+// words: s_in[IH][kStemSW][3], input pixel ix lives at column ix - (ix0 - 1).
+constexpr int kStemSW = kStemIW + 1;                  // 66 staged columns
+constexpr int kStemRowWords = kStemSW * 3 / 2;        // 99 words per staged row
+
 __device__ __forceinline__ void stem_stage_input(const StemDev& p, int n, int ty, int tx,
                                                  __nv_bfloat16* s_in) {
-  const int iy0 = ty * kStemTH * 2 - 1, ix0 = tx * kStemTW * 2 - 1;
+  const int iy0 = ty * kStemTH * 2 - 1, ixs = tx * kStemTW * 2 - 2;   // ixs even
   const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * 3;
-  for (int e = threadIdx.x; e < kStemIH * kStemIW * 3; e += 256) {
-    const int r = e / (kStemIW * 3), rem = e % (kStemIW * 3);
-    const int iy = iy0 + r, ix = ix0 + rem / 3;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
-      v = img[((size_t)iy * p.W + ix) * 3 + rem % 3];
-    s_in[e] = v;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(s_in);
+  for (int e = threadIdx.x; e < kStemIH * kStemRowWords; e += 256) {
+    const int r = e / kStemRowWords, wd = e - r * kStemRowWords;
+    const int iy = iy0 + r;
+    uint32_t v = 0u;
+    if ((unsigned)iy < (unsigned)p.H) {
+      // elements 2*wd, 2*wd+1 of the row's (pixel, channel) sequence starting at pixel ixs
+      const int k0 = 2 * wd;
+      const int px0 = ixs + k0 / 3, px1 = ixs + (k0 + 1) / 3;
+      const __nv_bfloat16* row = img + (size_t)iy * p.W * 3;
+      const long long off = (long long)ixs * 3 + k0;         // element offset inside the row
+      if (px0 >= 0 && px1 < p.W) {
+        v = *reinterpret_cast<const uint32_t*>(row + off);   // 4-byte aligned: W*3*iy + even
+      } else {
+        const uint16_t lo = (px0 >= 0 && px0 < p.W) ? *reinterpret_cast<const uint16_t*>(row + off) : 0;
+        const uint16_t hi = (px1 >= 0 && px1 < p.W) ? *reinterpret_cast<const uint16_t*>(row + off + 1) : 0;
+        v = (uint32_t)lo | ((uint32_t)hi << 16);
+      }
+    }
+    dst[e] = v;
   }
 }
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ StemDev p) {
   __shared__ __align__(16) float s_w[27 * 64];                     // [tap*3+ci][co]
-  __shared__ __align__(16) __nv_bfloat16 s_in[kStemIH * kStemIW * 3];
+  __shared__ __align__(16) __nv_bfloat16 s_in[kStemIH * kStemSW * 3];
   for (int e = threadIdx.x; e < 27 * p.Cout; e += 256) {
     const int co = e / 27, j = e % 27;           // w[co][ci][ky][kx]: j = ci*9 + ky*3 + kx
     const int ci = j / 9, tap = j % 9;
     s_w[(tap * 3 + ci) * p.Cout + co] = p.w[e];
   }
   const int ry = threadIdx.x / 16, cp = threadIdx.x % 16;          // output row, column pair
+  const bool aligned = ((p.W * 3) % 2) == 0;     // odd W*3: rows are only 2-byte aligned
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
     const int n = t / (p.tiles_h * p.tiles_w), r = t % (p.tiles_h * p.tiles_w);
     const int ty = r / p.tiles_w, tx = r % p.tiles_w;
     __syncthreads();
-    stem_stage_input(p, n, ty, tx, s_in);
+    if (aligned) {
+      stem_stage_input(p, n, ty, tx, s_in);
+    } else {   // generic 2-byte path (odd image widths)
+      const int iy0 = ty * kStemTH * 2 - 1, ixs = tx * kStemTW * 2 - 2;
+      const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * 3;
+      for (int e = threadIdx.x; e < kStemIH * kStemSW * 3; e += 256) {
+        const int rr = e / (kStemSW * 3), rem = e % (kStemSW * 3);
+        const int iy = iy0 + rr, ix = ixs + rem / 3;
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+          v = img[((size_t)iy * p.W + ix) * 3 + rem % 3];
+        s_in[e] = v;
+      }
+    }
     __syncthreads();
-    // 3 x 5 x 3 input patch of this thread's two output pixels
+    // 3 x 5 x 3 input patch of this thread's two output pixels, as (a, a) pairs for FFMA2
     float in[3][5][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -73,14 +105,14 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ S
       for (int b = 0; b < 5; ++b)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          in[a][b][c] = __bfloat162float(s_in[((2 * ry + a) * kStemIW + 4 * cp + b) * 3 + c]);
+          in[a][b][c] = __bfloat162float(s_in[((2 * ry + a) * kStemSW + 4 * cp + b + 1) * 3 + c]);
     const int oy = ty * kStemTH + ry, ox = tx * kStemTW + 2 * cp;
     const bool ok0 = oy < p.Ho && ox < p.Wo, ok1 = oy < p.Ho && ox + 1 < p.Wo;
     __nv_bfloat16* yrow = p.y + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout;
     for (int c0 = 0; c0 < p.Cout; c0 += 8) {
-      float acc[2][8];
+      float2 acc[2][4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+      for (int e = 0; e < 4; ++e) acc[0][e] = acc[1][e] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
@@ -89,52 +121,66 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ S
           for (int ci = 0; ci < 3; ++ci) {
             const float4 w0 = *reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + ci) * p.Cout + c0);
             const float4 w1 = *reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * 3 + ci) * p.Cout + c0 + 4);
-            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-            const float a0 = in[ky][kx][ci], a1 = in[ky][kx + 2][ci];
+            const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w),
+                                  make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+            const float2 a0 = make_float2(in[ky][kx][ci], in[ky][kx][ci]);
+            const float2 a1 = make_float2(in[ky][kx + 2][ci], in[ky][kx + 2][ci]);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              acc[0][e] = fmaf(a0, wv[e], acc[0][e]);
-              acc[1][e] = fmaf(a1, wv[e], acc[1][e]);
+            for (int e = 0; e < 4; ++e) {
+              acc[0][e] = ffma2(a0, wv[e], acc[0][e]);
+              acc[1][e] = ffma2(a1, wv[e], acc[1][e]);
             }
           }
       if (ok0)
         *reinterpret_cast<uint4*>(yrow + c0) =
-            make_uint4(pack_bf16(acc[0][0], acc[0][1]), pack_bf16(acc[0][2], acc[0][3]),
-                       pack_bf16(acc[0][4], acc[0][5]), pack_bf16(acc[0][6], acc[0][7]));
+            make_uint4(pack_bf16(acc[0][0].x, acc[0][0].y), pack_bf16(acc[0][1].x, acc[0][1].y),
+                       pack_bf16(acc[0][2].x, acc[0][2].y), pack_bf16(acc[0][3].x, acc[0][3].y));
       if (ok1)
         *reinterpret_cast<uint4*>(yrow + p.Cout + c0) =
-            make_uint4(pack_bf16(acc[1][0], acc[1][1]), pack_bf16(acc[1][2], acc[1][3]),
-                       pack_bf16(acc[1][4], acc[1][5]), pack_bf16(acc[1][6], acc[1][7]));
+            make_uint4(pack_bf16(acc[1][0].x, acc[1][0].y), pack_bf16(acc[1][1].x, acc[1][1].y),
+                       pack_bf16(acc[1][2].x, acc[1][2].y), pack_bf16(acc[1][3].x, acc[1][3].y));
     }
   }
 }
 
-// thread = (co pair q = tid % (Cout/2), position group jg = tid / (Cout/2)); positions j = jg + k*G
-template <int kMaxJ>   // positions per thread = ceil(27 / G)
+// wgrad: thread = (4 output channels cq, 4 positions jq, pixel subset ps): 256 threads =
+// (Cout/4) x 8 x PS.  16 FMAs (8 FFMA2) per 2 + 4 shared-memory loads.  Positions are walked in
+// staging order jj = (ky*3 + kx)*3 + ci and mapped to the parameter's j = ci*9 + ky*3 + kx at the end.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__ StemDev p) {
   extern __shared__ __align__(16) unsigned char stem_smem[];
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [IH][IW][3]
-  __nv_bfloat16* s_dh = s_in + ((kStemIH * kStemIW * 3 + 7) & ~7);            // [TH*TW][Cout]
-  const int CP = p.Cout / 2;
-  const int G = 256 / CP;                           // position groups (Cout=32: 16)
-  const int q = threadIdx.x % CP, jg = threadIdx.x / CP;
-  float acc[kMaxJ][2];
-  int joff[kMaxJ];                                  // smem offset of (tap, ci) relative to a pixel
-  bool jok[kMaxJ];
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [IH][SW][3]
+  __nv_bfloat16* s_dh = s_in + ((kStemIH * kStemSW * 3 + 7) & ~7);            // [TH*TW][Cout]
+  const int CQ = p.Cout / 4;                        // channel quads (8 for Cout = 32)
+  const int PS = 256 / (CQ * 8);                    // pixel subsets (4 for Cout = 32)
+  const int cq = threadIdx.x % CQ, jq = (threadIdx.x / CQ) % 8, ps = threadIdx.x / (CQ * 8);
+  float2 acc[4][2];
+  int joff[4];
 #pragma unroll
-  for (int k = 0; k < kMaxJ; ++k) {
-    acc[k][0] = acc[k][1] = 0.f;
-    const int j = jg + k * G;                       // j = ci*9 + ky*3 + kx (the parameter's layout)
-    jok[k] = jg < G && j < 27;
-    const int jj = jok[k] ? j : 0;
-    const int ci = jj / 9, ky = (jj % 9) / 3, kx = jj % 3;
-    joff[k] = (ky * kStemIW + kx) * 3 + ci;
+  for (int k = 0; k < 4; ++k) {
+    acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+    const int jj = min(4 * jq + k, 26);             // positions 27..31 of the last group: dummies
+    const int tap = jj / 3, ci = jj % 3;
+    joff[k] = ((tap / 3) * kStemSW + (tap % 3) + 1) * 3 + ci;
   }
+  const bool aligned = ((p.W * 3) % 2) == 0;
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
     const int n = t / (p.tiles_h * p.tiles_w), r = t % (p.tiles_h * p.tiles_w);
     const int ty = r / p.tiles_w, tx = r % p.tiles_w;
     __syncthreads();
-    stem_stage_input(p, n, ty, tx, s_in);
+    if (aligned) {
+      stem_stage_input(p, n, ty, tx, s_in);
+    } else {
+      const int iy0 = ty * kStemTH * 2 - 1, ixs = tx * kStemTW * 2 - 2;
+      const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * 3;
+      for (int e = threadIdx.x; e < kStemIH * kStemSW * 3; e += 256) {
+        const int rr = e / (kStemSW * 3), rem = e % (kStemSW * 3);
+        const int iy = iy0 + rr, ix = ixs + rem / 3;
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
+          v = img[((size_t)iy * p.W + ix) * 3 + rem % 3];
+        s_in[e] = v;
+      }
+    }
     // dh tile, zero outside the image: 16-byte vectors
     const int V = p.Cout / 8;
     for (int e = threadIdx.x; e < kStemTH * kStemTW * V; e += 256) {
@@ -146,28 +192,34 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__
       reinterpret_cast<uint4*>(s_dh)[e] = val;
     }
     __syncthreads();
-    if (jg < G) {
-#pragma unroll 2
-      for (int pix = 0; pix < kStemTH * kStemTW; ++pix) {
-        const uint32_t d = reinterpret_cast<const uint32_t*>(s_dh + (size_t)pix * p.Cout)[q];
-        const float d0 = bf16lo(d), d1 = bf16hi(d);
-        const int base = ((2 * (pix / kStemTW)) * kStemIW + 2 * (pix % kStemTW)) * 3;
+#pragma unroll 4
+    for (int pix = ps; pix < kStemTH * kStemTW; pix += PS) {
+      const uint2 d = reinterpret_cast<const uint2*>(s_dh + (size_t)pix * p.Cout)[cq];
+      const float2 d01 = make_float2(bf16lo(d.x), bf16hi(d.x));
+      const float2 d23 = make_float2(bf16lo(d.y), bf16hi(d.y));
+      const int base = ((2 * (pix / kStemTW)) * kStemSW + 2 * (pix % kStemTW)) * 3;
 #pragma unroll
-        for (int k = 0; k < kMaxJ; ++k) {
-          const float xv = __bfloat162float(s_in[base + joff[k]]);
-          acc[k][0] = fmaf(d0, xv, acc[k][0]);
-          acc[k][1] = fmaf(d1, xv, acc[k][1]);
-        }
+      for (int k = 0; k < 4; ++k) {
+        const float xv = __bfloat162float(s_in[base + joff[k]]);
+        const float2 xx = make_float2(xv, xv);
+        acc[k][0] = ffma2(xx, d01, acc[k][0]);
+        acc[k][1] = ffma2(xx, d23, acc[k][1]);
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxJ; ++k)
-    if (jok[k]) {
-      const int j = jg + k * G;
-      atomicAdd(p.dw + (size_t)(2 * q) * 27 + j, acc[k][0]);
-      atomicAdd(p.dw + (size_t)(2 * q + 1) * 27 + j, acc[k][1]);
+  for (int k = 0; k < 4; ++k) {
+    const int jj = 4 * jq + k;
+    if (jj < 27) {
+      const int tap = jj / 3, ci = jj % 3;
+      const int j = ci * 9 + tap;
+      float* d = p.dw + (size_t)(4 * cq) * 27 + j;
+      atomicAdd(d, acc[k][0].x);
+      atomicAdd(d + 27, acc[k][0].y);
+      atomicAdd(d + 54, acc[k][1].x);
+      atomicAdd(d + 81, acc[k][1].y);
     }
+  }
 }
 
 static int stem_fill(const yamb_stem_conv* a, StemDev& p) {
@@ -207,29 +259,18 @@ int stem_conv_wgrad_launch(const yamb_stem_conv* a, cudaStream_t st) {
   if (rc) return rc;
   if (!a->dh || !a->dw || (reinterpret_cast<uintptr_t>(a->dh) & 15))
     return set_error(YAMB_EINVAL, "stem conv wgrad: dh (16-byte aligned) / dw required");
-  if (256 % (a->Cout / 2)) return set_error(YAMB_EINVAL, "stem conv wgrad: Cout/2 must divide 256");
-  const size_t smem = (size_t)((kStemIH * kStemIW * 3 + 7) & ~7) * 2 +
+  if (256 % (a->Cout / 4 * 8)) return set_error(YAMB_EINVAL, "stem conv wgrad: Cout must be 8, 16, 32 or 64");
+  const size_t smem = (size_t)((kStemIH * kStemSW * 3 + 7) & ~7) * 2 +
                       (size_t)kStemTH * kStemTW * a->Cout * 2;
-  const int G = 256 / (a->Cout / 2);
-  const int kj = (27 + G - 1) / G;              // 1 (Cout <= 16), 2 (32), 4 (64)
-  const int cap = 2 * max_ctas();
-  const int grid = p.num_tiles < cap ? p.num_tiles : cap;
-  cudaError_t e = cudaSuccess;
-#define YAMB_STEM_WGRAD(KJ)                                                                        \
-  do {                                                                                            \
-    static size_t attr = 0; /* process-wide: only ever raise the limit */                         \
-    if (smem > attr) {                                                                            \
-      e = cudaFuncSetAttribute(stem_wgrad_kernel<KJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               (int)smem);                                                        \
-      if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem wgrad attr: %s", cudaGetErrorString(e)); \
-      attr = smem;                                                                                \
-    }                                                                                             \
-    stem_wgrad_kernel<KJ><<<grid, 256, smem, st>>>(p);                                            \
-  } while (0)
-  if (kj <= 1) YAMB_STEM_WGRAD(1);
-  else if (kj == 2) YAMB_STEM_WGRAD(2);
-  else YAMB_STEM_WGRAD(4);
-#undef YAMB_STEM_WGRAD
+  static size_t attr = 0;   // process-wide: only ever raise the limit
+  cudaError_t e;
+  if (smem > attr) {
+    e = cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem wgrad attr: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  const int cap = 4 * max_ctas();
+  stem_wgrad_kernel<<<p.num_tiles < cap ? p.num_tiles : cap, 256, smem, st>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem conv wgrad: %s", cudaGetErrorString(e));
   return 0;

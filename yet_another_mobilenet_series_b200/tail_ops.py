@@ -376,8 +376,8 @@ def stem_supported(mod, x):
     co = conv.out_channels
     return (x.is_cuda and conv.in_channels == 3 and conv.kernel_size == (3, 3)
             and conv.stride == (2, 2) and conv.padding == (1, 1) and conv.groups == 1
-            and conv.dilation == (1, 1) and conv.bias is None and co % 8 == 0 and co <= 64
-            and 256 % (co // 2) == 0 and bn.affine
+            and conv.dilation == (1, 1) and conv.bias is None and co in (8, 16, 32, 64)
+            and bn.affine
             and type(act).__name__ in ("ReLU", "ReLU6", "Swish", "HSwish", "Identity"))
 
 
