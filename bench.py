@@ -30,11 +30,27 @@ MODEL_KW = dict(num_classes=1000, input_channel=32, last_channel=1280, width_mul
                 batch_norm_momentum=0.01, batch_norm_epsilon=1e-3, dropout_ratio=0.2)
 
 
-def build_model(seed=1995):
+# The other BASELINE.json configurations (③ proxyless_mobile, ④ atomnas_c+, ⑤ autonl_l): model
+# keywords as the reference's own yml loader resolves them (tests/golden/model_cfgs.json, written by
+# oracle/make_model_cfgs.py from apps/**/*.yml; /root/reference does not exist on the GPU box).
+CONFIGS = {"mobilenet_v2": ("MobileNetV2-1.0", 256), "proxyless_mobile": ("Proxyless-mobile", 256),
+           "atomnas_c+": ("AtomNAS-C+ (SE, Swish)", 256), "autonl_l": ("AutoNL-L (non-local)", 128)}
+_PLUGIN = {"models.mobilenet_supernet": "yet_another_mobilenet_series_b200.mobilenet_supernet",
+           "models.searched_network": "yet_another_mobilenet_series_b200.searched_network"}
+
+
+def build_model(seed=1995, config="mobilenet_v2"):
+    import importlib
     import torch
     from yet_another_mobilenet_series_b200 import mobilenet_base as mb, mobilenet_supernet as sup
     torch.manual_seed(seed)
-    model = sup.Model(**MODEL_KW, input_size=224)
+    if config == "mobilenet_v2":
+        model = sup.Model(**MODEL_KW, input_size=224)
+    else:
+        with open(os.path.join(ROOT, "tests", "golden", "model_cfgs.json")) as f:
+            cfg = json.load(f)[config]
+        lib = importlib.import_module(_PLUGIN[cfg["flags"]["model"]])
+        model = lib.Model(**cfg["model_kwparams"], input_size=cfg["flags"]["image_size"])
     model.apply(mb.init_weights_mnas)
     return model
 
@@ -148,7 +164,7 @@ def host_cpu():
             "usable": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None}
 
 
-def torch_gpu_context(batch=256, steps=5, warmup=3, device=None):
+def torch_gpu_context(batch=256, steps=5, warmup=3, device=None, config="mobilenet_v2"):
     """CONTEXT ROW: the reference's own module graph on stock
     PyTorch kernels (cuDNN / ATen, `cudnn.benchmark = True` as train.py:133 sets it) on THIS GPU,
     the reference step sequence (Python-loop RMSprop / EMA / L2, the two host syncs of
@@ -164,7 +180,7 @@ def torch_gpu_context(batch=256, steps=5, warmup=3, device=None):
     out = {}
     for tag, ac, cl in (("fp32_nchw", None, False), ("autocast_bf16_channels_last",
                                                      torch.bfloat16, True)):
-        model = tm.as_reference(build_model()).to(dev)
+        model = tm.as_reference(build_model(config=config)).to(dev)
         xin = x
         if cl:
             model = model.to(memory_format=torch.channels_last)
@@ -214,14 +230,14 @@ def run_torch_gpu(args):
     if rank != 0:
         return
     ctx = torch_gpu_context(args.batch, steps=max(3, min(args.steps, 10)),
-                            warmup=max(3, min(args.warmup, 5)))
+                            warmup=max(3, min(args.warmup, 5)), config=args.config)
     best = ctx["autocast_bf16_channels_last"]
     print(json.dumps({
         "impl": "torch_gpu", "metric": "images/sec", "value": best["img_per_s"], "unit": "img/s",
         "n_gpus": 1, "ms_per_step": best["step_ms"], "higher_is_better": True, "dtype": "bf16",
         "data": "synthetic", "gpu_context": ctx, "host_cpu": host_cpu(),
-        "config": {"workload": "MobileNetV2-1.0 224x224 training step, reference graph on stock "
-                               "PyTorch GPU kernels", "per_gpu_batch": args.batch}}))
+        "config": {"workload": "%s 224x224 training step, reference graph on stock PyTorch GPU "
+                               "kernels" % CONFIGS[args.config][0], "per_gpu_batch": args.batch}}))
 
 
 def run_reference(args):
@@ -311,7 +327,7 @@ def run_ours(args):
     from yet_another_mobilenet_series_b200 import engine
     from yet_another_mobilenet_series_b200.trainer import TrainStep
     B = args.batch
-    model = build_model().to(dev)
+    model = build_model(config=args.config).to(dev)
     if world > 1:  # rank 0's weights everywhere (reference utils/distributed.py:183-190)
         for t in model.state_dict().values():
             dist.broadcast(t, 0)
@@ -388,22 +404,42 @@ def run_ours(args):
         kernels.append({"kernel": tag, "launches": r["launches"], "ms_per_step": round(r["ms"], 4),
                         "share": round(r["ms"] / tot_k, 4), "alg_GBps": round(gbs, 1),
                         "hbm_frac": round(gbs / hbm_peak, 4), "TFLOPs": round(tfs, 2)})
-    top = kernels[0] if kernels else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if top and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top["kernel"])
+    # ---- roofline of the dominant KERNEL (launch classes that run the same __global__ function are
+    # one kernel: all pw_* / head_conv_* / fc_* classes are yamb::gemm_tc_kernel) ----
+    def phys(tag):
+        if tag.startswith(("pw_", "head_conv", "fc_")):
+            return "pw_gemm"                       # the name profiles/summarize.py gives gemm_tc_kernel
+        return tag
+    groups = {}
+    for tag, r in agg.items():
+        gk = groups.setdefault(phys(tag), {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+        for k in gk:
+            gk[k] += r[k]
+    for k in kernels:
+        k["cuda_kernel"] = {"pw_gemm": "yamb::gemm_tc_kernel"}.get(phys(k["kernel"]),
+                                                                  "yamb::%s_kernel" % k["kernel"])
     roofline = None
-    if top:
-        r = agg[top["kernel"]]
+    if groups:
+        name, r = max(groups.items(), key=lambda kv: kv[1]["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(name)
+        gbs = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        tfs = r["flops"] / (r["ms"] * 1e-3) / 1e12
         roofline = {
-            "kernel": top["kernel"], "bound": "hbm",
-            "achieved": top["alg_GBps"], "peak": hbm_peak, "unit": "GB/s",
-            "frac": round(top["alg_GBps"] / hbm_peak, 4), "traffic": traffic,
-            "peak_kind": peak_kind, "share_of_kernel_time": top["share"],
+            "kernel": {"pw_gemm": "yamb::gemm_tc_kernel (all pointwise / head / classifier GEMM "
+                                  "launch classes)"}.get(name, name),
+            "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+            "frac": round(gbs / hbm_peak, 4), "traffic": traffic, "peak_kind": peak_kind,
+            "share_of_kernel_time": round(r["ms"] / tot_k, 4),
             "launches_per_step": r["launches"],
             "alg_bytes_per_launch": int(r["bytes"] / max(r["launches"], 1)),
             "avg_launch_ms": round(r["ms"] / max(r["launches"], 1), 5),
+            "tensor_TFLOPs": round(tfs, 2), "tensor_frac_of_sustained_bf16": round(tfs / tf_peak, 4),
+            "note": "achieved = sum of the launches' algorithmic bytes (engine.py, next to every "
+                    "launch) / sum of their CUDA-event times inside real steps; traffic = mean "
+                    "ncu dram bytes per launch (profiles/traffic.json)",
         }
     base = None
     gpu_ctx = None
@@ -413,7 +449,7 @@ def run_ours(args):
     if world == 1 and not args.no_gpu_context:
         del ts
         torch.cuda.empty_cache()
-        gpu_ctx = torch_gpu_context(B, device=dev)
+        gpu_ctx = torch_gpu_context(B, device=dev, config=args.config)
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
     e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
@@ -423,8 +459,9 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "MobileNetV2-1.0 224x224 training step (fwd+loss+bwd+all-reduce+"
-                               "RMSprop/L2/EMA), bf16 activations, fp32 master weights",
+        "config": {"workload": "%s 224x224 training step (fwd+loss+bwd+all-reduce+"
+                               "RMSprop/L2/EMA), bf16 activations, fp32 master weights"
+                               % CONFIGS[args.config][0],
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2_flush": "working set per step (>10 GB of activations at N=256) exceeds the "
                                "126 MB L2, inputs larger than L2",
@@ -454,11 +491,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"])
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=None,
+                    help="per-GPU batch (default: 256; 128 for autonl_l, BASELINE.json configs)")
+    ap.add_argument("--config", default="mobilenet_v2", choices=sorted(CONFIGS),
+                    help="BASELINE.json model configuration (default: the headline MobileNetV2-1.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-context", action="store_true",
                     help="skip the stock-PyTorch-on-this-GPU context measurement")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = CONFIGS[args.config][1]
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch_gpu":

@@ -152,3 +152,49 @@ def test_fused_rmsprop_ctor_contract():
     assert mnas_l2_mask(m.named_parameters()) == {
         "conv.weight": True, "bn.weight": False, "bn.bias": False, "classifier.weight": True,
         "classifier.bias": True}
+
+
+def test_padded_shadow_flat_transfers_cpu():
+    """AtomNAS-style odd widths: the zero-padded shadow block's batched transfers (one gather each
+    way, engine._PadShadow) put every real value where the per-tensor maps say, pads are 0 (1 for a
+    running variance), and the gradient gather is the exact inverse."""
+    from yet_another_mobilenet_series_b200 import engine
+    torch.manual_seed(0)
+    blk = mb.InvertedResidualChannelsFused(24, 24, 1, [15, 23, 13], [3, 5, 7], True,
+                                           mb.get_active_fn("nn.Swish"), BN, se_ratio=0.5)
+    for p in blk.parameters():
+        p.data.normal_()
+    for n, b in blk.named_buffers():
+        if b.dim():
+            b.data.uniform_(0.5, 2.0)
+    sh = engine._PadShadow(blk, torch.device("cpu"))
+    sh.push(blk)
+    real = dict(blk.named_parameters())
+    real.update(dict(blk.named_buffers()))
+    shad = dict(sh.shadow.named_parameters())
+    shad.update(dict(sh.shadow.named_buffers()))
+    for name, t in real.items():
+        st = shad[name]
+        if t.dim() == 0:
+            assert int(st) == int(t)
+            continue
+        m = sh.maps[name]
+        assert torch.equal(st.reshape(-1)[m], t.reshape(-1)), name
+        mask = torch.ones(st.numel(), dtype=torch.bool)
+        mask[m] = False
+        pad = st.reshape(-1)[mask]
+        want = 1.0 if name.endswith("running_var") else 0.0
+        assert bool((pad == want).all()), name
+    # statistics come back; gradients gather to the real shapes
+    for n in sh.stat_names:
+        shad[n].add_(1.0)
+    before = {n: real[n].clone() for n in sh.stat_names}
+    sh.pull_stats(blk)
+    for n in sh.stat_names:
+        assert torch.allclose(real[n], before[n] + 1.0), n
+    sp = dict(sh.shadow.named_parameters())
+    gmap = {id(p): torch.arange(p.numel(), dtype=torch.float32).view(p.shape) for p in sp.values()}
+    grads = sh.gather_grads(gmap, blk)
+    for (n, p), g in zip(blk.named_parameters(), grads):
+        assert g.shape == p.shape
+        assert torch.equal(g.reshape(-1), sh.maps[n].float()), n

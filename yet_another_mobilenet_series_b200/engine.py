@@ -1040,24 +1040,71 @@ class _PadShadow:
                 pos = pos.index_select(d, gi)
             self.maps[name] = pos.reshape(-1).to(device)
         self.real_names = list(real.keys())
+        self._build_flat(block, device)
 
-    def push(self, block):
-        """real -> shadow (parameters, running statistics, BN / module modes)."""
+    # ---- batched transfers ---------------------------------------------------------------------
+    # Round 1 moved every parameter / buffer with its own index_copy_ (and every gradient with its
+    # own index_select): ~100 tiny launches per padded block per step, 21 padded blocks in
+    # AtomNAS-C+.  Now every floating-point shadow tensor is a view of ONE flat arena S and the
+    # transfers are single gathers:
+    #   push : S = cat(real tensors, [0, 1])[idx]          (pads -> 0, running_var pads -> 1)
+    #   pull : real running statistics = S[stat_idx]       (one gather + one multi-tensor copy)
+    #   grads: real gradients = cat(shadow gradients)[grad_idx]
+    def _build_flat(self, block, device):
         real = dict(block.named_parameters())
         real.update(dict(block.named_buffers()))
-        shad = dict(self.shadow.named_parameters())
-        shad.update(dict(self.shadow.named_buffers()))
+        shad_p = dict(self.shadow.named_parameters())
+        shad_b = dict(self.shadow.named_buffers())
+        self.f_names = [n for n, t in real.items() if t.dim() > 0]          # float tensors
+        self.i_names = [n for n, t in real.items() if t.dim() == 0]         # num_batches_tracked
+        s_off, r_off, so, ro = {}, {}, 0, 0
+        for n in self.f_names:
+            st = shad_p[n] if n in shad_p else shad_b[n]
+            s_off[n], r_off[n] = so, ro
+            so += st.numel()
+            ro += real[n].numel()
+        self.S = torch.zeros(so, device=device, dtype=torch.float32)
+        idx = torch.full((so,), ro, dtype=torch.long)               # default: the constant 0
+        for n in self.f_names:
+            st = shad_p[n] if n in shad_p else shad_b[n]
+            if n.endswith("running_var"):
+                idx[s_off[n]:s_off[n] + st.numel()] = ro + 1       # pads of a variance: 1
+            m = self.maps[n].cpu()
+            idx[s_off[n] + m] = r_off[n] + torch.arange(real[n].numel())
+            view = self.S[s_off[n]:s_off[n] + st.numel()].view(st.shape)
+            if n in shad_p:
+                shad_p[n].data = view
+            else:
+                mod_name, _, key = n.rpartition(".")
+                mod = self.shadow.get_submodule(mod_name) if mod_name else self.shadow
+                mod._buffers[key] = view
+        self.idx = idx.to(device)
+        self.consts = torch.tensor([0.0, 1.0], device=device)
+        # running statistics back to the real buffers
+        self.stat_names = [n for n in self.f_names if n in shad_b]
+        self.stat_idx = torch.cat([s_off[n] + self.maps[n].cpu() for n in self.stat_names]).to(device) \
+            if self.stat_names else None
+        self.stat_sizes = [real[n].numel() for n in self.stat_names]
+        # gradients: positions of the real elements inside cat(shadow parameter gradients)
+        self.p_names = [n for n in self.f_names if n in shad_p]
+        g_off, go = {}, 0
+        for n in self.p_names:
+            g_off[n] = go
+            go += shad_p[n].numel()
+        self.grad_idx = torch.cat([g_off[n] + self.maps[n].cpu() for n in self.p_names]).to(device)
+        self.grad_sizes = [real[n].numel() for n in self.p_names]
+
+    def push(self, block):
+        """real -> shadow (parameters, running statistics, BN / module modes): two launches."""
+        real = dict(block.named_parameters())
+        real.update(dict(block.named_buffers()))
         with torch.no_grad():
-            for name, t in real.items():
-                st, m = shad[name], self.maps[name]
-                if m is None:
-                    st.copy_(t)
-                else:
-                    if name.endswith("running_var"):
-                        st.fill_(1.0)
-                    else:
-                        st.zero_()
-                    st.view(-1).index_copy_(0, m, t.reshape(-1))
+            src = torch.cat([real[n].detach().reshape(-1) for n in self.f_names] + [self.consts])
+            torch.index_select(src, 0, self.idx, out=self.S)
+            if self.i_names:
+                shad_b = dict(self.shadow.named_buffers())
+                for n in self.i_names:
+                    shad_b[n].copy_(real[n])
         for (_, rm), (_, sm) in zip(block.named_modules(), self.shadow.named_modules()):
             sm.training = rm.training
             if isinstance(rm, torch.nn.BatchNorm2d):
@@ -1065,14 +1112,26 @@ class _PadShadow:
 
     def pull_stats(self, block):
         """shadow -> real running statistics after a training-mode forward."""
-        shad = dict(self.shadow.named_buffers())
+        if self.stat_idx is None:
+            return
+        real_b = dict(block.named_buffers())
         with torch.no_grad():
-            for name, t in block.named_buffers():
-                st, m = shad[name], self.maps[name]
-                if m is None:
-                    t.copy_(st)
-                else:
-                    t.copy_(st.view(-1).index_select(0, m).view(t.shape))
+            flat = torch.index_select(self.S, 0, self.stat_idx)
+            parts = flat.split(self.stat_sizes)
+            torch._foreach_copy_([real_b[n].view(-1) for n in self.stat_names], list(parts))
+            shad_b = dict(self.shadow.named_buffers())
+            for n in self.i_names:
+                real_b[n].copy_(shad_b[n])
+
+    def gather_grads(self, gmap, block):
+        """{id(shadow param): grad} -> list of real-shaped gradients in block.named_parameters()
+        order (one cat + one gather)."""
+        sp = dict(self.shadow.named_parameters())
+        flat = torch.cat([gmap[id(sp[n])].reshape(-1).float() for n in self.p_names])
+        real_flat = torch.index_select(flat, 0, self.grad_idx)
+        parts = real_flat.split(self.grad_sizes)
+        by_name = dict(zip(self.p_names, parts))
+        return [by_name[n].view(p.shape) for n, p in block.named_parameters()]
 
 
 class _PadFn(torch.autograd.Function):
@@ -1097,15 +1156,12 @@ class _PadFn(torch.autograd.Function):
             raise RuntimeError("yamb: block re-entered before its backward (see _BlockFn)")
         (x,) = ctx.saved_tensors
         dx, gmap = run_backward(sh.shadow, plan, x, dy)
-        sp = dict(sh.shadow.named_parameters())
-        pgrads = []
-        for name, p in block.named_parameters():
-            g = gmap.get(id(sp[name]))
-            if g is None:
-                pgrads.append(None)
-            else:
-                pgrads.append(g.reshape(-1).index_select(0, sh.maps[name]).view(p.shape))
-        return (dx, None) + tuple(pgrads)
+        grads = sh.gather_grads(gmap, block)
+        params = list(block.parameters())
+        if all(getattr(p, "_yamb_direct", False) and p.grad is not None for p in params):
+            torch._foreach_add_([p.grad for p in params], grads)   # straight into the flat arena
+            return (dx, None) + (None,) * len(params)
+        return (dx, None) + tuple(grads)
 
 
 # ------------------------------------------------------------------------------------------------
