@@ -25,7 +25,8 @@ def tag_of(name, prev_gemm=[0]):
     if "gemm_tc_kernel" in name:
         return "pw_gemm"
     for k in ("bn_bwd_apply", "bn_stats", "bn_apply", "bn_reduce", "se_pool", "se_bwd_reduce", "se_bwd_apply", "rmsprop",
-              "ema_kernel", "cast_bf16"):
+              "ema_kernel", "cast_bf16", "stem_fwd", "stem_wgrad", "softmax_ce_fwd", "softmax_ce_bwd",
+              "colsum_bf16", "se_fc_fwd", "se_fc_bwd_sample", "se_fc_bwd_param", "nl_gram", "nl_rowmat"):
         if k in name:
             return k
     return "torch:" + re.sub(r"<.*", "", name.replace("void ", ""))[:48]

@@ -69,8 +69,14 @@ __device__ __forceinline__ void stem_stage_input(const StemDev& p, int n, int ty
 }
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ StemDev p) {
-  __shared__ __align__(16) float s_w[27 * 64];                     // [tap*3+ci][co]
-  __shared__ __align__(16) __nv_bfloat16 s_in[kStemIH * kStemSW * 3];
+  extern __shared__ __align__(16) unsigned char stem_smem[];
+  float* s_w = reinterpret_cast<float*>(stem_smem);                // [tap*3+ci][co], 27*64 floats
+  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(s_w + 27 * 64);   // [IH][SW][3]
+  // per-warp output staging: 2 output rows x 32 pixels x Cout channels, written back as whole
+  // 16-byte-per-lane coalesced rows (a thread's own 2 x Cout values are 128 B apart from its
+  // neighbour's: stored directly, every instruction touched 32 half-used sectors)
+  uint4* s_out = reinterpret_cast<uint4*>(s_in + ((kStemIH * kStemSW * 3 + 7) & ~7)) +
+                 (threadIdx.x >> 5) * (64 * (p.Cout / 8));
   for (int e = threadIdx.x; e < 27 * p.Cout; e += 256) {
     const int co = e / 27, j = e % 27;           // w[co][ci][ky][kx]: j = ci*9 + ky*3 + kx
     const int ci = j / 9, tap = j % 9;
@@ -106,9 +112,9 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ S
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           in[a][b][c] = __bfloat162float(s_in[((2 * ry + a) * kStemSW + 4 * cp + b + 1) * 3 + c]);
-    const int oy = ty * kStemTH + ry, ox = tx * kStemTW + 2 * cp;
-    const bool ok0 = oy < p.Ho && ox < p.Wo, ok1 = oy < p.Ho && ox + 1 < p.Wo;
-    __nv_bfloat16* yrow = p.y + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout;
+    const int V = p.Cout / 8;                       // 16-byte vectors per pixel
+    const int lane = threadIdx.x & 31;
+    const int hp = lane >> 4;                       // which of the warp's two output rows
     for (int c0 = 0; c0 < p.Cout; c0 += 8) {
       float2 acc[2][4];
 #pragma unroll
@@ -131,33 +137,44 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ S
               acc[1][e] = ffma2(a1, wv[e], acc[1][e]);
             }
           }
-      if (ok0)
-        *reinterpret_cast<uint4*>(yrow + c0) =
-            make_uint4(pack_bf16(acc[0][0].x, acc[0][0].y), pack_bf16(acc[0][1].x, acc[0][1].y),
-                       pack_bf16(acc[0][2].x, acc[0][2].y), pack_bf16(acc[0][3].x, acc[0][3].y));
-      if (ok1)
-        *reinterpret_cast<uint4*>(yrow + p.Cout + c0) =
-            make_uint4(pack_bf16(acc[1][0].x, acc[1][0].y), pack_bf16(acc[1][1].x, acc[1][1].y),
-                       pack_bf16(acc[1][2].x, acc[1][2].y), pack_bf16(acc[1][3].x, acc[1][3].y));
+      // staging layout: [row hp][pixel 0..31][V vectors]
+      uint4* so = s_out + (hp * 32 + 2 * cp) * V + (c0 >> 3);
+      so[0] = make_uint4(pack_bf16(acc[0][0].x, acc[0][0].y), pack_bf16(acc[0][1].x, acc[0][1].y),
+                         pack_bf16(acc[0][2].x, acc[0][2].y), pack_bf16(acc[0][3].x, acc[0][3].y));
+      so[V] = make_uint4(pack_bf16(acc[1][0].x, acc[1][0].y), pack_bf16(acc[1][1].x, acc[1][1].y),
+                         pack_bf16(acc[1][2].x, acc[1][2].y), pack_bf16(acc[1][3].x, acc[1][3].y));
     }
+    __syncwarp();
+    // the warp's two rows: oy = tile row (2 * warp + hp'), 32 pixels x V vectors each, contiguous
+    const int wrow = (threadIdx.x >> 5) * 2;
+    const int ox0 = tx * kStemTW;
+    for (int q = lane; q < 64 * V; q += 32) {
+      const int rr = q / (32 * V), within = q - rr * 32 * V;     // row, vector inside the row
+      const int oy = ty * kStemTH + wrow + rr, ox = ox0 + within / V;
+      if (oy < p.Ho && ox < p.Wo)
+        reinterpret_cast<uint4*>(p.y + (((size_t)n * p.Ho + oy) * p.Wo + ox0) * p.Cout)[within] =
+            s_out[q];
+    }
+    __syncwarp();
   }
 }
 
-// wgrad: thread = (4 output channels cq, 4 positions jq, pixel subset ps): 256 threads =
-// (Cout/4) x 8 x PS.  16 FMAs (8 FFMA2) per 2 + 4 shared-memory loads.  Positions are walked in
+// wgrad: thread = (8 output channels co8, 4 positions jq, pixel subset ps): 256 threads =
+// (Cout/8) x 8 x PS.  32 FMAs (16 FFMA2) per 2 + 4 shared-memory loads.  Positions are walked in
 // staging order jj = (ky*3 + kx)*3 + ci and mapped to the parameter's j = ci*9 + ky*3 + kx at the end.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__ StemDev p) {
   extern __shared__ __align__(16) unsigned char stem_smem[];
   __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [IH][SW][3]
   __nv_bfloat16* s_dh = s_in + ((kStemIH * kStemSW * 3 + 7) & ~7);            // [TH*TW][Cout]
-  const int CQ = p.Cout / 4;                        // channel quads (8 for Cout = 32)
-  const int PS = 256 / (CQ * 8);                    // pixel subsets (4 for Cout = 32)
-  const int cq = threadIdx.x % CQ, jq = (threadIdx.x / CQ) % 8, ps = threadIdx.x / (CQ * 8);
-  float2 acc[4][2];
+  const int CO = p.Cout / 8;                        // channel octets (4 for Cout = 32)
+  const int PS = 256 / (CO * 8);                    // pixel subsets (8 for Cout = 32)
+  const int co8 = threadIdx.x % CO, jq = (threadIdx.x / CO) % 8, ps = threadIdx.x / (CO * 8);
+  float2 acc[4][4];
   int joff[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[k][e] = make_float2(0.f, 0.f);
     const int jj = min(4 * jq + k, 26);             // positions 27..31 of the last group: dummies
     const int tap = jj / 3, ci = jj % 3;
     joff[k] = ((tap / 3) * kStemSW + (tap % 3) + 1) * 3 + ci;
@@ -192,18 +209,18 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__
       reinterpret_cast<uint4*>(s_dh)[e] = val;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
     for (int pix = ps; pix < kStemTH * kStemTW; pix += PS) {
-      const uint2 d = reinterpret_cast<const uint2*>(s_dh + (size_t)pix * p.Cout)[cq];
-      const float2 d01 = make_float2(bf16lo(d.x), bf16hi(d.x));
-      const float2 d23 = make_float2(bf16lo(d.y), bf16hi(d.y));
+      const uint4 d = reinterpret_cast<const uint4*>(s_dh + (size_t)pix * p.Cout)[co8];
+      const float2 dd[4] = {make_float2(bf16lo(d.x), bf16hi(d.x)), make_float2(bf16lo(d.y), bf16hi(d.y)),
+                            make_float2(bf16lo(d.z), bf16hi(d.z)), make_float2(bf16lo(d.w), bf16hi(d.w))};
       const int base = ((2 * (pix / kStemTW)) * kStemSW + 2 * (pix % kStemTW)) * 3;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float xv = __bfloat162float(s_in[base + joff[k]]);
         const float2 xx = make_float2(xv, xv);
-        acc[k][0] = ffma2(xx, d01, acc[k][0]);
-        acc[k][1] = ffma2(xx, d23, acc[k][1]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[k][e] = ffma2(xx, dd[e], acc[k][e]);
       }
     }
   }
@@ -213,11 +230,12 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__
     if (jj < 27) {
       const int tap = jj / 3, ci = jj % 3;
       const int j = ci * 9 + tap;
-      float* d = p.dw + (size_t)(4 * cq) * 27 + j;
-      atomicAdd(d, acc[k][0].x);
-      atomicAdd(d + 27, acc[k][0].y);
-      atomicAdd(d + 54, acc[k][1].x);
-      atomicAdd(d + 81, acc[k][1].y);
+      float* d = p.dw + (size_t)(8 * co8) * 27 + j;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        atomicAdd(d + (2 * e) * 27, acc[k][e].x);
+        atomicAdd(d + (2 * e + 1) * 27, acc[k][e].y);
+      }
     }
   }
 }
@@ -247,8 +265,17 @@ int stem_conv_fwd_launch(const yamb_stem_conv* a, cudaStream_t st) {
   if (!a->w || !a->y || (reinterpret_cast<uintptr_t>(a->y) & 15))
     return set_error(YAMB_EINVAL, "stem conv fwd: w / y (16-byte aligned) required");
   const int cap = 4 * max_ctas();
-  stem_fwd_kernel<<<p.num_tiles < cap ? p.num_tiles : cap, 256, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  const size_t smem = 27 * 64 * 4 + (size_t)((kStemIH * kStemSW * 3 + 7) & ~7) * 2 +
+                      (size_t)8 * 64 * (a->Cout / 8) * 16;
+  static size_t attr_f = 0;   // process-wide: only ever raise the limit
+  cudaError_t e;
+  if (smem > attr_f) {
+    e = cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem fwd attr: %s", cudaGetErrorString(e));
+    attr_f = smem;
+  }
+  stem_fwd_kernel<<<p.num_tiles < cap ? p.num_tiles : cap, 256, smem, st>>>(p);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem conv fwd: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -259,7 +286,7 @@ int stem_conv_wgrad_launch(const yamb_stem_conv* a, cudaStream_t st) {
   if (rc) return rc;
   if (!a->dh || !a->dw || (reinterpret_cast<uintptr_t>(a->dh) & 15))
     return set_error(YAMB_EINVAL, "stem conv wgrad: dh (16-byte aligned) / dw required");
-  if (256 % (a->Cout / 4 * 8)) return set_error(YAMB_EINVAL, "stem conv wgrad: Cout must be 8, 16, 32 or 64");
+  if (256 % (a->Cout / 8 * 8)) return set_error(YAMB_EINVAL, "stem conv wgrad: Cout must be 8, 16, 32 or 64");
   const size_t smem = (size_t)((kStemIH * kStemSW * 3 + 7) & ~7) * 2 +
                       (size_t)kStemTH * kStemTW * a->Cout * 2;
   static size_t attr = 0;   // process-wide: only ever raise the limit
