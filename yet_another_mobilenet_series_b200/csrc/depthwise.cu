@@ -27,6 +27,12 @@
 #include "host_util.h"
 #include "prims.cuh"
 
+// resident CTAs per SM the 3x3 kernels are compiled for (register cap 64 Ki / (256 * n)); the
+// profiling variant build overrides it (-DYAMB_DW_MINBLOCKS=3) to A/B occupancy against spills
+#ifndef YAMB_DW_MINBLOCKS
+#define YAMB_DW_MINBLOCKS 2
+#endif
+
 namespace yamb {
 
 __device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
@@ -86,7 +92,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // cp.async (zero-fill outside the image) while tile t is transformed IN PLACE (BN + activation,
 // rounded to bf16 like every other materialised activation) and convolved.
 template <int K, int S, int CT, int TW>
-__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_fwd_kernel(
+__global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_fwd_kernel(
     const __grid_constant__ DwFwdDev p) {
   using G = FwdGeom<K, S, CT, TW>;
   constexpr int P = (K - 1) / 2;
@@ -397,7 +403,7 @@ __device__ __forceinline__ constexpr bool tap_hits(int a, int k, int r) {
 // gathers a 2x2 pixel tile from registers: every staged gradient vector feeds up to 4 dgrad and
 // 4 wgrad FMAs, all shared-memory offsets are immediates, no bounds or parity branches.
 template <int K, int S, int CT, int TAP0, int TAP1, bool DGRAD>
-__global__ void __launch_bounds__(256, (K == 3 ? 2 : 1)) dw_bwd_kernel(
+__global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_bwd_kernel(
     const __grid_constant__ DwBwdDev p) {
   using G = BwdGeom<K, S, CT>;
   constexpr int P = G::P, TIH = G::TIH, TIW = G::TIW, RH = G::RH, RW = G::RW, R = G::R;

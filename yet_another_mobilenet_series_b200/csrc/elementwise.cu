@@ -275,11 +275,35 @@ __global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ Se
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
-    for (int i = pl; i < p.HW; i += 8) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + ((size_t)n * p.HW + i) * p.ldh + c0)), v);
+    // 4 rows in flight per thread: one dependent load per iteration left this kernel waiting a
+    // DRAM round trip per 16 bytes (254 us per SE block of AtomNAS-C+ at 56x56)
+    const ActParam ap = make_act(p.act);
+    const __nv_bfloat16* base = p.h + (size_t)n * p.HW * p.ldh + c0;
+    int i = pl;
+    for (; i + 24 < p.HW; i += 32) {
+      uint4 raw[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] += round_bf16(act_fwd(fmaf(sc[e], v[e], sh[e]), p.act));
+      for (int u = 0; u < 4; ++u)
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(i + 8 * u) * p.ldh));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(raw[u], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+        act_vec<8>(v, ap);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += round_bf16(v[e]);
+      }
+    }
+    for (; i < p.HW; i += 8) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)i * p.ldh)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+      act_vec<8>(v, ap);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += round_bf16(v[e]);
     }
   }
 #pragma unroll
@@ -320,14 +344,32 @@ __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const __grid_constan
     float sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
-    for (int i = pl; i < p.HW; i += 8) {
+    const __nv_bfloat16* hb = p.h + (size_t)n * p.HW * p.ldh + c0;
+    const __nv_bfloat16* db = p.dy + (size_t)n * p.HW * p.ldd + c0;
+    auto body = [&](const uint4& hr, const uint4& dr) {
       float v[8], d[8];
-      const size_t row = (size_t)n * p.HW + i;
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), v);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ldd + c0)), d);
+      unpack8(hr, v);
+      unpack8(dr, d);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] = fmaf(d[e], round_bf16(act_rt(fmaf(sc[e], v[e], sh[e]), ap)), s[e]);
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+      act_vec<8>(v, ap);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = fmaf(d[e], round_bf16(v[e]), s[e]);
+    };
+    int i = pl;
+    for (; i + 24 < p.HW; i += 32) {      // 4 rows (8 loads) in flight per thread
+      uint4 hr[4], dr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        hr[u] = __ldg(reinterpret_cast<const uint4*>(hb + (size_t)(i + 8 * u) * p.ldh));
+        dr[u] = __ldg(reinterpret_cast<const uint4*>(db + (size_t)(i + 8 * u) * p.ldd));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(hr[u], dr[u]);
     }
+    for (; i < p.HW; i += 8)
+      body(__ldg(reinterpret_cast<const uint4*>(hb + (size_t)i * p.ldh)),
+           __ldg(reinterpret_cast<const uint4*>(db + (size_t)i * p.ldd)));
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) red[pl][threadIdx.x & 31][e] = s[e];
@@ -379,16 +421,20 @@ __global__ void __launch_bounds__(256) se_bwd_apply_kernel(const __grid_constant
       }
       for (long long row = (long long)blockIdx.x * PX + px; row < p.M;
            row += (long long)gridDim.x * PX) {
-        const long long n = row / p.rows_per_sample;
+        const long long n = (p.M < 0x7fffffffLL)
+            ? (long long)((unsigned)row / (unsigned)p.rows_per_sample) : row / p.rows_per_sample;
         float d[8], hv[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.dy + row * p.ldd + c0)), d);
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.h + row * p.ldh + c0)), hv);
-        const float* g = p.gate + n * p.ldg + c0;
-        const float* dp = p.dpool + n * p.ldg + c0;
+        const float4* g4 = reinterpret_cast<const float4*>(p.gate + n * p.ldg + c0);
+        const float4* d4 = reinterpret_cast<const float4*>(p.dpool + n * p.ldg + c0);
+        const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), pa = __ldg(d4), pb = __ldg(d4 + 1);
+        const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        const float pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float z = fmaf(sc[e], hv[e], sh[e]);
-          d[e] = fmaf(d[e], __ldg(g + e), __ldg(dp + e)) * act_bwd_rt(z, ap, p.act);
+          d[e] = fmaf(d[e], gg[e], pp[e]) * act_bwd_rt(z, ap, p.act);
         }
         const uint4 o = pack8(d);
         *reinterpret_cast<uint4*>(p.dz + row * p.ldz + c0) = o;
@@ -528,6 +574,8 @@ int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t st) {
   p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
   p.scale = a->scale; p.shift = a->shift; p.act = a->act;
   p.gate = a->gate; p.dpool = a->dpool; p.ldg = a->ldg > 0 ? a->ldg : a->C;
+  if (((reinterpret_cast<uintptr_t>(a->gate) | reinterpret_cast<uintptr_t>(a->dpool)) & 15) || (p.ldg % 4))
+    return set_error(YAMB_EINVAL, "se_bwd_apply: gate / dpool must be 16-byte aligned, pitch % 4 == 0");
   p.dz = (__nv_bfloat16*)a->dz; p.bn = *a->bn;
   const int CG = a->C / 8;
   const int PX = 256 / CG > 0 ? 256 / CG : 1;

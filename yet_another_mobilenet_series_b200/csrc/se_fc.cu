@@ -8,8 +8,8 @@
 //   backward: dt = dgate*gate*(1-gate) ;  du = (W_e^T dt) * act'(u) ;  dpool = (W_r^T du) / HW ;
 //             dW_e += dt^T v, db_e += sum dt, dW_r += du^T s, db_r += sum du   (sums over samples)
 // fp32 throughout (the reference keeps these tiny layers in fp32 too).  One CTA per sample for
-// the per-sample chain; the parameter gradients are owned one-output-per-thread (no atomics:
-// deterministic).  C <= 4096, R <= 1024.
+// the per-sample chain; the parameter gradients are owned one-output-per-thread (no global
+// atomics; the per-sample chain uses a handful of shared-memory float adds).  C <= 4096, R <= 1024.
 #include <cuda_runtime.h>
 
 #include "host_util.h"
@@ -46,8 +46,16 @@ __global__ void __launch_bounds__(256) se_fc_fwd_kernel(const __grid_constant__ 
   __syncthreads();
   for (int c = tid; c < a.C; c += 256) {
     const float* w = a.w_e + (size_t)c * a.R;
-    float acc = a.b_e[c];
-    for (int j = 0; j < a.R; ++j) acc = fmaf(w[j], s_v[j], acc);
+    float acc0 = a.b_e[c], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int j = 0;
+    for (; j + 3 < a.R; j += 4) {          // 4 independent chains: the loads pipeline
+      acc0 = fmaf(w[j], s_v[j], acc0);
+      acc1 = fmaf(w[j + 1], s_v[j + 1], acc1);
+      acc2 = fmaf(w[j + 2], s_v[j + 2], acc2);
+      acc3 = fmaf(w[j + 3], s_v[j + 3], acc3);
+    }
+    for (; j < a.R; ++j) acc0 = fmaf(w[j], s_v[j], acc0);
+    const float acc = (acc0 + acc1) + (acc2 + acc3);
     a.gate[(size_t)n * a.C + c] = 1.f / (1.f + __expf(-acc));
   }
 }
@@ -65,18 +73,49 @@ __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_cons
     a.dt[(size_t)n * a.C + c] = dt;
   }
   __syncthreads();
-  for (int j = tid; j < a.R; j += 256) {         // consecutive threads: consecutive W_e columns
-    float acc = 0.f;
-    for (int c = 0; c < a.C; ++c) acc = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], acc);
-    const float du = acc * act_bwd(a.u[(size_t)n * a.R + j], a.act);
+  // dv[j] = sum_c dt[c] * W_e[c][j]: consecutive threads own consecutive columns j (coalesced rows
+  // of W_e) and the C-long sum is split over the P = 256 / R' thread groups, 4 loads in flight each
+  // (one thread per j walked all C rows alone: ~170 us of exposed L2 latency per SE block)
+  for (int j = tid; j < a.R; j += 256) s_du[j] = 0.f;
+  __syncthreads();
+  {
+    int Rp = 32;
+    while (Rp < a.R && Rp < 256) Rp <<= 1;          // columns per pass, power of two <= 256
+    const int P = 256 / Rp, part = tid / Rp;
+    for (int j0 = 0; j0 < a.R; j0 += Rp) {
+      const int j = j0 + (tid % Rp);
+      if (j < a.R) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int c = part;
+        for (; c + 3 * P < a.C; c += 4 * P) {
+          a0 = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], a0);
+          a1 = fmaf(s_dt[c + P], a.w_e[(size_t)(c + P) * a.R + j], a1);
+          a2 = fmaf(s_dt[c + 2 * P], a.w_e[(size_t)(c + 2 * P) * a.R + j], a2);
+          a3 = fmaf(s_dt[c + 3 * P], a.w_e[(size_t)(c + 3 * P) * a.R + j], a3);
+        }
+        for (; c < a.C; c += P) a0 = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], a0);
+        atomicAdd(&s_du[j], (a0 + a1) + (a2 + a3));
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < a.R; j += 256) {
+    const float du = s_du[j] * act_bwd(a.u[(size_t)n * a.R + j], a.act);
     s_du[j] = du;
     a.du[(size_t)n * a.R + j] = du;
   }
   __syncthreads();
   for (int c = tid; c < a.C; c += 256) {
-    float acc = 0.f;
-    for (int j = 0; j < a.R; ++j) acc = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], acc);
-    a.dpool[(size_t)n * a.C + c] = acc * a.inv_hw;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = 0;
+    for (; j + 3 < a.R; j += 4) {
+      a0 = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], a0);
+      a1 = fmaf(s_du[j + 1], a.w_r[(size_t)(j + 1) * a.C + c], a1);
+      a2 = fmaf(s_du[j + 2], a.w_r[(size_t)(j + 2) * a.C + c], a2);
+      a3 = fmaf(s_du[j + 3], a.w_r[(size_t)(j + 3) * a.C + c], a3);
+    }
+    for (; j < a.R; ++j) a0 = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], a0);
+    a.dpool[(size_t)n * a.C + c] = ((a0 + a1) + (a2 + a3)) * a.inv_hw;
   }
 }
 
@@ -87,6 +126,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_param_kernel(const __grid_const
        i += (long long)gridDim.x * 256) {
     const int c = (int)(i / a.R), j = (int)(i % a.R);
     float we = 0.f, wr = 0.f, be = 0.f, br = 0.f;
+#pragma unroll 4
     for (int n = 0; n < a.N; ++n) {
       const float dt = a.dt[(size_t)n * a.C + c], du = a.du[(size_t)n * a.R + j];
       we = fmaf(dt, a.v[(size_t)n * a.R + j], we);
