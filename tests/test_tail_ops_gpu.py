@@ -149,3 +149,26 @@ def test_stem_conv(built_lib):
         assert _rel(mod[0].weight.grad, ref[0].weight.grad) < 2e-2, (cout, hw)
         assert _rel(mod[1].weight.grad, ref[1].weight.grad) < 2e-2
         assert _rel(mod[1].running_var, ref[1].running_var) < 5e-3
+
+
+def test_data_prefetcher_surface_and_values(built_lib):
+    """DataPrefetcher (reference utils/dataflow.py:13-58): iterator surface, device placement,
+    bf16 channels_last conversion, buffer recycling without tearing."""
+    from yet_another_mobilenet_series_b200.dataflow import DataPrefetcher
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(4, 3, 32, 32, generator=g).pin_memory(),
+                torch.randint(0, 10, (4,), generator=g).pin_memory()) for _ in range(5)]
+    pf = DataPrefetcher(batches)
+    assert len(pf) == 5
+    seen = 0
+    acc = []
+    for (x, t), (hx, ht) in zip(pf, batches):
+        assert x.is_cuda and x.dtype == torch.bfloat16
+        assert x.is_contiguous(memory_format=torch.channels_last)
+        acc.append((x.float().sum(), hx.bfloat16().float().sum()))   # consumed before the next batch
+        assert torch.equal(t.cpu(), ht)
+        seen += 1
+    assert seen == 5
+    torch.cuda.synchronize()
+    for a, b in acc:
+        assert abs(float(a) - float(b)) < 1e-2 * (abs(float(b)) + 1.0)
