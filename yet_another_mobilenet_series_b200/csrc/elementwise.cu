@@ -260,63 +260,80 @@ struct SePoolDev {
   int act;
   float* pooled;  // [N][C]
 };
-__global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ SePoolDev p) {
-  // grid: (N, ceil(C/8/32)); block: 32 channel groups x 8 pixel lanes
-  const int n = blockIdx.x;
-  const int cg = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int pl = threadIdx.x >> 5;  // 0..7
-  __shared__ float red[8][32][8];
+// grid (pixel chunks, N); thread = (8-channel group cg, pixel lane px): whole 16-byte-per-lane rows
+// are read (every lane busy whatever C is), 4 rows in flight per thread, lanes reduced through
+// shared memory, one fp32 reduction per (n, c) per CTA into the pre-zeroed output.
+template <bool kBwd>
+__device__ __forceinline__ void se_rows_reduce(int N, int HW, int C, const __nv_bfloat16* h, int ldh,
+                                               const __nv_bfloat16* dy, int ldd, const float* scale,
+                                               const float* shift, int act, float out_scale,
+                                               float* out) {
+  __shared__ float red[256][9];
+  const int CG = C / 8;
+  const int PX = 256 / CG;                       // pixel lanes (host guarantees CG <= 256)
+  const int cg = threadIdx.x % CG, px = threadIdx.x / CG;
+  const int n = blockIdx.y;
+  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per, r1 = min(HW, r0 + rows_per);
   float s[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = 0.f;
-  const bool ok = cg * 8 < p.C;
-  if (ok) {
+  if (px < PX) {
     const int c0 = cg * 8;
+    const ActParam ap = make_act(act);
     float sc[8], sh[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
-    // 4 rows in flight per thread: one dependent load per iteration left this kernel waiting a
-    // DRAM round trip per 16 bytes (254 us per SE block of AtomNAS-C+ at 56x56)
-    const ActParam ap = make_act(p.act);
-    const __nv_bfloat16* base = p.h + (size_t)n * p.HW * p.ldh + c0;
-    int i = pl;
-    for (; i + 24 < p.HW; i += 32) {
-      uint4 raw[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(i + 8 * u) * p.ldh));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float v[8];
-        unpack8(raw[u], v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
-        act_vec<8>(v, ap);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] += round_bf16(v[e]);
-      }
-    }
-    for (; i < p.HW; i += 8) {
+    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(scale + c0 + e); sh[e] = __ldg(shift + c0 + e); }
+    const __nv_bfloat16* hb = h + (size_t)n * HW * ldh + c0;
+    const __nv_bfloat16* db = kBwd ? dy + (size_t)n * HW * ldd + c0 : nullptr;
+    auto body = [&](const uint4& hr, const uint4& dr) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t)i * p.ldh)), v);
+      unpack8(hr, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
       act_vec<8>(v, ap);
+      if (kBwd) {
+        float d[8];
+        unpack8(dr, d);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] += round_bf16(v[e]);
+        for (int e = 0; e < 8; ++e) s[e] = fmaf(d[e], round_bf16(v[e]), s[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += round_bf16(v[e]);
+      }
+    };
+    int i = r0 + px;
+    for (; i + 3 * PX < r1; i += 4 * PX) {
+      uint4 hr[4], dr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        hr[u] = __ldg(reinterpret_cast<const uint4*>(hb + (size_t)(i + u * PX) * ldh));
+        dr[u] = kBwd ? __ldg(reinterpret_cast<const uint4*>(db + (size_t)(i + u * PX) * ldd))
+                     : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(hr[u], dr[u]);
     }
+    for (; i < r1; i += PX)
+      body(__ldg(reinterpret_cast<const uint4*>(hb + (size_t)i * ldh)),
+           kBwd ? __ldg(reinterpret_cast<const uint4*>(db + (size_t)i * ldd)) : make_uint4(0u, 0u, 0u, 0u));
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[pl][threadIdx.x & 31][e] = s[e];
+  for (int e = 0; e < 8; ++e) red[threadIdx.x][e] = s[e];
   __syncthreads();
-  if (pl == 0 && ok) {
+  if (px == 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float t = 0.f;
-      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x & 31][e];
-      p.pooled[(size_t)n * p.C + cg * 8 + e] = t / (float)p.HW;
+      for (int j = 0; j < PX; ++j) t += red[j * CG + cg][e];
+      atomicAdd(out + (size_t)n * C + cg * 8 + e, t * out_scale);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ SePoolDev p) {
+  se_rows_reduce<false>(p.N, p.HW, p.C, p.h, p.ldh, nullptr, 0, p.scale, p.shift, p.act,
+                        1.f / (float)p.HW, p.pooled);
 }
 
 // dgate[n][c] = sum over HW of dY[n,hw,c] * round_bf16(act(scale*h + shift))  (SE backward, the
@@ -330,58 +347,8 @@ struct SeBwdReduceDev {
   float* dgate;  // [N][C]
 };
 __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const __grid_constant__ SeBwdReduceDev p) {
-  const int n = blockIdx.x;
-  const int cg = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int pl = threadIdx.x >> 5;
-  __shared__ float red[8][32][8];
-  float s[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s[e] = 0.f;
-  const bool ok = cg * 8 < p.C;
-  if (ok) {
-    const int c0 = cg * 8;
-    const ActParam ap = make_act(p.act);
-    float sc[8], sh[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e); }
-    const __nv_bfloat16* hb = p.h + (size_t)n * p.HW * p.ldh + c0;
-    const __nv_bfloat16* db = p.dy + (size_t)n * p.HW * p.ldd + c0;
-    auto body = [&](const uint4& hr, const uint4& dr) {
-      float v[8], d[8];
-      unpack8(hr, v);
-      unpack8(dr, d);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
-      act_vec<8>(v, ap);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] = fmaf(d[e], round_bf16(v[e]), s[e]);
-    };
-    int i = pl;
-    for (; i + 24 < p.HW; i += 32) {      // 4 rows (8 loads) in flight per thread
-      uint4 hr[4], dr[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        hr[u] = __ldg(reinterpret_cast<const uint4*>(hb + (size_t)(i + 8 * u) * p.ldh));
-        dr[u] = __ldg(reinterpret_cast<const uint4*>(db + (size_t)(i + 8 * u) * p.ldd));
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) body(hr[u], dr[u]);
-    }
-    for (; i < p.HW; i += 8)
-      body(__ldg(reinterpret_cast<const uint4*>(hb + (size_t)i * p.ldh)),
-           __ldg(reinterpret_cast<const uint4*>(db + (size_t)i * p.ldd)));
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) red[pl][threadIdx.x & 31][e] = s[e];
-  __syncthreads();
-  if (pl == 0 && ok) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float t = 0.f;
-      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x & 31][e];
-      p.dgate[(size_t)n * p.C + cg * 8 + e] = t;
-    }
-  }
+  se_rows_reduce<true>(p.N, p.HW, p.C, p.h, p.ldh, p.dy, p.ldd, p.scale, p.shift, p.act, 1.f,
+                       p.dgate);
 }
 
 // dz = (dY * gate[n][c] + dpool[n][c]) * act'(scale*h + shift)   (in place allowed: dz == dY)
@@ -534,6 +501,16 @@ int bn_bwd_apply_launch(const yamb_bn_bwd_apply* a, cudaStream_t st) {
   return 0;
 }
 
+// pixel chunks per sample: enough CTAs to fill the GPU ~4x, every pixel lane with >= 4 rows
+static int se_chunks(int N, int HW, int C) {
+  const int PX = 256 / (C / 8) > 0 ? 256 / (C / 8) : 1;
+  int want = (4 * max_ctas() + N - 1) / N;
+  int most = HW / (4 * PX);
+  if (most < 1) most = 1;
+  if (want > most) want = most;
+  return want < 1 ? 1 : want;
+}
+
 int se_pool_launch(const yamb_se_pool* a, cudaStream_t st) {
   if (!a || a->N <= 0 || a->HW <= 0 || a->C <= 0 || (a->C % 8))
     return set_error(YAMB_EINVAL, "se_pool shape");
@@ -542,9 +519,12 @@ int se_pool_launch(const yamb_se_pool* a, cudaStream_t st) {
   p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldh = a->ldh;
   p.h = (const __nv_bfloat16*)a->h; p.scale = a->scale; p.shift = a->shift; p.act = a->act;
   p.pooled = a->pooled;
-  dim3 grid(a->N, (a->C / 8 + 31) / 32);
+  if (a->C > 2048 || a->N > 65535) return set_error(YAMB_EINVAL, "se_pool: C <= 2048, N <= 65535");
+  cudaError_t e = cudaMemsetAsync(a->pooled, 0, (size_t)a->N * a->C * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool memset: %s", cudaGetErrorString(e));
+  dim3 grid(se_chunks(a->N, a->HW, a->C), a->N);
   se_pool_kernel<<<grid, 256, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool: %s", cudaGetErrorString(e));
   return 0;
 }
@@ -557,9 +537,12 @@ int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t st) {
   p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldd = a->ldd; p.ldh = a->ldh;
   p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
   p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dgate = a->dgate;
-  dim3 grid(a->N, (a->C / 8 + 31) / 32);
+  if (a->C > 2048 || a->N > 65535) return set_error(YAMB_EINVAL, "se_bwd_reduce: C <= 2048, N <= 65535");
+  cudaError_t e = cudaMemsetAsync(a->dgate, 0, (size_t)a->N * a->C * sizeof(float), st);
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_reduce memset: %s", cudaGetErrorString(e));
+  dim3 grid(se_chunks(a->N, a->HW, a->C), a->N);
   se_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_reduce: %s", cudaGetErrorString(e));
   return 0;
 }

@@ -41,31 +41,38 @@ struct StemDev {
 constexpr int kStemSW = kStemIW + 1;                  // 66 staged columns
 constexpr int kStemRowWords = kStemSW * 3 / 2;        // 99 words per staged row
 
+// All copies of a tile are issued as asynchronous 4-byte cp.async (zero-filled outside the image)
+// and awaited ONCE by the caller (stem_stage_wait): a plain load loop exposed one DRAM round
+// trip per iteration, 13 per tile.
 __device__ __forceinline__ void stem_stage_input(const StemDev& p, int n, int ty, int tx,
                                                  __nv_bfloat16* s_in) {
   const int iy0 = ty * kStemTH * 2 - 1, ixs = tx * kStemTW * 2 - 2;   // ixs even
   const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * 3;
   uint32_t* dst = reinterpret_cast<uint32_t*>(s_in);
+#pragma unroll 1
   for (int e = threadIdx.x; e < kStemIH * kStemRowWords; e += 256) {
     const int r = e / kStemRowWords, wd = e - r * kStemRowWords;
     const int iy = iy0 + r;
-    uint32_t v = 0u;
-    if ((unsigned)iy < (unsigned)p.H) {
-      // elements 2*wd, 2*wd+1 of the row's (pixel, channel) sequence starting at pixel ixs
-      const int k0 = 2 * wd;
-      const int px0 = ixs + k0 / 3, px1 = ixs + (k0 + 1) / 3;
-      const __nv_bfloat16* row = img + (size_t)iy * p.W * 3;
-      const long long off = (long long)ixs * 3 + k0;         // element offset inside the row
-      if (px0 >= 0 && px1 < p.W) {
-        v = *reinterpret_cast<const uint32_t*>(row + off);   // 4-byte aligned: W*3*iy + even
-      } else {
-        const uint16_t lo = (px0 >= 0 && px0 < p.W) ? *reinterpret_cast<const uint16_t*>(row + off) : 0;
-        const uint16_t hi = (px1 >= 0 && px1 < p.W) ? *reinterpret_cast<const uint16_t*>(row + off + 1) : 0;
-        v = (uint32_t)lo | ((uint32_t)hi << 16);
-      }
+    // elements 2*wd, 2*wd+1 of the row's (pixel, channel) sequence starting at pixel ixs
+    const int k0 = 2 * wd;
+    const int px0 = ixs + k0 / 3, px1 = ixs + (k0 + 1) / 3;
+    const bool rowok = (unsigned)iy < (unsigned)p.H;
+    const bool v0 = rowok && px0 >= 0 && px0 < p.W, v1 = rowok && px1 >= 0 && px1 < p.W;
+    const __nv_bfloat16* src = img + (size_t)(rowok ? iy : 0) * p.W * 3 + ((long long)ixs * 3 + k0);
+    if (v0 == v1) {        // whole word inside (copy) or outside (zero-fill): 4-byte aligned
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + e)),
+                   "l"(v0 ? (const void*)src : (const void*)img), "r"(v0 ? 4 : 0)
+                   : "memory");
+    } else {               // image border inside the word (odd widths only)
+      const uint16_t lo = v0 ? *reinterpret_cast<const uint16_t*>(src) : 0;
+      const uint16_t hi = v1 ? *reinterpret_cast<const uint16_t*>(src + 1) : 0;
+      dst[e] = (uint32_t)lo | ((uint32_t)hi << 16);
     }
-    dst[e] = v;
   }
+}
+__device__ __forceinline__ void stem_stage_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ StemDev p) {
@@ -90,6 +97,7 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const __grid_constant__ S
     __syncthreads();
     if (aligned) {
       stem_stage_input(p, n, ty, tx, s_in);
+      stem_stage_wait();
     } else {   // generic 2-byte path (odd image widths)
       const int iy0 = ty * kStemTH * 2 - 1, ixs = tx * kStemTW * 2 - 2;
       const __nv_bfloat16* img = p.x + (size_t)n * p.H * p.W * 3;
@@ -203,11 +211,16 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const __grid_constant__
     for (int e = threadIdx.x; e < kStemTH * kStemTW * V; e += 256) {
       const int pix = e / V, v = e % V;
       const int oy = ty * kStemTH + pix / kStemTW, ox = tx * kStemTW + pix % kStemTW;
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (oy < p.Ho && ox < p.Wo)
-        val = __ldg(reinterpret_cast<const uint4*>(p.dh + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout) + v);
-      reinterpret_cast<uint4*>(s_dh)[e] = val;
+      const bool ok = oy < p.Ho && ox < p.Wo;
+      const void* src = ok ? (const void*)(reinterpret_cast<const uint4*>(
+                                 p.dh + (((size_t)n * p.Ho + oy) * p.Wo + ox) * p.Cout) + v)
+                           : (const void*)p.dh;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                       smem_u32(reinterpret_cast<uint4*>(s_dh) + e)),
+                   "l"(src), "r"(ok ? 16 : 0)
+                   : "memory");
     }
+    stem_stage_wait();
     __syncthreads();
 #pragma unroll 2
     for (int pix = ps; pix < kStemTH * kStemTW; pix += PS) {
@@ -274,7 +287,12 @@ int stem_conv_fwd_launch(const yamb_stem_conv* a, cudaStream_t st) {
     if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem fwd attr: %s", cudaGetErrorString(e));
     attr_f = smem;
   }
-  stem_fwd_kernel<<<p.num_tiles < cap ? p.num_tiles : cap, 256, smem, st>>>(p);
+  static int per_sm_f = 0;
+  if (per_sm_f == 0 &&
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, stem_fwd_kernel, 256, smem) != cudaSuccess)
+    per_sm_f = 2;
+  const int res_f = max_ctas() * (per_sm_f > 0 ? per_sm_f : 1);   // one resident wave: no tail
+  stem_fwd_kernel<<<p.num_tiles < res_f ? p.num_tiles : res_f, 256, smem, st>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem conv fwd: %s", cudaGetErrorString(e));
   return 0;
@@ -297,7 +315,12 @@ int stem_conv_wgrad_launch(const yamb_stem_conv* a, cudaStream_t st) {
     attr = smem;
   }
   const int cap = 4 * max_ctas();
-  stem_wgrad_kernel<<<p.num_tiles < cap ? p.num_tiles : cap, 256, smem, st>>>(p);
+  static int per_sm_w = 0;
+  if (per_sm_w == 0 &&
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, stem_wgrad_kernel, 256, smem) != cudaSuccess)
+    per_sm_w = 2;
+  const int res_w = max_ctas() * (per_sm_w > 0 ? per_sm_w : 1);
+  stem_wgrad_kernel<<<p.num_tiles < res_w ? p.num_tiles : res_w, 256, smem, st>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "stem conv wgrad: %s", cudaGetErrorString(e));
   return 0;
