@@ -258,7 +258,8 @@ struct SePoolDev {
   const __nv_bfloat16* h;
   const float *scale, *shift;
   int act;
-  float* pooled;  // [N][C]
+  float* pooled;  // [N][out_ld]
+  int out_ld;
 };
 // grid (pixel chunks, N); thread = (8-channel group cg, pixel lane px): whole 16-byte-per-lane rows
 // are read (every lane busy whatever C is), 4 rows in flight per thread, lanes reduced through
@@ -267,7 +268,7 @@ template <bool kBwd>
 __device__ __forceinline__ void se_rows_reduce(int N, int HW, int C, const __nv_bfloat16* h, int ldh,
                                                const __nv_bfloat16* dy, int ldd, const float* scale,
                                                const float* shift, int act, float out_scale,
-                                               float* out) {
+                                               float* out, int out_ld) {
   __shared__ float red[256][9];
   const int CG = C / 8;
   const int PX = 256 / CG;                       // pixel lanes (host guarantees CG <= 256)
@@ -326,14 +327,14 @@ __device__ __forceinline__ void se_rows_reduce(int N, int HW, int C, const __nv_
     for (int e = 0; e < 8; ++e) {
       float t = 0.f;
       for (int j = 0; j < PX; ++j) t += red[j * CG + cg][e];
-      atomicAdd(out + (size_t)n * C + cg * 8 + e, t * out_scale);
+      atomicAdd(out + (size_t)n * out_ld + cg * 8 + e, t * out_scale);
     }
   }
 }
 
 __global__ void __launch_bounds__(256) se_pool_kernel(const __grid_constant__ SePoolDev p) {
   se_rows_reduce<false>(p.N, p.HW, p.C, p.h, p.ldh, nullptr, 0, p.scale, p.shift, p.act,
-                        1.f / (float)p.HW, p.pooled);
+                        1.f / (float)p.HW, p.pooled, p.out_ld);
 }
 
 // dgate[n][c] = sum over HW of dY[n,hw,c] * round_bf16(act(scale*h + shift))  (SE backward, the
@@ -344,11 +345,12 @@ struct SeBwdReduceDev {
   const __nv_bfloat16* h;
   const float *scale, *shift;
   int act;
-  float* dgate;  // [N][C]
+  float* dgate;  // [N][out_ld]
+  int out_ld;
 };
 __global__ void __launch_bounds__(256) se_bwd_reduce_kernel(const __grid_constant__ SeBwdReduceDev p) {
   se_rows_reduce<true>(p.N, p.HW, p.C, p.h, p.ldh, p.dy, p.ldd, p.scale, p.shift, p.act, 1.f,
-                       p.dgate);
+                       p.dgate, p.out_ld);
 }
 
 // dz = (dY * gate[n][c] + dpool[n][c]) * act'(scale*h + shift)   (in place allowed: dz == dY)
@@ -519,11 +521,17 @@ int se_pool_launch(const yamb_se_pool* a, cudaStream_t st) {
   p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldh = a->ldh;
   p.h = (const __nv_bfloat16*)a->h; p.scale = a->scale; p.shift = a->shift; p.act = a->act;
   p.pooled = a->pooled;
-  if (a->C > 2048 || a->N > 65535) return set_error(YAMB_EINVAL, "se_pool: C <= 2048, N <= 65535");
+  if (a->N > 65535) return set_error(YAMB_EINVAL, "se_pool: N <= 65535");
   cudaError_t e = cudaMemsetAsync(a->pooled, 0, (size_t)a->N * a->C * sizeof(float), st);
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool memset: %s", cudaGetErrorString(e));
-  dim3 grid(se_chunks(a->N, a->HW, a->C), a->N);
-  se_pool_kernel<<<grid, 256, 0, st>>>(p);
+  p.out_ld = a->C;
+  for (int c0 = 0; c0 < a->C; c0 += 2048) {       // a thread owns one 8-channel group: <= 256 per CTA
+    SePoolDev q = p;
+    q.C = a->C - c0 < 2048 ? a->C - c0 : 2048;
+    q.h = p.h + c0; q.scale = p.scale + c0; q.shift = p.shift + c0; q.pooled = p.pooled + c0;
+    dim3 grid(se_chunks(a->N, a->HW, q.C), a->N);
+    se_pool_kernel<<<grid, 256, 0, st>>>(q);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_pool: %s", cudaGetErrorString(e));
   return 0;
@@ -537,11 +545,18 @@ int se_bwd_reduce_launch(const yamb_se_bwd_reduce* a, cudaStream_t st) {
   p.N = a->N; p.HW = a->HW; p.C = a->C; p.ldd = a->ldd; p.ldh = a->ldh;
   p.dy = (const __nv_bfloat16*)a->dy; p.h = (const __nv_bfloat16*)a->h;
   p.scale = a->scale; p.shift = a->shift; p.act = a->act; p.dgate = a->dgate;
-  if (a->C > 2048 || a->N > 65535) return set_error(YAMB_EINVAL, "se_bwd_reduce: C <= 2048, N <= 65535");
+  if (a->N > 65535) return set_error(YAMB_EINVAL, "se_bwd_reduce: N <= 65535");
   cudaError_t e = cudaMemsetAsync(a->dgate, 0, (size_t)a->N * a->C * sizeof(float), st);
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_reduce memset: %s", cudaGetErrorString(e));
-  dim3 grid(se_chunks(a->N, a->HW, a->C), a->N);
-  se_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p);
+  p.out_ld = a->C;
+  for (int c0 = 0; c0 < a->C; c0 += 2048) {
+    SeBwdReduceDev q = p;
+    q.C = a->C - c0 < 2048 ? a->C - c0 : 2048;
+    q.h = p.h + c0; q.dy = p.dy + c0; q.scale = p.scale + c0; q.shift = p.shift + c0;
+    q.dgate = p.dgate + c0;
+    dim3 grid(se_chunks(a->N, a->HW, q.C), a->N);
+    se_bwd_reduce_kernel<<<grid, 256, 0, st>>>(q);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_reduce: %s", cudaGetErrorString(e));
   return 0;
