@@ -93,8 +93,11 @@ def act_code_of(active_fn):
 
 
 class Workspace:
-    """Per-device scratch shared by all kernels of a stream (they serialise on it)."""
-    _per_device = {}
+    """Scratch of the statistics-producing kernels: the global fp32 accumulator of the per-channel
+    sums (2*C floats, zero between launches — the last CTA of every launch returns it to zero) and
+    the arrival counter.  The kernels of ONE stream serialise on it, so there is one per
+    (device, stream): blocks driven from two streams at the same time do not share."""
+    _per_stream = {}
 
     def __init__(self, device):
         lib = nat.lib()
@@ -102,18 +105,17 @@ class Workspace:
         if self.max_ctas <= 0:
             raise nat.NativeError("no CUDA device visible to libyamb200 (there is no CPU path)")
         self.max_c = 4096
-        self.partials = torch.zeros(self.max_ctas * 2 * self.max_c, device=device,
-                                    dtype=torch.float32)
+        self.partials = torch.zeros(4 * self.max_c, device=device, dtype=torch.float32)
         self.counter = torch.zeros(4, device=device, dtype=torch.int32)
 
     @classmethod
     def get(cls, device):
-        key = (device.type, device.index if device.index is not None
-               else torch.cuda.current_device())
-        ws = cls._per_device.get(key)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+        ws = cls._per_stream.get(key)
         if ws is None:
             ws = cls(device)
-            cls._per_device[key] = ws
+            cls._per_stream[key] = ws
         return ws
 
 
@@ -293,8 +295,9 @@ class BlockPlan:
         """yamb_bn_fwd for channels [c0, c0+C) of stage `bn` (per-branch slice for depthwise)."""
         C = bn.C if C is None else C
         s = nat.BnFwd()
-        s.partials = self.ws.partials.data_ptr()
-        s.counter = self.ws.counter.data_ptr()
+        ws = Workspace.get(self.dev)     # of the stream this launch goes to
+        s.partials = ws.partials.data_ptr()
+        s.counter = ws.counter.data_ptr()
         if bn.single:
             m = bn.mods[0]
             g, b = m.weight, m.bias
@@ -329,8 +332,9 @@ class BlockPlan:
     def _bn_bwd_struct(self, bn, count, grads, c0=0, C=None):
         C = bn.C if C is None else C
         s = nat.BnBwd()
-        s.partials = self.ws.partials.data_ptr()
-        s.counter = self.ws.counter.data_ptr()
+        ws = Workspace.get(self.dev)     # of the stream this launch goes to
+        s.partials = ws.partials.data_ptr()
+        s.counter = ws.counter.data_ptr()
         f4 = 4
         if bn.single:
             mi, off = 0, c0
@@ -816,13 +820,22 @@ def _bf16_operand(w, own, shape):
     return mirror.view(shape)
 
 
+MAX_PLANS_PER_BLOCK = 2   # e.g. the training batch and the validation / calibration batch
+
+
 def _plan_for(block, x):
+    """BlockPlan (intermediates + argument structs) of `block` for this input shape.  At most
+    MAX_PLANS_PER_BLOCK shapes are kept per block, least recently used first out: a partial last
+    batch or another evaluation resolution no longer pins a whole extra activation set for ever
+    (ADVICE r1)."""
     plans = block.__dict__.setdefault("_yamb_plans", {})
     key = (tuple(x.shape), x.device.index)
-    p = plans.get(key)
+    p = plans.pop(key, None)
     if p is None:
         p = BlockPlan(block, x)
-        plans[key] = p
+        while len(plans) >= MAX_PLANS_PER_BLOCK:
+            plans.pop(next(iter(plans)))        # dicts keep insertion order: oldest first
+    plans[key] = p                              # (re-)insert as most recent
     return p
 
 
@@ -1198,7 +1211,8 @@ class _BnActFn(torch.autograd.Function):
         hm = h.permute(0, 2, 3, 1).reshape(M, Cc)        # view of the channels_last storage
         if b.batch_stats:
             f = nat.BnFwd()
-            f.partials, f.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+            ws = Workspace.get(h.device)
+            f.partials, f.counter = ws.partials.data_ptr(), ws.counter.data_ptr()
             f.gamma, f.beta = nat.ptr(bn.weight), nat.ptr(bn.bias)
             f.eps, f.momentum = b.eps, b.momentum_value()
             if bn.track_running_stats and bn.running_mean is not None:
@@ -1253,7 +1267,8 @@ class _BnActFn(torch.autograd.Function):
             st.gbuf[1].zero_()
             dg, db = st.gbuf
         g = nat.BnBwd()
-        g.partials, g.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+        ws = Workspace.get(h.device)
+        g.partials, g.counter = ws.partials.data_ptr(), ws.counter.data_ptr()
         g.gamma = nat.ptr(bn.weight)
         g.mean, g.invstd = c_mean, c_invstd
         g.dgamma, g.dbeta = dg.data_ptr(), db.data_ptr()

@@ -77,7 +77,8 @@ class _PwConvBnActFn(torch.autograd.Function):
         g = _gemm(M, Cout, Cin, xm.data_ptr(), Cin, wbf.data_ptr(), Cin, h.data_ptr(), Cout)
         if b.batch_stats:
             f = nat.BnFwd()
-            f.partials, f.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+            ws = engine.Workspace.get(x.device)
+            f.partials, f.counter = ws.partials.data_ptr(), ws.counter.data_ptr()
             f.gamma, f.beta = nat.ptr(bn.weight), nat.ptr(bn.bias)
             f.eps, f.momentum = b.eps, b.momentum_value()
             if bn.track_running_stats and bn.running_mean is not None:
@@ -134,7 +135,8 @@ class _PwConvBnActFn(torch.autograd.Function):
             dg, db, gw = st.gbuf[0], st.gbuf[1], st.g_own
         # BatchNorm-backward statistics of dz = dy * act'(z), then dh = ca*dz + cb*h + cc
         q = nat.BnBwd()
-        q.partials, q.counter = st.ws.partials.data_ptr(), st.ws.counter.data_ptr()
+        ws = engine.Workspace.get(x.device)
+        q.partials, q.counter = ws.partials.data_ptr(), ws.counter.data_ptr()
         q.gamma = nat.ptr(bn.weight)
         q.mean, q.invstd = c_mean, c_invstd
         q.dgamma, q.dbeta = dg.data_ptr(), db.data_ptr()
