@@ -149,8 +149,54 @@ def block(rnd, name="b3"):
     print("block summary written")
 
 
+def bench_launches(rnd):
+    """ncu launch list of `python bench.py --steps 2 --warmup 1` itself
+    (`ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv`): trimmed CSV +
+    per-class shares of the complete eager steps it contains (between two rmsprop launches)."""
+    path = os.path.join(SRC, rnd + "_launches_bench.csv")
+    if not os.path.exists(path):
+        return
+    hdr, body = read_ncu_csv(path)
+    col = {h: i for i, h in enumerate(hdr)}
+    rows = []
+    for r in body:
+        if len(r) < len(hdr) or r[col["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        unit = r[col["Metric Unit"]]
+        t = float(r[col["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(unit, 1)
+        rows.append((int(r[col["ID"]]), r[col["Kernel Name"]], t))
+    with open(os.path.join(OUT, rnd + "_launches_bench.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["id", "class", "kernel", "time_us"])
+        for lid, name, t in rows:
+            w.writerow([lid, tag_of(name), name[:70], round(t, 2)])
+    ends = [i for i, (_, n, _) in enumerate(rows) if "rmsprop" in n]
+    agg, nsteps = {}, 0
+    for a, b in zip(ends[:-1], ends[1:]):
+        nsteps += 1
+        for _, n, t in rows[a + 1:b + 1]:
+            g = agg.setdefault(tag_of(n), [0, 0.0])
+            g[0] += 1
+            g[1] += t
+    if not nsteps:
+        return
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(OUT, rnd + "_launches_bench_summary.md"), "w") as f:
+        f.write("# %s — kernel launches of `python bench.py --steps 2 --warmup 1` under ncu\n\n" % rnd)
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv` -> "
+                "`%s_launches_bench.csv` (%d launches).  Below: the %d complete steps between "
+                "consecutive `rmsprop` launches, %.2f ms of kernel time per step (serialised, "
+                "cold-cache: compare the SHARES with the `kernels` block of the bench line).\n\n"
+                % (rnd, len(rows), nsteps, tot / nsteps / 1e3))
+        f.write("| class | launches/step | ms/step | share |\n|---|---|---|---|\n")
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+            f.write("| %s | %.1f | %.3f | %.1f %% |\n" % (k, n / nsteps, t / nsteps / 1e3, 100 * t / tot))
+    print("bench launch summary written:", nsteps, "steps")
+
+
 if __name__ == "__main__":
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
     step(rnd)
     for b in ("b1", "b2", "b3", "b8", "b15"):
         block(rnd, b)
+    bench_launches(rnd)

@@ -60,24 +60,30 @@ __global__ void __launch_bounds__(256) se_fc_fwd_kernel(const __grid_constant__ 
   }
 }
 
-// per-sample chain of the backward
+// per-sample chain of the backward, kSeS samples per CTA: every weight element fetched from L2 is
+// used for kSeS samples (one sample per CTA re-read both weight matrices per sample — 256 MB of L2
+// traffic and ~1000 dependent load batches per SE block of AtomNAS-C+, 225 us)
+constexpr int kSeS = 4;
 __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_constant__ yamb_se_fc_grad a) {
   extern __shared__ float sf[];
-  float* s_dt = sf;           // [C]
-  float* s_du = sf + a.C;     // [R]
-  const int n = blockIdx.x, tid = threadIdx.x;
-  for (int c = tid; c < a.C; c += 256) {
-    const float g = a.gate[(size_t)n * a.C + c];
-    const float dt = a.dgate[(size_t)n * a.C + c] * g * (1.f - g);
-    s_dt[c] = dt;
-    a.dt[(size_t)n * a.C + c] = dt;
+  float* s_dt = sf;                    // [kSeS][C]
+  float* s_du = sf + kSeS * a.C;       // [kSeS][R]
+  const int n0 = blockIdx.x * kSeS, tid = threadIdx.x;
+  const int ns = min(kSeS, a.N - n0);
+  for (int e = tid; e < kSeS * a.C; e += 256) {
+    const int s = e / a.C, c = e - s * a.C;
+    float dt = 0.f;
+    if (s < ns) {
+      const float g = a.gate[(size_t)(n0 + s) * a.C + c];
+      dt = a.dgate[(size_t)(n0 + s) * a.C + c] * g * (1.f - g);
+      a.dt[(size_t)(n0 + s) * a.C + c] = dt;
+    }
+    s_dt[e] = dt;
   }
+  for (int e = tid; e < kSeS * a.R; e += 256) s_du[e] = 0.f;
   __syncthreads();
-  // dv[j] = sum_c dt[c] * W_e[c][j]: consecutive threads own consecutive columns j (coalesced rows
-  // of W_e) and the C-long sum is split over the P = 256 / R' thread groups, 4 loads in flight each
-  // (one thread per j walked all C rows alone: ~170 us of exposed L2 latency per SE block)
-  for (int j = tid; j < a.R; j += 256) s_du[j] = 0.f;
-  __syncthreads();
+  // dv[s][j] = sum_c dt[s][c] * W_e[c][j]: consecutive threads own consecutive columns j (coalesced
+  // rows of W_e); the C-long sum is split over the P = 256 / R' thread groups
   {
     int Rp = 32;
     while (Rp < a.R && Rp < 256) Rp <<= 1;          // columns per pass, power of two <= 256
@@ -85,37 +91,42 @@ __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_cons
     for (int j0 = 0; j0 < a.R; j0 += Rp) {
       const int j = j0 + (tid % Rp);
       if (j < a.R) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int c = part;
-        for (; c + 3 * P < a.C; c += 4 * P) {
-          a0 = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], a0);
-          a1 = fmaf(s_dt[c + P], a.w_e[(size_t)(c + P) * a.R + j], a1);
-          a2 = fmaf(s_dt[c + 2 * P], a.w_e[(size_t)(c + 2 * P) * a.R + j], a2);
-          a3 = fmaf(s_dt[c + 3 * P], a.w_e[(size_t)(c + 3 * P) * a.R + j], a3);
+        float acc[kSeS];
+#pragma unroll
+        for (int s = 0; s < kSeS; ++s) acc[s] = 0.f;
+#pragma unroll 4
+        for (int c = part; c < a.C; c += P) {
+          const float w = a.w_e[(size_t)c * a.R + j];
+#pragma unroll
+          for (int s = 0; s < kSeS; ++s) acc[s] = fmaf(s_dt[s * a.C + c], w, acc[s]);
         }
-        for (; c < a.C; c += P) a0 = fmaf(s_dt[c], a.w_e[(size_t)c * a.R + j], a0);
-        atomicAdd(&s_du[j], (a0 + a1) + (a2 + a3));
+#pragma unroll
+        for (int s = 0; s < kSeS; ++s) atomicAdd(&s_du[s * a.R + j], acc[s]);
       }
     }
   }
   __syncthreads();
-  for (int j = tid; j < a.R; j += 256) {
-    const float du = s_du[j] * act_bwd(a.u[(size_t)n * a.R + j], a.act);
-    s_du[j] = du;
-    a.du[(size_t)n * a.R + j] = du;
+  for (int e = tid; e < kSeS * a.R; e += 256) {
+    const int s = e / a.R, j = e - s * a.R;
+    float du = 0.f;
+    if (s < ns) {
+      du = s_du[e] * act_bwd(a.u[(size_t)(n0 + s) * a.R + j], a.act);
+      a.du[(size_t)(n0 + s) * a.R + j] = du;
+    }
+    s_du[e] = du;
   }
   __syncthreads();
   for (int c = tid; c < a.C; c += 256) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int j = 0;
-    for (; j + 3 < a.R; j += 4) {
-      a0 = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], a0);
-      a1 = fmaf(s_du[j + 1], a.w_r[(size_t)(j + 1) * a.C + c], a1);
-      a2 = fmaf(s_du[j + 2], a.w_r[(size_t)(j + 2) * a.C + c], a2);
-      a3 = fmaf(s_du[j + 3], a.w_r[(size_t)(j + 3) * a.C + c], a3);
+    float acc[kSeS];
+#pragma unroll
+    for (int s = 0; s < kSeS; ++s) acc[s] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < a.R; ++j) {
+      const float w = a.w_r[(size_t)j * a.C + c];
+#pragma unroll
+      for (int s = 0; s < kSeS; ++s) acc[s] = fmaf(s_du[s * a.R + j], w, acc[s]);
     }
-    for (; j < a.R; ++j) a0 = fmaf(s_du[j], a.w_r[(size_t)j * a.C + c], a0);
-    a.dpool[(size_t)n * a.C + c] = ((a0 + a1) + (a2 + a3)) * a.inv_hw;
+    for (int s = 0; s < ns; ++s) a.dpool[(size_t)(n0 + s) * a.C + c] = acc[s] * a.inv_hw;
   }
 }
 
@@ -167,8 +178,16 @@ int se_fc_bwd_launch(const yamb_se_fc_grad* a, cudaStream_t st) {
   if (!a->dgate || !a->gate || !a->u || !a->v || !a->pooled || !a->w_r || !a->w_e || !a->dpool ||
       !a->dt || !a->du || !a->g_wr || !a->g_br || !a->g_we || !a->g_be)
     return set_error(YAMB_EINVAL, "se_fc bwd: null pointer");
-  se_fc_bwd_sample_kernel<<<a->N, 256, (a->C + a->R) * sizeof(float), st>>>(*a);
-  cudaError_t e = cudaGetLastError();
+  const size_t smem = (size_t)kSeS * (a->C + a->R) * sizeof(float);
+  static size_t attr = 0;   // process-wide: only ever raise the limit
+  cudaError_t e;
+  if (smem > attr && smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(se_fc_bwd_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_fc bwd attr: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  se_fc_bwd_sample_kernel<<<(a->N + kSeS - 1) / kSeS, 256, smem, st>>>(*a);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_fc bwd: %s", cudaGetErrorString(e));
   const long long total = (long long)a->C * a->R;
   long long blocks = (total + 255) / 256;

@@ -126,6 +126,14 @@ class AllReduceDistributedDataParallel(nn.Module):
             states += [b.data for b in self.module.buffers()]
         for t in states:
             dist.broadcast(t, 0)
+        # the broadcast wrote the fp32 masters through detached views: if a fused optimizer already
+        # keeps a bf16 mirror of them (the tensor-core operand), re-cast it now
+        with torch.no_grad():
+            for p in self.module.parameters():
+                mirror = getattr(p, "_yamb_bf16", None)
+                if mirror is not None:
+                    mirror.copy_(p)
+                    p._yamb_bf16_version = p._version
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)

@@ -288,6 +288,7 @@ class BlockPlan:
         self.g_proj = _f32(Cout * Chid, dev).view(Cout, Chid)
         self.g_dw = [torch.zeros_like(c.weight, dtype=torch.float32) for c in self.conv_dw]
         self.generation = 0
+        self.pinned = False
         self._keep = []
 
     # -- helpers -------------------------------------------------------------------------------
@@ -833,8 +834,13 @@ def _plan_for(block, x):
     p = plans.pop(key, None)
     if p is None:
         p = BlockPlan(block, x)
-        while len(plans) >= MAX_PLANS_PER_BLOCK:
-            plans.pop(next(iter(plans)))        # dicts keep insertion order: oldest first
+        # dicts keep insertion order: oldest first.  A plan whose buffers a captured CUDA graph
+        # addresses is never evicted (the graph holds raw pointers).
+        for k in [k for k, q in plans.items() if not q.pinned][:max(0, len(plans) + 1 -
+                                                                   MAX_PLANS_PER_BLOCK)]:
+            plans.pop(k)
+    if torch.cuda.is_current_stream_capturing():
+        p.pinned = True
     plans[key] = p                              # (re-)insert as most recent
     return p
 
