@@ -61,9 +61,9 @@ __global__ void __launch_bounds__(256) se_fc_fwd_kernel(const __grid_constant__ 
 }
 
 // per-sample chain of the backward, kSeS samples per CTA: every weight element fetched from L2 is
-// used for kSeS samples (one sample per CTA re-read both weight matrices per sample — 256 MB of L2
+// used for kSeS samples, 16 weight loads in flight per thread (one sample per CTA re-read both weight matrices per sample — 256 MB of L2
 // traffic and ~1000 dependent load batches per SE block of AtomNAS-C+, 225 us)
-constexpr int kSeS = 4;
+constexpr int kSeS = 2;
 __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_constant__ yamb_se_fc_grad a) {
   extern __shared__ float sf[];
   float* s_dt = sf;                    // [kSeS][C]
@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_cons
         float acc[kSeS];
 #pragma unroll
         for (int s = 0; s < kSeS; ++s) acc[s] = 0.f;
-#pragma unroll 4
-        for (int c = part; c < a.C; c += P) {
+#pragma unroll 16
+        for (int c = part; c < a.C; c += P) {      // 16 independent weight loads in flight
           const float w = a.w_e[(size_t)c * a.R + j];
 #pragma unroll
           for (int s = 0; s < kSeS; ++s) acc[s] = fmaf(s_dt[s * a.C + c], w, acc[s]);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_sample_kernel(const __grid_cons
     float acc[kSeS];
 #pragma unroll
     for (int s = 0; s < kSeS; ++s) acc[s] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int j = 0; j < a.R; ++j) {
       const float w = a.w_r[(size_t)j * a.C + c];
 #pragma unroll
