@@ -52,7 +52,7 @@ typedef void* yamb_stream_t; /* cudaStream_t */
  *   momentum < 0  => momentum=None in PyTorch: cumulative average with factor 1/num_batches_tracked
  *   (utils/common.py:175-187 bn_calibration). */
 typedef struct yamb_bn_fwd {
-  float* partials;              /* accumulator, >= 2*C floats, ZERO on entry, returned to zero */
+  double* partials;             /* accumulator, >= 2*C doubles, ZERO on entry, returned to zero */
   uint32_t* counter;            /* one zero-initialised word, self-resetting */
   const float* gamma;           /* [C] or NULL (=1) */
   const float* beta;            /* [C] or NULL (=0) */
@@ -71,7 +71,7 @@ typedef struct yamb_bn_fwd {
 /* Backward of the same BN: given sum(dz), sum(dz*xhat) produce dgamma, dbeta (ACCUMULATED into the
  * gradient buffers) and the affine form of the input gradient  dh = ca*dz + cb*h + cc. */
 typedef struct yamb_bn_bwd {
-  float* partials;
+  double* partials;
   uint32_t* counter;
   const float* gamma;  /* [C] or NULL */
   const float* mean;   /* [C] saved by forward */

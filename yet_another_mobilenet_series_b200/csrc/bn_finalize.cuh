@@ -1,9 +1,15 @@
 // Per-channel statistics plumbing shared by every producer kernel (pointwise GEMM, depthwise).
 //
-// A producer CTA accumulates per-channel partial sums in registers / shared memory, adds them to the
-// global accumulator partials[stat][C] with fire-and-forget fp32 reductions (red.global.add — a
-// serial reduction of a [CTAs][2][C] table by the last CTA cost 15-30 us per BatchNorm, measured),
-// and the LAST CTA to finish (threadfence + counter) reads the 2C totals, returns the accumulator
+// A producer CTA accumulates per-channel partial sums in registers (fp32, fixed order) and hands
+// them on through shared memory and the global accumulator partials[stat][C] with fire-and-forget
+// reductions (red.add — a serial reduction of a [CTAs][2][C] table by the last CTA cost 15-30 us
+// per BatchNorm, measured).  Everything that crosses warps or CTAs is accumulated in DOUBLE
+// (stat_t): the order of those additions is not fixed, and in fp32 their reordering changed the
+// BatchNorm coefficients in the last bits, which bf16 rounding flips downstream amplified to a
+// 1e-3 run-to-run difference of the loss; fp64 sums of fp32 partials are reproducible to 1e-16
+// relative, i.e. the fp32 mean / invstd they are rounded to are the same bits run after run
+// (barring an exact rounding tie).  It also takes the E[x^2]-mean^2 cancellation out of fp32.
+// The LAST CTA to finish (threadfence + counter) reads the 2C totals, returns the accumulator
 // to zero (it must be zero on entry) and runs the BatchNorm bookkeeping of nn.BatchNorm2d
 // (reference: models/mobilenet_base.py:203,417 -> torch.nn.BatchNorm2d semantics):
 //   forward : mean / biased var -> scale, shift (what the consumer kernel applies), saved
@@ -17,6 +23,8 @@
 #include "../../include/yamb200.h"
 
 namespace yamb {
+
+typedef double stat_t;   // cross-warp / cross-CTA statistics accumulator
 
 // Count this CTA as finished; true in the LAST CTA of the grid (whose later reads see every other
 // CTA's earlier global reductions).  Must be called by ALL threads of the CTA.
@@ -35,19 +43,19 @@ __device__ __forceinline__ bool arrive_last(uint32_t* counter) {
 
 // Add this CTA's partials (s_part: [2][C] in shared memory) to the global accumulator and return
 // true in the last CTA.  Must be called by ALL threads of the CTA.
-__device__ __forceinline__ bool publish_partials(const float* s_part, int C, float* partials,
+__device__ __forceinline__ bool publish_partials(const stat_t* s_part, int C, stat_t* partials,
                                                  uint32_t* counter) {
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float v = s_part[i];
-    if (v != 0.f) atomicAdd(partials + i, v);  // result unused -> RED.E.ADD.F32
+    stat_t v = s_part[i];
+    if (v != 0.0) atomicAdd(partials + i, v);  // result unused -> RED.E.ADD.F64
   }
   return arrive_last(counter);
 }
 
 // Read-and-clear one total (L2 is the point of coherence for the reductions above).
-__device__ __forceinline__ float take_total(float* p) {
-  float v = __ldcg(p);
-  __stcg(p, 0.f);
+__device__ __forceinline__ double take_total(stat_t* p) {
+  double v = __ldcg(p);
+  __stcg(p, 0.0);
   return v;
 }
 
@@ -61,7 +69,7 @@ __device__ __forceinline__ void bn_fwd_finalize(const yamb_bn_fwd& f, int C) {
     if (threadIdx.x == 0) *f.num_batches_tracked = nbt;
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = (double)take_total(f.partials + c), q = (double)take_total(f.partials + C + c);
+    double s = take_total(f.partials + c), q = take_total(f.partials + C + c);
     double mean = s * inv_count;
     double var = q * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -84,7 +92,7 @@ __device__ __forceinline__ void bn_fwd_finalize(const yamb_bn_fwd& f, int C) {
 __device__ __forceinline__ void bn_bwd_finalize(const yamb_bn_bwd& f, int C) {
   const double inv_count = 1.0 / (double)f.count;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = (double)take_total(f.partials + c), q = (double)take_total(f.partials + C + c);
+    double s = take_total(f.partials + c), q = take_total(f.partials + C + c);
     // s = sum(dz), q = sum(dz * xhat)
     if (f.dgamma) f.dgamma[c] += (float)q;
     if (f.dbeta) f.dbeta[c] += (float)s;

@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_fwd_
   constexpr int TILE_ELEMS = NPIX * CT;    // bf16 elements per staging buffer
   extern __shared__ __align__(16) float smem_f[];
   __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(smem_f);  // [2][TILE_ELEMS]
-  float* s_part = smem_f + TILE_ELEMS;     // [2][CT] statistics of the current channel chunk
+  stat_t* s_part = reinterpret_cast<stat_t*>(smem_f + TILE_ELEMS);  // [2][CT] statistics of the current chunk (double)
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.f;
+  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.0;
   const ActParam ap = make_act(p.in_scale ? p.in_act : ACT_NONE);
   const bool identity = p.in_scale == nullptr;
   const int cg = tid % NCG;
@@ -188,17 +188,17 @@ __global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_fwd_
         b += __shfl_xor_sync(0xffffffffu, b, 16);
       }
       if ((tid & 31) < NCG) {
-        atomicAdd(&s_part[cg * 4 + v], a);
-        atomicAdd(&s_part[CT + cg * 4 + v], b);
+        atomicAdd(&s_part[cg * 4 + v], (stat_t)a);
+        atomicAdd(&s_part[CT + cg * 4 + v], (stat_t)b);
       }
       ssum[v] = ssq[v] = 0.f;
     }
     __syncthreads();
     if (tid < 2 * CT) {
       const int c = chunk * CT + (tid % CT);
-      const float v = s_part[tid];
-      if (c < p.C && v != 0.f) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
-      s_part[tid] = 0.f;
+      const stat_t v = s_part[tid];
+      if (c < p.C && v != 0.0) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
+      s_part[tid] = 0.0;
     }
     __syncthreads();
   };
@@ -422,10 +422,10 @@ __global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_bwd_
   float* s_tab = smem_f + BUF_ELEMS;         // [7][CT]: in_scale, in_shift, ca, cb, cc, mean, invstd
   float* s_w = s_tab + 7 * CT;               // [K*K][CT]
   float* s_gw = s_w + KK * CT;               // [K*K][CT]
-  float* s_part = s_gw + KK * CT;            // [2][CT]
+  stat_t* s_part = reinterpret_cast<stat_t*>(s_gw + KK * CT);   // [2][CT], double
   const int tid = threadIdx.x;
   for (int i = tid; i < KK * CT; i += 256) s_gw[i] = 0.f;
-  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.f;
+  for (int i = tid; i < 2 * CT; i += 256) s_part[i] = 0.0;
   const int act = p.in_scale ? p.in_act : ACT_NONE;
   const ActParam ap = make_act(act);
   const int cg = tid % NCG;
@@ -456,8 +456,8 @@ __global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_bwd_
     if (DGRAD) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        atomicAdd(&s_part[cg * 4 + v], ssum[v]);
-        atomicAdd(&s_part[CT + cg * 4 + v], ssq[v]);
+        atomicAdd(&s_part[cg * 4 + v], (stat_t)ssum[v]);
+        atomicAdd(&s_part[CT + cg * 4 + v], (stat_t)ssq[v]);
         ssum[v] = ssq[v] = 0.f;
       }
     }
@@ -471,9 +471,9 @@ __global__ void __launch_bounds__(256, (K == 3 ? YAMB_DW_MINBLOCKS : 1)) dw_bwd_
     }
     if (DGRAD && p.has_bn && tid < 2 * CT) {
       const int c = cbase + tid % CT;
-      const float v = s_part[tid];
-      if (c < p.C && v != 0.f) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
-      s_part[tid] = 0.f;
+      const stat_t v = s_part[tid];
+      if (c < p.C && v != 0.0) atomicAdd(p.bn.partials + (tid / CT) * p.C + c, v);
+      s_part[tid] = 0.0;
     }
     __syncthreads();
   };
@@ -844,7 +844,7 @@ int dw_fwd_launch(const yamb_dw_fwd* a, cudaStream_t st) {
     p.num_tiles = (int)nt;
   }
   const int ih = (toh - 1) * s + k, iw = (tow - 1) * s + k;
-  const size_t smem = (size_t)ih * iw * ct * sizeof(float) + 2 * (size_t)ct * sizeof(float);
+  const size_t smem = (size_t)ih * iw * ct * sizeof(float) + 2 * (size_t)ct * sizeof(stat_t);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise fwd: tile too large");
   cudaError_t e;
 #define YAMB_FWD_CASE(KK, SS, CC, TT) \
@@ -895,7 +895,8 @@ int dw_bwd_launch(const yamb_dw_bwd* a, cudaStream_t st) {
   }
   // two staging buffers of bf16 {dz, h over the region; x over the tile} + fp32 tables
   const size_t smem =
-      ((size_t)(2 * rh * rw + tih * tiw) * ct + (size_t)(7 + 2 * k * k + 2) * ct) * sizeof(float);
+      ((size_t)(2 * rh * rw + tih * tiw) * ct + (size_t)(7 + 2 * k * k) * ct) * sizeof(float) +
+      2 * (size_t)ct * sizeof(stat_t);
   if (smem > 220 * 1024) return set_error(YAMB_EINVAL, "depthwise bwd: slice too wide for smem");
   cudaError_t e;
   if (k == 3 && s == 1 && ct == 64) YAMB_DW_BWD(3, 1, 64, p, smem, p.num_tiles, st);

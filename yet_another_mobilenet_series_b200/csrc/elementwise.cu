@@ -23,6 +23,40 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
                     pack_bf16(v[6], v[7]));
 }
 
+// Merge the per-thread partial sums (s, q: 8 channels each) of the threads of a CTA that own the
+// same 8-channel group (tid = px * CG + cg, px < PX) into the CTA's statistics slots WITHOUT
+// atomics: staged through shared memory and summed in pixel-lane order by the px == 0 thread, in
+// double.  (Shared-memory double atomics are CAS loops; PX threads contending for every slot cost
+// bn_reduce 20 %.)  Must be called by ALL threads of the CTA; `active` = this thread holds sums.
+__device__ __forceinline__ void cta_stats_merge(stat_t* s_part, int C, int CG, int PX, int cg, int px,
+                                                bool active, const float (&s)[8],
+                                                const float (&q)[8]) {
+  __shared__ float red[256][17];
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[threadIdx.x][e] = s[e];
+      red[threadIdx.x][8 + e] = q[e];
+    }
+  }
+  __syncthreads();
+  if (active && px == 0) {
+    const int c0 = cg * 8;
+    const int base = threadIdx.x;              // = cg (relative to this pass) when px == 0
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      stat_t a = 0.0, b = 0.0;
+      for (int j = 0; j < PX; ++j) {
+        a += (stat_t)red[base + j * CG][e];
+        b += (stat_t)red[base + j * CG][8 + e];
+      }
+      s_part[c0 + e] += a;
+      s_part[C + c0 + e] += b;
+    }
+  }
+  __syncthreads();
+}
+
 struct BnApplyDev {
   long long M;
   int C, ldh, ldr, ldy;
@@ -90,18 +124,22 @@ struct BnReduceDev {
 
 // sum(dy), sum(dy * xhat) with xhat = (h - mean) * invstd; thread owns one 8-channel group.
 __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ BnReduceDev p) {
-  extern __shared__ float s_part[];  // [2][C]
+  extern __shared__ stat_t s_part[];  // [2][C], double
   const int CG = p.C / 8;
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.0;
   __syncthreads();
   // channel groups beyond 256 are covered by looping cg
   for (int cgb = 0; cgb < CG; cgb += 256) {
     const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
     const int px = CG >= 256 ? 0 : threadIdx.x / CG;
-    if (cg < CG && px < PX) {
+    const bool active = cg < CG && px < PX;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    if (active) {
       const int c0 = cg * 8;
-      float mu[8], rs[8], s[8], q[8], zs[8], zt[8];
+      float mu[8], rs[8], zs[8], zt[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         mu[e] = __ldg(p.bn.mean + c0 + e);
@@ -144,12 +182,8 @@ __global__ void __launch_bounds__(256) bn_reduce_kernel(const __grid_constant__ 
           }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s_part[c0 + e], s[e]);
-        atomicAdd(&s_part[p.C + c0 + e], q[e]);
-      }
     }
+    cta_stats_merge(s_part, p.C, CG >= 256 ? 256 : CG, PX, cg, px, active, s, q);
   }
   __syncthreads();
   if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
@@ -168,19 +202,20 @@ struct BnStatsDev {
   yamb_bn_fwd bn;
 };
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __grid_constant__ BnStatsDev p) {
-  extern __shared__ float s_part[];  // [2][C]
+  extern __shared__ stat_t s_part[];  // [2][C], double
   const int CG = p.C / 8;
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.0;
   __syncthreads();
   for (int cgb = 0; cgb < CG; cgb += 256) {
     const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
     const int px = CG >= 256 ? 0 : threadIdx.x / CG;
-    if (cg < CG && px < PX) {
-      const int c0 = cg * 8;
-      float s[8], q[8];
+    const bool active = cg < CG && px < PX;
+    float s[8], q[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    if (active) {
+      const int c0 = cg * 8;
       const long long rstep = (long long)gridDim.x * PX;
       for (long long row = (long long)blockIdx.x * PX + px; row < p.M; row += 4 * rstep) {
         uint4 uh[4];
@@ -201,12 +236,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __grid_constant__ B
           }
         }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s_part[c0 + e], s[e]);
-        atomicAdd(&s_part[p.C + c0 + e], q[e]);
-      }
     }
+    cta_stats_merge(s_part, p.C, CG >= 256 ? 256 : CG, PX, cg, px, active, s, q);
   }
   __syncthreads();
   if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
@@ -370,18 +401,22 @@ struct SeBwdApplyDev {
   yamb_bn_bwd bn;
 };
 __global__ void __launch_bounds__(256) se_bwd_apply_kernel(const __grid_constant__ SeBwdApplyDev p) {
-  extern __shared__ float s_part[];  // [2][C]
+  extern __shared__ stat_t s_part[];  // [2][C], double
   const int CG = p.C / 8;
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
-  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * p.C; i += blockDim.x) s_part[i] = 0.0;
   __syncthreads();
   const ActParam ap = make_act(p.act);
   for (int cgb = 0; cgb < CG; cgb += 256) {
     const int cg = cgb + (CG >= 256 ? threadIdx.x : threadIdx.x % CG);
     const int px = CG >= 256 ? 0 : threadIdx.x / CG;
-    if (cg < CG && px < PX) {
+    const bool active = cg < CG && px < PX;
+    float s[8], q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+    if (active) {
       const int c0 = cg * 8;
-      float sc[8], sh[8], mu[8], rs[8], s[8], q[8];
+      float sc[8], sh[8], mu[8], rs[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         sc[e] = __ldg(p.scale + c0 + e); sh[e] = __ldg(p.shift + c0 + e);
@@ -415,12 +450,8 @@ __global__ void __launch_bounds__(256) se_bwd_apply_kernel(const __grid_constant
           q[e] = fmaf(r[e], (hv[e] - mu[e]) * rs[e], q[e]);
         }
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s_part[c0 + e], s[e]);
-        atomicAdd(&s_part[p.C + c0 + e], q[e]);
-      }
     }
+    cta_stats_merge(s_part, p.C, CG >= 256 ? 256 : CG, PX, cg, px, active, s, q);
   }
   __syncthreads();
   if (publish_partials(s_part, p.C, p.bn.partials, p.bn.counter)) {
@@ -461,7 +492,7 @@ int bn_reduce_launch(const yamb_bn_reduce* a, cudaStream_t st) {
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
   long long want = (a->M + PX - 1) / PX;
   int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
-  bn_reduce_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  bn_reduce_kernel<<<grid, 256, 2 * a->C * sizeof(stat_t), st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_reduce: %s", cudaGetErrorString(e));
   return 0;
@@ -478,7 +509,7 @@ int bn_stats_launch(const yamb_bn_stats* a, cudaStream_t st) {
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
   long long want = (a->M + PX - 1) / PX;
   int grid = (int)(want < (long long)4 * max_ctas() ? want : 4 * max_ctas());
-  bn_stats_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  bn_stats_kernel<<<grid, 256, 2 * a->C * sizeof(stat_t), st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "bn_stats: %s", cudaGetErrorString(e));
   return 0;
@@ -579,7 +610,7 @@ int se_bwd_apply_launch(const yamb_se_bwd_apply* a, cudaStream_t st) {
   const int PX = 256 / CG > 0 ? 256 / CG : 1;
   long long want = (a->M + PX - 1) / PX;
   int grid = (int)(want < (long long)2 * max_ctas() ? want : 2 * max_ctas());
-  se_bwd_apply_kernel<<<grid, 256, 2 * a->C * sizeof(float), st>>>(p);
+  se_bwd_apply_kernel<<<grid, 256, 2 * a->C * sizeof(stat_t), st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "se_bwd_apply: %s", cudaGetErrorString(e));
   return 0;

@@ -268,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   Bars* bars = reinterpret_cast<Bars*>(smem + p.off_bars);
-  float* s_stats = reinterpret_cast<float*>(smem + p.off_stats);  // [2][N]
+  stat_t* s_stats = reinterpret_cast<stat_t*>(smem + p.off_stats);  // [2][N], double
   float* s_coef = reinterpret_cast<float*>(smem + p.off_coef);
 
   const int warp = threadIdx.x >> 5;
@@ -297,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   // zero the per-CTA statistics accumulators
   if (p.has_bnf || p.has_bnb) {
-    for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) s_stats[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -737,10 +737,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 default: racc[3][0] += s0; racc[3][1] += s1; racc[3][2] += q0; racc[3][3] += q1; break;
               }
             } else {
-              atomicAdd(&s_stats[c], s0);
-              atomicAdd(&s_stats[c + 1], s1);
-              atomicAdd(&s_stats[p.N + c], q0);
-              atomicAdd(&s_stats[p.N + c + 1], q1);
+              atomicAdd(&s_stats[c], (stat_t)s0);
+              atomicAdd(&s_stats[c + 1], (stat_t)s1);
+              atomicAdd(&s_stats[p.N + c], (stat_t)q0);
+              atomicAdd(&s_stats[p.N + c + 1], (stat_t)q1);
             }
           }
           __syncwarp();  // s_h / sO reads done before the next sub-tile overwrites them
@@ -760,10 +760,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < 4; ++j) {
         const int c = j * 64 + 2 * lane;
         if (c < p.N) {
-          atomicAdd(&s_stats[c], racc[j][0]);
-          atomicAdd(&s_stats[c + 1], racc[j][1]);
-          atomicAdd(&s_stats[p.N + c], racc[j][2]);
-          atomicAdd(&s_stats[p.N + c + 1], racc[j][3]);
+          atomicAdd(&s_stats[c], (stat_t)racc[j][0]);
+          atomicAdd(&s_stats[c + 1], (stat_t)racc[j][1]);
+          atomicAdd(&s_stats[p.N + c], (stat_t)racc[j][2]);
+          atomicAdd(&s_stats[p.N + c + 1], (stat_t)racc[j][3]);
         }
       }
     }
@@ -1140,7 +1140,7 @@ int gemm_launch(const yamb_gemm* a, cudaStream_t stream) {
   // every epilogue warp stages its own 32 x 64 sub-tile: 2 buffers each unless smem is short
   const int side_bytes = (a->epi == 1) ? kEpiWarps * kWarpOutBytes : 0;  // raw H rows (epi 1)
   const int coef_bytes = ((a->epi == 1 ? 4 * p.N : 0) + 3 * Ca + 3 * Cb) * 4;
-  const int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * 4 : 0;
+  const int stats_bytes = (p.has_bnf || p.has_bnb) ? 2 * p.N * (int)sizeof(stat_t) : 0;
   const int budget = 232448 - 2048;  // 227 KB minus the kernel's static shared memory
   int stages = 0, out_bytes = 0;
   for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
