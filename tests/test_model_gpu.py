@@ -159,11 +159,13 @@ def _restore(ts, model, st):
 
 def test_graph_replay_equals_eager(built_lib):
     """The SAME iteration (same state, same batch) run eagerly TWICE and once as a CUDA-graph
-    replay.  The kernels' fp32 reductions (BatchNorm statistics, split-K weight gradients) are
-    order-free atomics: a 1e-7 change of a BatchNorm scale flips bf16 roundings downstream, so two
-    runs of the same iteration differ by the bf16 budget itself (measured on B200: loss 1.6e-3,
-    the RMSprop-normalised parameter update 0.2 rel-L2 at this toy size).  The graph replay must
-    sit inside that run-to-run noise: no further from an eager run than a second eager run is."""
+    replay.  Everything that crosses warps or CTAs in the BatchNorm statistics is accumulated in
+    double (csrc/bn_finalize.cuh), so the forward pass and every activation gradient are the same
+    bits run after run; the only order-dependent sums left are the fp32 split-K / depthwise
+    weight-gradient reductions (1e-7 relative).  Measured on B200: identical losses, parameter
+    update 4e-7 rel-L2 between two eager runs and between eager and replay.  (With fp32 statistics
+    atomics, round 1, two eager runs differed by 1.6e-3 in the loss and 0.2 in the update: bf16
+    rounding flips amplified the last-bit differences of the BatchNorm coefficients.)"""
     from yet_another_mobilenet_series_b200.trainer import TrainStep
     B = 32
     g = torch.Generator().manual_seed(0)
@@ -194,8 +196,9 @@ def test_graph_replay_equals_eager(built_lib):
     diff = _rel(p_g - st["p"], p_e - st["p"])
     print("eager-vs-eager update rel-L2 %.3e, graph-vs-eager %.3e; losses %r %r %r"
           % (noise, diff, loss_e, loss_e2, loss_g))
-    assert abs(loss_g - loss_e) < max(3 * abs(loss_e2 - loss_e), 2e-3 * abs(loss_e))
-    assert diff < max(3e-2, 1.5 * noise)
+    assert abs(loss_e2 - loss_e) <= 1e-6 * abs(loss_e)
+    assert abs(loss_g - loss_e) <= 1e-6 * abs(loss_e)
+    assert noise < 1e-4 and diff < 1e-4
     # replaying again advances the training (the graph is not a frozen snapshot)
     loss_next = float(ts(x, t))
     assert loss_next < loss_g
