@@ -350,6 +350,39 @@ int yamb_softmax_ce_bwd(const yamb_softmax_ce_grad* args, yamb_stream_t stream);
 int yamb_colsum_bf16(const void* X, int64_t M, int32_t C, int64_t ld, float* out,
                      yamb_stream_t stream);
 
+/* ---- eval-mode inverted-residual block, ONE launch, no intermediate in HBM -----------------------
+ * Replaces the forward of InvertedResidualChannels (reference models/mobilenet_base.py:446-451;
+ * single branch, expand=True, 3x3 depthwise, stride 1) when every BatchNorm uses its running
+ * statistics (model.eval(): validation / forward_loss under no_grad, common.py:67-80,
+ * train.py:273-309): x tile -> tcgen05 expand -> BN1+act -> 3x3 stencil -> BN2+act -> tcgen05
+ * project (accumulated over 64-channel slices of the hidden dimension) -> BN3 (+x) -> y.
+ * The BatchNorm folding scale = gamma*rsqrt(var+eps), shift = beta - mean*scale is done inside
+ * the kernel from the module's buffers (csrc/block_eval.cu).  Shapes it does not cover return
+ * YAMB_EINVAL; the caller then runs the four-launch sequence with folded coefficients. */
+typedef struct yamb_bn_eval {
+  const float* gamma;         /* [C] or NULL (=1) */
+  const float* beta;          /* [C] or NULL (=0) */
+  const float* running_mean;  /* [C] */
+  const float* running_var;   /* [C] */
+  float eps;
+} yamb_bn_eval;
+
+typedef struct yamb_block_eval {
+  int32_t N, H, W;            /* input pixels (NHWC); stride 1: the output has the same H, W */
+  int32_t Cin, Chid, Cout;    /* multiples of 8; Cin <= 256, Cout <= 320 */
+  int32_t kernel, stride;     /* 3, 1 */
+  int32_t act;                /* YAMB_ACT_* of the two inner activations */
+  int32_t residual;           /* y += x (needs Cin == Cout) */
+  const void* x;              /* bf16 [N,H,W,Cin] */
+  const void* w_expand;       /* bf16 [Chid][Cin] */
+  const float* w_dw;          /* fp32 [Chid][3][3] */
+  const void* w_project;      /* bf16 [Cout][Chid] */
+  yamb_bn_eval bn1, bn2, bn3; /* over Chid, Chid, Cout channels */
+  void* y;                    /* bf16 [N,H,W,Cout] */
+} yamb_block_eval;
+
+int yamb_block_eval_fwd(const yamb_block_eval* args, yamb_stream_t stream);
+
 /* ---- fused flat-arena RMSprop (+L2 decay, +DDP mean, +EMA, +bf16 repack) -------------------------
  * Replaces RMSprop.step (reference utils/rmsprop.py:67-129), the gradient of cal_l2_loss
  * (utils/optim.py:177-200; l2 * p added where bit 0 of wd_mask is set; bit 1 marks a parameter
@@ -380,7 +413,7 @@ int yamb_max_ctas(void);
 /* sizeof() of the ABI structs (0 bn_fwd, 1 bn_bwd, 2 gemm, 3 dw_fwd, 4 dw_bwd, 5 bn_apply,
  * 6 bn_reduce, 7 se_pool, 8 rmsprop, 9 se_bwd_reduce, 10 se_bwd_apply, 11 bn_stats,
  * 12 bn_bwd_apply, 13 nl_gram, 14 nl_rowmat, 15 se_fc, 16 se_fc_grad, 17 softmax_ce,
- * 18 softmax_ce_grad, 19 stem_conv) so bindings can self-check */
+ * 18 softmax_ce_grad, 19 stem_conv, 20 bn_eval, 21 block_eval) so bindings can self-check */
 int yamb_struct_size(int which);
 
 const char* yamb_last_error(void);

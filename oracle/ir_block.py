@@ -174,7 +174,11 @@ def _dw(a, w_list, channels, stride):
 def forward(x, cfg, P, training=True, quant=False):
     """y, saved.  x: [N,Cin,H,W] fp32.  `saved` holds every intermediate the backward needs plus
     the batch statistics (for the running-stat check)."""
-    q = quant
+    q = bool(quant)
+    # quant="fused": rounding points of the one-launch eval kernel (csrc/block_eval.cu), which keeps
+    # the raw convolution outputs h1 / h2 / h3 in fp32 (TMEM / registers) and rounds only the
+    # activations it stages as tensor-core operands and the block output
+    qr = quant is True
     S = {}
     x = _rnd(x, q)
     S["x"] = x
@@ -195,7 +199,7 @@ def forward(x, cfg, P, training=True, quant=False):
         return h * scale[None, :, None, None] + shift[None, :, None, None]
 
     if cfg.expand:
-        h1 = _rnd(F.conv2d(x, _rnd(P["w_exp"], q)[:, :, None, None]), q)
+        h1 = _rnd(F.conv2d(x, _rnd(P["w_exp"], q)[:, :, None, None]), qr)
         S["h1"] = h1
         a1 = _rnd(act_fwd(bn(h1, "bn1"), cfg.act), q)  # staged in shared memory as bf16
     else:
@@ -203,7 +207,7 @@ def forward(x, cfg, P, training=True, quant=False):
         a1 = x if len(cfg.channels) == 1 else torch.cat([x] * len(cfg.channels), 1)
     S["a1"] = a1
     h2_acc = _dw(a1, P["w_dw"], cfg.channels, cfg.stride)
-    h2 = _rnd(h2_acc, q)
+    h2 = _rnd(h2_acc, qr)
     S["h2"] = h2
     # the depthwise kernel takes the BN2 statistics from its fp32 accumulators, not from the
     # bf16 values it stores (a zero-mean 2^-9 rounding noise apart they are the same numbers)
@@ -218,7 +222,7 @@ def forward(x, cfg, P, training=True, quant=False):
         S.update(se_s=s, se_u=u, se_v=v, se_gate=gate)
         a2 = _rnd(a2 * gate[:, :, None, None], q)
         S["a2s"] = a2
-    h3 = _rnd(F.conv2d(a2, _rnd(P["w_proj"], q)[:, :, None, None]), q)
+    h3 = _rnd(F.conv2d(a2, _rnd(P["w_proj"], q)[:, :, None, None]), qr)
     S["h3"] = h3
     y = bn(h3, "bn3")
     if cfg.nl_c > 0:

@@ -198,3 +198,36 @@ def test_padded_shadow_flat_transfers_cpu():
     for (n, p), g in zip(blk.named_parameters(), grads):
         assert g.shape == p.shape
         assert torch.equal(g.reshape(-1), sh.maps[n].float()), n
+
+
+def test_kernel_scratch_does_not_travel_with_a_deepcopy():
+    """The EMA model is a deepcopy of the wrapper (reference common.py:164), possibly taken AFTER a
+    forward has cached per-module kernel scratch (device buffers, ctypes argument structs) in the
+    modules' __dict__: the copy must succeed and start without scratch."""
+    import copy
+    import pickle
+    from yet_another_mobilenet_series_b200 import engine, native, tail_ops
+
+    class Holder(engine.Scratch):
+        def __init__(self):
+            self.arg = native.Gemm()          # ctypes struct with pointers: not copyable
+
+    blk = mb.InvertedResidualChannels(16, 16, 1, [32], [3], True, active_fn=mb.get_active_fn("nn.ReLU"),
+                                      batch_norm_kwargs={"momentum": 0.01, "eps": 1e-3})
+    seq = nn.Sequential(blk, nn.Linear(4, 4))
+    plans = engine._ScratchDict()
+    plans["k"] = Holder()
+    blk.__dict__["_yamb_plans"] = plans
+    blk.__dict__["_yamb_eval"] = engine._ScratchDict(a=torch.zeros(1))
+    blk.pw_bn.__dict__["_yamb_bnact"] = Holder()
+    seq[1].__dict__["_yamb_lin"] = Holder()
+    assert issubclass(tail_ops._PwState, engine.Scratch)
+    assert issubclass(tail_ops._LinearState, engine.Scratch)
+    assert issubclass(engine._BnActState, engine.Scratch)
+    c = copy.deepcopy(seq)
+    assert "_yamb_plans" not in c[0].__dict__ and "_yamb_eval" not in c[0].__dict__
+    assert c[0].pw_bn.__dict__["_yamb_bnact"] is None and c[1].__dict__["_yamb_lin"] is None
+    for (k, a), (_, b) in zip(seq.state_dict().items(), c.state_dict().items()):
+        assert torch.equal(a, b), k
+    r = pickle.loads(pickle.dumps(seq[1]))
+    assert r.__dict__["_yamb_lin"] is None

@@ -72,6 +72,8 @@ int yamb_struct_size(int which) {
     case 17: return (int)sizeof(yamb_softmax_ce);
     case 18: return (int)sizeof(yamb_softmax_ce_grad);
     case 19: return (int)sizeof(yamb_stem_conv);
+    case 20: return (int)sizeof(yamb_bn_eval);
+    case 21: return (int)sizeof(yamb_block_eval);
     default: return -1;
   }
 }
@@ -102,6 +104,7 @@ int yamb_stem_conv_fwd(const yamb_stem_conv* a, yamb_stream_t s) { return yamb::
 int yamb_stem_conv_wgrad(const yamb_stem_conv* a, yamb_stream_t s) { return yamb::stem_conv_wgrad_launch(a, YAMB_ST(s)); }
 int yamb_nl_gram_fwd(const yamb_nl_gram* a, yamb_stream_t s) { return yamb::nl_gram_launch(a, YAMB_ST(s)); }
 int yamb_nl_rowmat_fwd(const yamb_nl_rowmat* a, yamb_stream_t s) { return yamb::nl_rowmat_launch(a, YAMB_ST(s)); }
+int yamb_block_eval_fwd(const yamb_block_eval* a, yamb_stream_t s) { return yamb::block_eval_launch(a, YAMB_ST(s)); }
 int yamb_rmsprop_step(const yamb_rmsprop* a, yamb_stream_t s) { return yamb::rmsprop_launch(a, YAMB_ST(s)); }
 int yamb_ema_update(float* shadow, const float* x, int64_t n, const float* hyper, float m,
                     yamb_stream_t s) {

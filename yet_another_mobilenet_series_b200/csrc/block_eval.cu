@@ -1,0 +1,543 @@
+// Eval-mode inverted-residual block in ONE launch, no intermediate tensor in HBM (sm_100a).
+//
+// Replaces, behind yamb_block_eval_fwd (include/yamb200.h), the whole forward of
+// InvertedResidualChannels (reference models/mobilenet_base.py:446-451: 1x1 expand -> BatchNorm ->
+// act -> depthwise 3x3 -> BatchNorm -> act -> 1x1 project -> BatchNorm (+x)) when every BatchNorm
+// normalises with its running statistics (model.eval(): validation, utils/common.py forward_loss
+// under torch.no_grad()).  With the statistics known up front the block is a pure function of an
+// input tile plus a one-pixel halo: SURVEY.md §7.1 step 2 / §7.2, BASELINE.json's "fused block".
+//
+// One persistent CTA per SM (two where shared memory and TMEM allow) walks output tiles of <= 128
+// pixels (8x16, 7x14 or two 7x7 images).  Per tile:
+//   x tile (+halo, <= 256 pixels) --cp.async--> smem, SWIZZLE_128B K-major  (A operand, read once)
+//   for every 64-channel slice of the hidden dimension:
+//     W1 slice, W3 slice --cp.async--> smem (double-buffered when it fits)
+//     tcgen05.mma  [256 px x Cin] x [Cin x 64]       -> TMEM (fp32)                   expand
+//     tcgen05.ld -> BatchNorm1 + act -> bf16, zero outside the image -> smem          epilogue 1
+//     3x3 stencil on the CUDA cores (FFMA2) -> BatchNorm2 + act -> bf16 -> smem (A operand layout)
+//     tcgen05.mma  [128 px x 64] x [64 x Cout]  accumulated over the slices -> TMEM   project
+//   tcgen05.ld -> BatchNorm3 (+ x) -> bf16 -> global                                  epilogue 2
+// HBM traffic: x once (+ halo re-reads from L2), y once; the hidden tensors (6 x the block's
+// input) never leave the SM.  BatchNorm folding (gamma * rsqrt(var + eps), beta - mean * scale) is
+// done by the kernel from the module's own buffers: no preparation launches.
+//
+// Rounding points: a1 = bf16(act(bn1(fp32 accumulator))), a2 = bf16(act(bn2(fp32 stencil))),
+// y = bf16(bn3(fp32 accumulator) + x) — one rounding fewer per stage than the four-launch path
+// (which stores the raw convolution outputs in bf16 first).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "host_util.h"
+#include "prims.cuh"
+
+namespace yamb {
+
+struct BnEvalDev {
+  const float *gamma, *beta, *mean, *var;
+  float eps;
+};
+
+struct BlockEvalDev {
+  int N, H, W, Cin, Chid, Cout, act, residual;
+  const __nv_bfloat16 *x, *w1, *w3;
+  const float* wdw;
+  BnEvalDev bn1, bn2, bn3;
+  __nv_bfloat16* y;
+  int tiles_h, tiles_w, num_tiles;
+  int KB;            // 64-channel panels of the x tile
+  int cpr;           // 16-byte chunks per x / W1 row incl. the zero padding to a multiple of 16 channels
+  int Npad;          // Cout rounded up to a multiple of 16 (UMMA N)
+  int NC;            // 64-channel slices of the hidden dimension
+  int nbuf;          // weight staging buffers (1 or 2)
+  int xpanel_bytes;  // MT * 16 KB
+  int off_w, wbuf_bytes, off_w3, off_tab, off_h1, off_h2, off_c3, off_bars;
+  int tmem_cols, proj_col;
+};
+
+// Output tile TI images x TOH x TOW pixels (<= 128 = the M of the project MMA); the input tile with
+// its one-pixel halo is the M of the expand MMAs (MT tiles of 128 rows).
+template <int TOH_, int TOW_, int TI_>
+struct EvGeom {
+  static constexpr int TOH = TOH_, TOW = TOW_, TI = TI_;
+  static constexpr int IH = TOH + 2, IW = TOW + 2;
+  static constexpr int NPI = TI * IH * IW;
+  static constexpr int MT = (NPI + 127) / 128;
+  static constexpr int NPO = TI * TOH * TOW;
+  static constexpr int RUN = (TOW % 8 == 0) ? 8 : 7;   // consecutive outputs of one row per stencil thread
+  static constexpr int NRUN = NPO / RUN;
+  static_assert(NPO <= 128 && MT <= 2 && TOW % RUN == 0 && NRUN <= 16, "tile geometry");
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool ok) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <class G>
+__global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constant__ BlockEvalDev p) {
+  constexpr int TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
+  constexpr int NPI = G::NPI, MT = G::MT, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bar_e = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+  uint64_t* bar_p = bar_e + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_e + 2);
+  float* c3 = reinterpret_cast<float*>(smem + p.off_c3);     // [scale3 | shift3] x Npad
+  float* tab = reinterpret_cast<float*>(smem + p.off_tab);   // s1 t1 s2 t2 [64] + taps [9][64]
+  uint8_t* sH1 = smem + p.off_h1;
+  uint8_t* sH2 = smem + p.off_h2;
+  const uint32_t sX_u = smem_u32(smem), sH2_u = smem_u32(sH2);
+
+  if (tid == 0) {
+    mbar_init(bar_e, 1);
+    mbar_init(bar_p, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < p.Npad; i += 256) {
+    float sc = 0.f, sh = 0.f;
+    if (i < p.Cout) {
+      const float r = rsqrtf(p.bn3.var[i] + p.bn3.eps);
+      sc = (p.bn3.gamma ? p.bn3.gamma[i] : 1.f) * r;
+      sh = (p.bn3.beta ? p.bn3.beta[i] : 0.f) - p.bn3.mean[i] * sc;
+    }
+    c3[i] = sc;
+    c3[p.Npad + i] = sh;
+  }
+  // rows of the project A operand beyond the tile's pixels are never written: keep them zero
+  for (int i = tid; i < 16384 / 16; i += 256) reinterpret_cast<uint4*>(sH2)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const ActParam ap = make_act(p.act);
+
+  // ---- per-slice coefficient tables, fetched one slice ahead into registers -------------------
+  // threads 0..127: BatchNorm1 / BatchNorm2 of hidden channel (slice*64 + tid%64); all threads: taps
+  float pre_s = 0.f, pre_t = 0.f, pre_w[3] = {0.f, 0.f, 0.f};
+  auto tab_fetch = [&](int c) {
+    if (tid < 128) {
+      const BnEvalDev& b = tid < 64 ? p.bn1 : p.bn2;
+      const int hc = c * 64 + (tid & 63);
+      pre_s = pre_t = 0.f;
+      if (hc < p.Chid) {
+        const float r = rsqrtf(__ldg(b.var + hc) + b.eps);
+        pre_s = (b.gamma ? __ldg(b.gamma + hc) : 1.f) * r;
+        pre_t = (b.beta ? __ldg(b.beta + hc) : 0.f) - __ldg(b.mean + hc) * pre_s;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + 256 * k;   // i = ch * 9 + tap: contiguous in global memory
+      const int hc = c * 64 + i / 9;
+      pre_w[k] = (i < 576 && hc < p.Chid) ? __ldg(p.wdw + (size_t)c * 576 + i) : 0.f;
+    }
+  };
+  auto tab_store = [&]() {
+    if (tid < 128) {
+      const int which = tid >> 6, ch = tid & 63;
+      tab[which * 128 + ch] = pre_s;          // s1 at 0, s2 at 128
+      tab[which * 128 + 64 + ch] = pre_t;     // t1 at 64, t2 at 192
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + 256 * k;
+      if (i < 576) tab[256 + (i % 9) * 64 + i / 9] = pre_w[k];
+    }
+  };
+
+  // ---- operand staging ---------------------------------------------------------------------------
+  auto load_x = [&](int t) {
+    const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
+    const int total = NPI * p.cpr;
+    for (int i = tid; i < total; i += 256) {
+      const int r = i / p.cpr, j = i - r * p.cpr;
+      const int ti = r / (IH * IW), rem = r % (IH * IW), iy = rem / IW, ix = rem % IW;
+      const int n = g * TI + ti, yy = ty * TOH - 1 + iy, xx = tx * TOW - 1 + ix;
+      const bool ok = n < p.N && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W &&
+                      j * 8 < p.Cin;
+      const __nv_bfloat16* src =
+          ok ? p.x + ((size_t)(n * p.H + yy) * p.W + xx) * p.Cin + j * 8 : p.x;
+      cp_async_16(sX_u + (uint32_t)((j >> 3) * p.xpanel_bytes + r * 128 + (((j & 7) ^ (r & 7)) << 4)),
+                  src, ok);
+    }
+  };
+  auto load_w = [&](int c, int buf) {
+    const uint32_t wb = sX_u + (uint32_t)(p.off_w + buf * p.wbuf_bytes);
+    const int n1 = 64 * p.cpr;
+    for (int i = tid; i < n1; i += 256) {
+      const int hr = i / p.cpr, j = i - hr * p.cpr, hc = c * 64 + hr;
+      const bool ok = hc < p.Chid && j * 8 < p.Cin;
+      const __nv_bfloat16* src = ok ? p.w1 + (size_t)hc * p.Cin + j * 8 : p.w1;
+      cp_async_16(wb + (uint32_t)((j >> 3) * 8192 + hr * 128 + (((j & 7) ^ (hr & 7)) << 4)), src, ok);
+    }
+    const int n3 = p.Npad * 8;
+    for (int i = tid; i < n3; i += 256) {
+      const int n = i >> 3, j = i & 7, kc = c * 64 + j * 8;
+      const bool ok = n < p.Cout && kc < p.Chid;
+      const __nv_bfloat16* src = ok ? p.w3 + (size_t)n * p.Chid + kc : p.w3;
+      cp_async_16(wb + (uint32_t)(p.off_w3 + n * 128 + ((j ^ (n & 7)) << 4)), src, ok);
+    }
+  };
+
+  uint32_t pe = 0, pp = 0;      // mbarrier phase parities
+  int p_issued = 0, p_waited = 0;   // project commits issued / waited for (whole kernel)
+  auto wait_projects = [&](int upto) {
+    while (p_waited < upto) {
+      mbar_wait(bar_p, pp);
+      pp ^= 1;
+      ++p_waited;
+    }
+  };
+
+  const int NC = p.NC;
+  tab_fetch(0);
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
+    // every MMA of the previous tile has been waited for: all staging buffers are free
+    load_x(t);
+    load_w(0, 0);
+    cp_commit();
+    tab_store();
+    for (int c = 0; c < NC; ++c) {
+      const int buf = p.nbuf == 2 ? (c & 1) : 0;
+      const bool ahead = p.nbuf == 2 && c + 1 < NC;
+      if (ahead) {
+        wait_projects(p_issued);        // the project MMA that read buffer buf^1 has retired
+        load_w(c + 1, buf ^ 1);
+        cp_commit();
+      }
+      tab_fetch(c + 1 < NC ? c + 1 : 0);   // registers; stored after this slice's stencil
+      if (ahead) cp_wait<1>(); else cp_wait<0>();
+      fence_proxy_async_smem();
+      __syncthreads();                                                     // S1: operands + tables
+      const uint32_t wb = sX_u + (uint32_t)(p.off_w + buf * p.wbuf_bytes);
+      if (warp == 0) {
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+          const int nks = p.cpr >> 1;   // K steps of 16 channels
+#pragma unroll 1
+          for (int mt = 0; mt < MT; ++mt)
+            for (int ks = 0; ks < nks; ++ks) {
+              const int kb = ks >> 2, kk = ks & 3;
+              const uint64_t ad = umma_smem_desc(
+                  sX_u + (uint32_t)(kb * p.xpanel_bytes + mt * 16384 + kk * 32), 16, 1024);
+              const uint64_t bd = umma_smem_desc(wb + (uint32_t)(kb * 8192 + kk * 32), 16, 1024);
+              umma_bf16(tmem + (uint32_t)(mt * 64), ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+          umma_commit(bar_e);
+        }
+        __syncwarp();
+      }
+      mbar_wait(bar_e, pe);
+      pe ^= 1;
+      tc_fence_after();
+      // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
+      {
+        const int q = warp & 3;
+#pragma unroll 1
+        for (int mt = warp >> 2; mt < MT; mt += 2) {
+          const int r = mt * 128 + q * 32 + lane;
+          const int ti = r / (IH * IW), rem = r % (IH * IW), iy = rem / IW, ix = rem % IW;
+          const int n = g * TI + ti, yy = ty * TOH - 1 + iy, xx = tx * TOW - 1 + ix;
+          const bool inside = r < NPI && n < p.N && (unsigned)yy < (unsigned)p.H &&
+                              (unsigned)xx < (unsigned)p.W;
+#pragma unroll
+          for (int hcol = 0; hcol < 2; ++hcol) {
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + hcol * 32), acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const int cb = hcol * 32 + ch * 8;
+              const float4 s0 = *reinterpret_cast<const float4*>(tab + cb);
+              const float4 s1 = *reinterpret_cast<const float4*>(tab + cb + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(tab + 64 + cb);
+              const float4 t1 = *reinterpret_cast<const float4*>(tab + 64 + cb + 4);
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(ss[e], __uint_as_float(acc[ch * 8 + e]), tt[e]);
+              act_vec<8>(v, ap);
+              uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+              if (!inside) o = make_uint4(0u, 0u, 0u, 0u);
+              if (r < NPI)
+                *reinterpret_cast<uint4*>(sH1 + r * 128 + (((cb >> 3) ^ (r & 7)) << 4)) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncthreads();                                                     // S2: a1 tile complete
+      // ---- 3x3 stencil: RUN consecutive outputs of one row x 4 channels per thread ----
+      const int cg = tid & 15, sp = tid >> 4;
+      float2 o2[RUN][2];
+#pragma unroll
+      for (int j = 0; j < RUN; ++j) o2[j][0] = o2[j][1] = make_float2(0.f, 0.f);
+      const int r0 = sp * RUN;
+      if (sp < NRUN) {
+        const int ti = r0 / (TOH * TOW), rem = r0 % (TOH * TOW), oy = rem / TOW, ox0 = rem % TOW;
+        const int pbase = ti * IH * IW + oy * IW + ox0;
+        float2 w2[9][2];
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          const float4 wv = *reinterpret_cast<const float4*>(tab + 256 + tp * 64 + cg * 4);
+          w2[tp][0] = make_float2(wv.x, wv.y);
+          w2[tp][1] = make_float2(wv.z, wv.w);
+        }
+        const uint8_t* hb = sH1 + (cg & 1) * 8;
+        const int cgh = cg >> 1;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int ixx = 0; ixx < RUN + 2; ++ixx) {
+            const int pi = pbase + ky * IW + ixx;
+            const uint2 a = *reinterpret_cast<const uint2*>(hb + pi * 128 + ((cgh ^ (pi & 7)) << 4));
+            const float2 alo = make_float2(bf16lo(a.x), bf16hi(a.x));
+            const float2 ahi = make_float2(bf16lo(a.y), bf16hi(a.y));
+#pragma unroll
+            for (int j = 0; j < RUN; ++j) {
+              const int kx = ixx - j;   // compile-time after unrolling
+              if (kx >= 0 && kx < 3) {
+                o2[j][0] = ffma2(w2[ky * 3 + kx][0], alo, o2[j][0]);
+                o2[j][1] = ffma2(w2[ky * 3 + kx][1], ahi, o2[j][1]);
+              }
+            }
+          }
+        }
+      }
+      // the project MMA of the previous slice must have read sH2 before it is rewritten
+      wait_projects(p_issued);
+      if (sp < NRUN) {
+        const float4 s2 = *reinterpret_cast<const float4*>(tab + 128 + cg * 4);
+        const float4 t2 = *reinterpret_cast<const float4*>(tab + 192 + cg * 4);
+#pragma unroll
+        for (int j = 0; j < RUN; ++j) {
+          float v[4] = {fmaf(s2.x, o2[j][0].x, t2.x), fmaf(s2.y, o2[j][0].y, t2.y),
+                        fmaf(s2.z, o2[j][1].x, t2.z), fmaf(s2.w, o2[j][1].y, t2.w)};
+          act_vec<4>(v, ap);
+          const int r = r0 + j;
+          *reinterpret_cast<uint2*>(sH2 + r * 128 + (((cg >> 1) ^ (r & 7)) << 4) + (cg & 1) * 8) =
+              make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncthreads();                                                     // S3: a2 tile complete
+      if (warp == 0) {
+        tc_fence_after();
+        if (lane == 0) {
+          const int halves = p.Npad > 256 ? 2 : 1;
+          const int nn = p.Npad / halves;
+          const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
+          for (int h = 0; h < halves; ++h)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = umma_smem_desc(sH2_u + (uint32_t)(kk * 32), 16, 1024);
+              const uint64_t bd =
+                  umma_smem_desc(wb + (uint32_t)(p.off_w3 + h * nn * 128 + kk * 32), 16, 1024);
+              umma_bf16(tmem + (uint32_t)(p.proj_col + h * nn), ad, bd, idesc,
+                        (c > 0 || kk > 0) ? 1u : 0u);
+            }
+          umma_commit(bar_p);
+        }
+        __syncwarp();
+      }
+      ++p_issued;
+      tab_store();    // next slice's tables (this slice's readers are behind S3)
+      if (p.nbuf == 1 && c + 1 < NC) {
+        wait_projects(p_issued);        // W3 / W1 of this slice are free
+        load_w(c + 1, 0);
+        cp_commit();
+      }
+    }
+    // ---- epilogue 2: y = bf16(bn3(h3) (+ x)) ----
+    wait_projects(p_issued);
+    tc_fence_after();
+    {
+      const int q = warp & 3, r = q * 32 + lane;
+      const int ti = r / (TOH * TOW), rem = r % (TOH * TOW), oy = rem / TOW, ox = rem % TOW;
+      const int n = g * TI + ti, yy = ty * TOH + oy, xx = tx * TOW + ox;
+      const bool valid = r < NPO && n < p.N && yy < p.H && xx < p.W;
+      const size_t pix = valid ? ((size_t)(n * p.H + yy) * p.W + xx) : 0;
+      const int units = p.Npad >> 4;
+#pragma unroll 1
+      for (int u = warp >> 2; u < units; u += 2) {
+        uint32_t acc[16];
+        tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col + u * 16), acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = u * 16 + h * 8;
+          if (valid && col < p.Cout) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = fmaf(c3[col + e], __uint_as_float(acc[h * 8 + e]), c3[p.Npad + col + e]);
+            if (p.residual) {
+              const uint4 rx = __ldg(reinterpret_cast<const uint4*>(p.x + pix * p.Cin + col));
+              const uint32_t rw[4] = {rx.x, rx.y, rx.z, rx.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[2 * e] += bf16lo(rw[e]);
+                v[2 * e + 1] += bf16hi(rw[e]);
+              }
+            }
+            *reinterpret_cast<uint4*>(p.y + pix * p.Cout + col) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                           pack_bf16(v[6], v[7]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // accumulators and staging buffers are free for the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+template <class G>
+static cudaError_t launch_eval(BlockEvalDev& p, size_t smem_fixed, cudaStream_t st) {
+  // shared-memory plan (bytes from the 1024-aligned base)
+  p.xpanel_bytes = G::MT * 16384;
+  int off = p.KB * p.xpanel_bytes;
+  p.off_w = off;
+  p.off_w3 = p.KB * 8192;
+  p.wbuf_bytes = ((p.off_w3 + p.Npad * 128) + 1023) & ~1023;
+  const int rest = G::MT * 16384 + 16384 + (int)smem_fixed;
+  p.nbuf = (off + 2 * p.wbuf_bytes + rest <= 227 * 1024 - 1024) ? 2 : 1;
+  if (p.NC == 1) p.nbuf = 1;
+  off += p.nbuf * p.wbuf_bytes;
+  p.off_h1 = off; off += G::MT * 16384;
+  p.off_h2 = off; off += 16384;
+  p.off_tab = off; off += (256 + 576) * 4;
+  p.off_c3 = off; off += 2 * p.Npad * 4;
+  p.off_bars = (off + 15) & ~15; off = p.off_bars + 32;
+  const int smem = off;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  p.proj_col = G::MT * 64;
+  int need = p.proj_col + p.Npad, cols = 32;
+  while (cols < need) cols *= 2;
+  if (cols > 512) return cudaErrorInvalidValue;
+  p.tmem_cols = cols;
+  const int tiles_img = p.tiles_h * p.tiles_w;
+  const int groups = (p.N + G::TI - 1) / G::TI;
+  p.num_tiles = groups * tiles_img;
+  // the dynamic-smem limit is process-wide state: only ever raise it; occupancy cached per size
+  static std::mutex mu;
+  static int attr = 0;
+  static int occ_smem[8], occ_val[8], n_occ = 0;
+  int per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (attr < smem) {
+      cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      attr = smem;
+    }
+    for (int i = 0; i < n_occ; ++i)
+      if (occ_smem[i] == smem) per_sm = occ_val[i];
+    if (per_sm == 0) {
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_eval_kernel<G>,
+                                                                    256, smem);
+      if (e != cudaSuccess) return e;
+      if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+      if (n_occ < 8) { occ_smem[n_occ] = smem; occ_val[n_occ++] = per_sm; }
+    }
+  }
+  // resident CTAs per SM are also bounded by the TMEM columns each one allocates
+  if (per_sm > 512 / cols) per_sm = 512 / cols;
+  if (per_sm > 2) per_sm = 2;
+  long long cap = (long long)max_ctas() * per_sm;
+  const int grid = (int)(p.num_tiles < cap ? p.num_tiles : cap);
+  block_eval_kernel<G><<<grid, 256, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
+  if (!a) return set_error(YAMB_EINVAL, "null args");
+  if (max_ctas() <= 0) return set_error(YAMB_ENODEV, "no CUDA device");
+  if (a->N <= 0 || a->H <= 0 || a->W <= 0) return set_error(YAMB_EINVAL, "block_eval: bad shape");
+  if (a->Cin % 8 || a->Chid % 8 || a->Cout % 8 || a->Cin <= 0 || a->Chid <= 0 || a->Cout <= 0)
+    return set_error(YAMB_EINVAL, "block_eval: channel counts must be positive multiples of 8");
+  if (a->Cin > 256 || a->Cout > 320)
+    return set_error(YAMB_EINVAL, "block_eval: Cin <= 256, Cout <= 320 (got %d, %d)", a->Cin, a->Cout);
+  if (a->kernel != 3 || a->stride != 1)
+    return set_error(YAMB_EINVAL, "block_eval: only 3x3 stride-1 depthwise (got k=%d s=%d)",
+                     a->kernel, a->stride);
+  if (a->residual && a->Cin != a->Cout)
+    return set_error(YAMB_EINVAL, "block_eval: residual needs Cin == Cout");
+  if (!a->x || !a->y || !a->w_expand || !a->w_dw || !a->w_project)
+    return set_error(YAMB_EINVAL, "block_eval: null pointer");
+  const yamb_bn_eval* bns[3] = {&a->bn1, &a->bn2, &a->bn3};
+  for (int i = 0; i < 3; ++i)
+    if (!bns[i]->running_mean || !bns[i]->running_var)
+      return set_error(YAMB_EINVAL, "block_eval: BatchNorm %d has no running statistics", i + 1);
+  if ((((uintptr_t)a->x) | ((uintptr_t)a->y) | ((uintptr_t)a->w_expand) | ((uintptr_t)a->w_project)) & 15)
+    return set_error(YAMB_EINVAL, "block_eval: tensors must be 16-byte aligned");
+  if ((long long)a->N * a->H * a->W > 0x7fffffffLL / 2)
+    return set_error(YAMB_EINVAL, "block_eval: too many pixels");
+  BlockEvalDev p;
+  memset(&p, 0, sizeof(p));
+  p.N = a->N; p.H = a->H; p.W = a->W;
+  p.Cin = a->Cin; p.Chid = a->Chid; p.Cout = a->Cout;
+  p.act = a->act; p.residual = a->residual ? 1 : 0;
+  p.x = (const __nv_bfloat16*)a->x; p.y = (__nv_bfloat16*)a->y;
+  p.w1 = (const __nv_bfloat16*)a->w_expand; p.w3 = (const __nv_bfloat16*)a->w_project;
+  p.wdw = a->w_dw;
+  auto cvt = [](const yamb_bn_eval& s) {
+    BnEvalDev d;
+    d.gamma = s.gamma; d.beta = s.beta; d.mean = s.running_mean; d.var = s.running_var; d.eps = s.eps;
+    return d;
+  };
+  p.bn1 = cvt(a->bn1); p.bn2 = cvt(a->bn2); p.bn3 = cvt(a->bn3);
+  const int kpad = (a->Cin + 15) / 16 * 16;
+  p.cpr = kpad / 8;
+  p.KB = (kpad + 63) / 64;
+  p.Npad = (a->Cout + 15) / 16 * 16;
+  p.NC = (a->Chid + 63) / 64;
+  // tile geometry: the one that wastes the fewest of the 128 rows of a tile
+  struct Cand { int toh, tow, ti; };
+  const Cand cands[3] = {{8, 16, 1}, {7, 14, 1}, {7, 7, 2}};
+  int best = 0;
+  long long best_tiles = -1;
+  for (int i = 0; i < 3; ++i) {
+    const long long th = (a->H + cands[i].toh - 1) / cands[i].toh;
+    const long long tw = (a->W + cands[i].tow - 1) / cands[i].tow;
+    const long long tiles = th * tw * ((a->N + cands[i].ti - 1) / cands[i].ti);
+    if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best = i; }
+  }
+  if (best_tiles > 0x7fffffffLL) return set_error(YAMB_EINVAL, "block_eval: too many tiles");
+  p.tiles_h = (a->H + cands[best].toh - 1) / cands[best].toh;
+  p.tiles_w = (a->W + cands[best].tow - 1) / cands[best].tow;
+  cudaError_t e;
+  if (best == 0) e = launch_eval<EvGeom<8, 16, 1>>(p, 8192, st);
+  else if (best == 1) e = launch_eval<EvGeom<7, 14, 1>>(p, 8192, st);
+  else e = launch_eval<EvGeom<7, 7, 2>>(p, 8192, st);
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace yamb

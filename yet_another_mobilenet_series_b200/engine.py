@@ -119,6 +119,24 @@ class Workspace:
         return ws
 
 
+class Scratch:
+    """Per-module kernel scratch (device buffers, C-ABI argument structs) cached in a module's
+    `__dict__`.  It never travels with the module: a `copy.deepcopy` (the EMA model, reference
+    common.py:164) or a pickle of the module gets None there and builds its own on first use
+    (ctypes structs holding pointers can be neither copied nor pickled)."""
+
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
+
+
+class _ScratchDict(dict, Scratch):
+    __deepcopy__ = Scratch.__deepcopy__
+    __reduce__ = Scratch.__reduce__
+
+
 def to_nhwc_bf16(x):
     """[N,C,H,W] any float dtype/layout -> channels_last bf16 (no copy if already so)."""
     if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
@@ -829,7 +847,9 @@ def _plan_for(block, x):
     MAX_PLANS_PER_BLOCK shapes are kept per block, least recently used first out: a partial last
     batch or another evaluation resolution no longer pins a whole extra activation set for ever
     (ADVICE r1)."""
-    plans = block.__dict__.setdefault("_yamb_plans", {})
+    plans = block.__dict__.get("_yamb_plans")
+    if plans is None:
+        plans = block.__dict__["_yamb_plans"] = _ScratchDict()
     key = (tuple(x.shape), x.device.index)
     p = plans.pop(key, None)
     if p is None:
@@ -1005,7 +1025,7 @@ def needs_padding(block):
     return any(c % 8 for c in block.channels)
 
 
-class _PadShadow:
+class _PadShadow(Scratch):
     def __init__(self, block, device):
         from . import mobilenet_base as mb
         fused = hasattr(block, "expand_conv")
@@ -1189,7 +1209,7 @@ class _PadFn(torch.autograd.Function):
 # statistics kernel (+ finalize) -> y = act(scale*h + shift); backward: statistics of
 # dz = dy*act'(z) (+ finalize: dgamma, dbeta, ca/cb/cc) -> dh = ca*dz + cb*h + cc.
 # ------------------------------------------------------------------------------------------------
-class _BnActState:
+class _BnActState(Scratch):
     def __init__(self, bn, dev):
         self.bn = _Bn([bn], dev)
         self.ws = Workspace.get(dev)
@@ -1308,6 +1328,86 @@ def bn_act_apply(bn, active_fn, h):
     return _BnActFn.apply(h, bn, act_code_of(active_fn), bn.weight, bn.bias)
 
 
+# ---- eval mode: the whole block in one launch (csrc/block_eval.cu) ---------------------------------
+# YAMB_EVAL_FUSED=0 keeps the four-launch sequence (folded coefficients) for every block.
+EVAL_FUSED = os.environ.get("YAMB_EVAL_FUSED", "1") != "0"
+EVAL_FUSED_CALLS = 0     # blocks that went through yamb_block_eval_fwd (tests / bench)
+
+
+def fused_eval_supported(block, x):
+    """True when yamb_block_eval_fwd covers this block for this call: no gradient wanted, every
+    BatchNorm normalising with running statistics, unfused single-branch block with expansion,
+    3x3 stride-1 depthwise (reference models/mobilenet_base.py:380-421; the 12 such blocks of
+    MobileNetV2-1.0), channel counts the kernel's tiles hold."""
+    if not EVAL_FUSED or torch.is_grad_enabled() or hasattr(block, "expand_conv"):
+        return False
+    if not getattr(block, "expand", False) or block.stride != 1:
+        return False
+    if list(block.kernel_sizes) != [3] or len(block.channels) != 1:
+        return False
+    cin, chid, cout = block.input_dim, block.channels[0], block.output_dim
+    if cin % 8 or chid % 8 or cout % 8 or cin > 256 or cout > 320:
+        return False
+    if x.dim() != 4 or x.shape[0] * x.shape[2] * x.shape[3] >= 2 ** 30:
+        return False
+    op = block.ops[0]
+    for bn in (op[0][1], op[1][1], block.pw_bn):
+        if not isinstance(bn, torch.nn.BatchNorm2d) or bn.training or \
+                not bn.track_running_stats or bn.running_mean is None:
+            return False
+    try:
+        act_code_of(block.active_fn)
+    except ValueError:
+        return False
+    return True
+
+
+def fused_eval_forward(block, x):
+    """y = block(x) in eval mode through ONE kernel launch; x channels_last bf16 on CUDA."""
+    global EVAL_FUSED_CALLS
+    dev = x.device
+    N, Cin, H, W = x.shape
+    op = block.ops[0]
+    conv_e, bn1, conv_d, bn2, conv_p, bn3 = op[0][0], op[0][1], op[1][0], op[1][1], op[2], \
+        block.pw_bn
+    Chid, Cout = block.channels[0], block.output_dim
+    st = block.__dict__.get("_yamb_eval")
+    if st is None:
+        st = block.__dict__["_yamb_eval"] = _ScratchDict()
+    key = dev.index
+    own = st.get(key)
+    if own is None:
+        own = (torch.empty(Chid, Cin, device=dev, dtype=torch.bfloat16),
+               torch.empty(Cout, Chid, device=dev, dtype=torch.bfloat16))
+        st[key] = own
+    with torch.no_grad():
+        w1 = _bf16_operand(conv_e.weight, own[0], (Chid, Cin))
+        w3 = _bf16_operand(conv_p.weight, own[1], (Cout, Chid))
+    y = torch.empty((N, Cout, H, W), device=dev, dtype=torch.bfloat16,
+                    memory_format=torch.channels_last)
+    a = nat.BlockEval()
+    a.N, a.H, a.W = N, H, W
+    a.Cin, a.Chid, a.Cout = Cin, Chid, Cout
+    a.kernel, a.stride = 3, 1
+    a.act = act_code_of(block.active_fn)
+    a.residual = 1 if block.use_res_connect else 0
+    a.x, a.y = x.data_ptr(), y.data_ptr()
+    a.w_expand, a.w_project = w1.data_ptr(), w3.data_ptr()
+    a.w_dw = conv_d.weight.data_ptr()
+    for dst, bn in ((a.bn1, bn1), (a.bn2, bn2), (a.bn3, bn3)):
+        dst.gamma = nat.ptr(bn.weight)
+        dst.beta = nat.ptr(bn.bias)
+        dst.running_mean = bn.running_mean.data_ptr()
+        dst.running_var = bn.running_var.data_ptr()
+        dst.eps = bn.eps
+    M = N * H * W
+    launch(lib_fn("yamb_block_eval_fwd"), a, "block_eval",
+           2 * M * (Cin * (2 if block.use_res_connect else 1) + Cout),
+           2 * M * Chid * (Cin + Cout + 9))
+    EVAL_FUSED_CALLS += 1
+    return y
+
+
 def block_apply(block, x):
     """Forward of a reference-compatible block module through the sm_100a path."""
     if not x.is_cuda:
@@ -1315,6 +1415,8 @@ def block_apply(block, x):
             "the inverted-residual block runs only on CUDA sm_100a (no CPU fallback); got a %s "
             "tensor" % x.device)
     x = to_nhwc_bf16(x)
+    if fused_eval_supported(block, x):
+        return fused_eval_forward(block, x)
     params = list(block.parameters())
     if needs_padding(block):
         return _PadFn.apply(x, block, *params)

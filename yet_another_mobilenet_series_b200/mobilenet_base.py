@@ -211,7 +211,7 @@ class _FusedBlockBase(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_yamb_plans", "_yamb_shadow"):
+            if k in ("_yamb_plans", "_yamb_shadow", "_yamb_eval"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         return new

@@ -24,7 +24,7 @@ def _mat(t):
     return t.permute(0, 2, 3, 1).reshape(n * h * w, c)
 
 
-class _PwState:
+class _PwState(engine.Scratch):
     """Per-module device state of a 1x1 ConvBNReLU: BatchNorm coefficients, bf16 weight copy."""
 
     def __init__(self, conv, bn, dev):
@@ -190,7 +190,7 @@ def pw_conv_supported(mod, x):
 
 
 # ---- classifier --------------------------------------------------------------------------------
-class _LinearState:
+class _LinearState(engine.Scratch):
     def __init__(self, lin, dev):
         self.w_own = torch.empty(lin.out_features, lin.in_features, device=dev,
                                  dtype=torch.bfloat16)
