@@ -16,8 +16,40 @@ SHAPES = {"b1": (32, 16, 1, 32, 112), "b2": (16, 24, 2, 96, 112), "b3": (24, 24,
           "b13": (96, 96, 1, 576, 14), "b15": (160, 160, 1, 960, 7), "b16": (160, 160, 1, 960, 7)}
 
 
+def main_eval(names):
+    """YAMB_PROFILE_EVAL=1: eval-mode forward of the same blocks under no_grad (the one-launch
+    kernel of csrc/block_eval.cu where it applies)."""
+    N = int(os.environ.get("YAMB_N", "256"))
+    dev = torch.device("cuda")
+    bn = {"momentum": 0.01, "eps": 1e-3}
+    blocks = []
+    for n in names:
+        inp, oup, s, hid, H = SHAPES[n]
+        torch.manual_seed(0)
+        blk = mb.InvertedResidualChannels(inp, oup, s, [hid], [3], hid != inp,
+                                          mb.get_active_fn("nn.ReLU"), bn).to(dev)
+        blk.apply(mb.init_weights_mnas)
+        blk.eval()
+        x = torch.randn(N, inp, H, H, device=dev).to(torch.bfloat16).contiguous(
+            memory_format=torch.channels_last)
+        blocks.append((blk, x))
+    with torch.no_grad():
+        for it in range(3):
+            if it == 2:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.start()
+            for blk, x in blocks:
+                blk(x)
+            if it == 2:
+                torch.cuda.synchronize()
+                torch.cuda.profiler.stop()
+    print("done")
+
+
 def main():
     names = sys.argv[1:] or ["b2", "b3"]
+    if os.environ.get("YAMB_PROFILE_EVAL"):
+        return main_eval(names)
     N = int(os.environ.get("YAMB_N", "256"))
     dev = torch.device("cuda")
     bn = {"momentum": 0.01, "eps": 1e-3}

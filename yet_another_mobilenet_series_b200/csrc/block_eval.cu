@@ -26,6 +26,8 @@
 // (which stores the raw convolution outputs in bf16 first).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -82,7 +84,7 @@ __device__ __forceinline__ void cp_wait() {
 }
 
 template <class G>
-__global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constant__ BlockEvalDev p) {
+__global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constant__ BlockEvalDev p) {
   constexpr int TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
   constexpr int NPI = G::NPI, MT = G::MT, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const ActParam ap = make_act(p.act);
 
-  // ---- per-slice coefficient tables, fetched one slice ahead into registers -------------------
+  // ---- per-slice coefficient tables (double-buffered), fetched one slice ahead into registers ----
   // threads 0..127: BatchNorm1 / BatchNorm2 of hidden channel (slice*64 + tid%64); all threads: taps
   float pre_s = 0.f, pre_t = 0.f, pre_w[3] = {0.f, 0.f, 0.f};
   auto tab_fetch = [&](int c) {
@@ -144,16 +146,16 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
       pre_w[k] = (i < 576 && hc < p.Chid) ? __ldg(p.wdw + (size_t)c * 576 + i) : 0.f;
     }
   };
-  auto tab_store = [&]() {
+  auto tab_store = [&](float* tb) {
     if (tid < 128) {
       const int which = tid >> 6, ch = tid & 63;
-      tab[which * 128 + ch] = pre_s;          // s1 at 0, s2 at 128
-      tab[which * 128 + 64 + ch] = pre_t;     // t1 at 64, t2 at 192
+      tb[which * 128 + ch] = pre_s;          // s1 at 0, s2 at 128
+      tb[which * 128 + 64 + ch] = pre_t;     // t1 at 64, t2 at 192
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int i = tid + 256 * k;
-      if (i < 576) tab[256 + (i % 9) * 64 + i / 9] = pre_w[k];
+      if (i < 576) tb[256 + (i % 9) * 64 + i / 9] = pre_w[k];
     }
   };
 
@@ -173,26 +175,49 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
                   src, ok);
     }
   };
-  auto load_w = [&](int c, int buf) {
-    const uint32_t wb = sX_u + (uint32_t)(p.off_w + buf * p.wbuf_bytes);
+  const uint32_t sW1_u = sX_u + (uint32_t)p.off_w, sW3_u = sW1_u + (uint32_t)p.off_w3;
+  auto load_w1 = [&](int c) {
     const int n1 = 64 * p.cpr;
     for (int i = tid; i < n1; i += 256) {
       const int hr = i / p.cpr, j = i - hr * p.cpr, hc = c * 64 + hr;
       const bool ok = hc < p.Chid && j * 8 < p.Cin;
       const __nv_bfloat16* src = ok ? p.w1 + (size_t)hc * p.Cin + j * 8 : p.w1;
-      cp_async_16(wb + (uint32_t)((j >> 3) * 8192 + hr * 128 + (((j & 7) ^ (hr & 7)) << 4)), src, ok);
+      cp_async_16(sW1_u + (uint32_t)((j >> 3) * 8192 + hr * 128 + (((j & 7) ^ (hr & 7)) << 4)), src, ok);
     }
+  };
+  auto load_w3 = [&](int c) {
     const int n3 = p.Npad * 8;
     for (int i = tid; i < n3; i += 256) {
       const int n = i >> 3, j = i & 7, kc = c * 64 + j * 8;
       const bool ok = n < p.Cout && kc < p.Chid;
       const __nv_bfloat16* src = ok ? p.w3 + (size_t)n * p.Chid + kc : p.w3;
-      cp_async_16(wb + (uint32_t)(p.off_w3 + n * 128 + ((j ^ (n & 7)) << 4)), src, ok);
+      cp_async_16(sW3_u + (uint32_t)(n * 128 + ((j ^ (n & 7)) << 4)), src, ok);
+    }
+  };
+  // expand MMAs of one slice: [MT x 128 pixels, Cin] x [Cin, 64] -> TMEM columns [0, MT*64)
+  auto issue_expand = [&]() {
+    if (warp == 0) {
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+        const int nks = p.cpr >> 1;   // K steps of 16 channels
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt)
+          for (int ks = 0; ks < nks; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            const uint64_t ad = umma_smem_desc(
+                sX_u + (uint32_t)(kb * p.xpanel_bytes + mt * 16384 + kk * 32), 16, 1024);
+            const uint64_t bd = umma_smem_desc(sW1_u + (uint32_t)(kb * 8192 + kk * 32), 16, 1024);
+            umma_bf16(tmem + (uint32_t)(mt * 64), ad, bd, idesc, ks > 0 ? 1u : 0u);
+          }
+        umma_commit(bar_e);
+      }
+      __syncwarp();
     }
   };
 
-  uint32_t pe = 0, pp = 0;      // mbarrier phase parities
-  int p_issued = 0, p_waited = 0;   // project commits issued / waited for (whole kernel)
+  uint32_t pe = 0, pp = 0;          // mbarrier phase parities
+  int p_waited = 0;                 // project commits waited for (whole kernel)
   auto wait_projects = [&](int upto) {
     while (p_waited < upto) {
       mbar_wait(bar_p, pp);
@@ -201,49 +226,41 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
     }
   };
 
+  // Software pipeline over the slices gc = 0, 1, ... of all tiles of this CTA.  While slice gc is in
+  // its epilogue / stencil, the tensor core already runs expand(gc+1) and project(gc-1), and the
+  // operands of gc+1 (W1 slice; the x tile when gc+1 starts a new tile) stream in: every staging
+  // buffer is single, each is refilled right after its last reader retired.
+  //   wait expand(gc) | load W1(gc+1) [+ x] | epilogue 1 | load W3(gc) | S2 | issue expand(gc+1)
+  //   | stencil -> sH2 | S3 | issue project(gc) | (last slice of a tile: epilogue 2)
   const int NC = p.NC;
-  tab_fetch(0);
-  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-    const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
-    // every MMA of the previous tile has been waited for: all staging buffers are free
+  int t = blockIdx.x;
+  if (t < p.num_tiles) {
     load_x(t);
-    load_w(0, 0);
+    load_w1(0);
     cp_commit();
-    tab_store();
-    for (int c = 0; c < NC; ++c) {
-      const int buf = p.nbuf == 2 ? (c & 1) : 0;
-      const bool ahead = p.nbuf == 2 && c + 1 < NC;
-      if (ahead) {
-        wait_projects(p_issued);        // the project MMA that read buffer buf^1 has retired
-        load_w(c + 1, buf ^ 1);
-        cp_commit();
-      }
-      tab_fetch(c + 1 < NC ? c + 1 : 0);   // registers; stored after this slice's stencil
-      if (ahead) cp_wait<1>(); else cp_wait<0>();
-      fence_proxy_async_smem();
-      __syncthreads();                                                     // S1: operands + tables
-      const uint32_t wb = sX_u + (uint32_t)(p.off_w + buf * p.wbuf_bytes);
-      if (warp == 0) {
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-          const int nks = p.cpr >> 1;   // K steps of 16 channels
-#pragma unroll 1
-          for (int mt = 0; mt < MT; ++mt)
-            for (int ks = 0; ks < nks; ++ks) {
-              const int kb = ks >> 2, kk = ks & 3;
-              const uint64_t ad = umma_smem_desc(
-                  sX_u + (uint32_t)(kb * p.xpanel_bytes + mt * 16384 + kk * 32), 16, 1024);
-              const uint64_t bd = umma_smem_desc(wb + (uint32_t)(kb * 8192 + kk * 32), 16, 1024);
-              umma_bf16(tmem + (uint32_t)(mt * 64), ad, bd, idesc, ks > 0 ? 1u : 0u);
-            }
-          umma_commit(bar_e);
-        }
-        __syncwarp();
-      }
-      mbar_wait(bar_e, pe);
+    tab_fetch(0);
+    tab_store(tab);
+    cp_wait<0>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    issue_expand();
+  }
+  int gc = 0;
+  for (; t < p.num_tiles; t += gridDim.x) {
+    const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
+    for (int c = 0; c < NC; ++c, ++gc) {
+      const bool last_c = c + 1 == NC;
+      const bool has_next = !last_c || t + (int)gridDim.x < p.num_tiles;
+      float* tb = tab + (gc & 1) * 832;
+      mbar_wait(bar_e, pe);           // expand(gc) retired: accumulator ready, sW1 (and sX) free
       pe ^= 1;
       tc_fence_after();
+      if (has_next) {
+        if (last_c) load_x(t + gridDim.x);
+        load_w1(last_c ? 0 : c + 1);
+        cp_commit();                                                        // group A
+        tab_fetch(last_c ? 0 : c + 1);   // registers; stored before S3
+      }
       // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
       {
         const int q = warp & 3;
@@ -262,10 +279,10 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const int cb = hcol * 32 + ch * 8;
-              const float4 s0 = *reinterpret_cast<const float4*>(tab + cb);
-              const float4 s1 = *reinterpret_cast<const float4*>(tab + cb + 4);
-              const float4 t0 = *reinterpret_cast<const float4*>(tab + 64 + cb);
-              const float4 t1 = *reinterpret_cast<const float4*>(tab + 64 + cb + 4);
+              const float4 s0 = *reinterpret_cast<const float4*>(tb + cb);
+              const float4 s1 = *reinterpret_cast<const float4*>(tb + cb + 4);
+              const float4 t0 = *reinterpret_cast<const float4*>(tb + 64 + cb);
+              const float4 t1 = *reinterpret_cast<const float4*>(tb + 64 + cb + 4);
               const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
               const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
               float v[8];
@@ -281,21 +298,29 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
           }
         }
       }
+      // project(gc-1) retired long ago (it was issued before this slice's accumulator wait):
+      // sW3 and sH2 are free
+      wait_projects(gc);
+      load_w3(c);
+      cp_commit();                                                          // group B
+      cp_wait<1>();                   // group A landed (B may still be in flight)
+      fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();                                                     // S2: a1 tile complete
+      if (has_next) issue_expand();   // expand(gc+1) runs under the stencil
       // ---- 3x3 stencil: RUN consecutive outputs of one row x 4 channels per thread ----
       const int cg = tid & 15, sp = tid >> 4;
-      float2 o2[RUN][2];
-#pragma unroll
-      for (int j = 0; j < RUN; ++j) o2[j][0] = o2[j][1] = make_float2(0.f, 0.f);
       const int r0 = sp * RUN;
       if (sp < NRUN) {
+        float2 o2[RUN][2];
+#pragma unroll
+        for (int j = 0; j < RUN; ++j) o2[j][0] = o2[j][1] = make_float2(0.f, 0.f);
         const int ti = r0 / (TOH * TOW), rem = r0 % (TOH * TOW), oy = rem / TOW, ox0 = rem % TOW;
         const int pbase = ti * IH * IW + oy * IW + ox0;
         float2 w2[9][2];
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp) {
-          const float4 wv = *reinterpret_cast<const float4*>(tab + 256 + tp * 64 + cg * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(tb + 256 + tp * 64 + cg * 4);
           w2[tp][0] = make_float2(wv.x, wv.y);
           w2[tp][1] = make_float2(wv.z, wv.w);
         }
@@ -319,12 +344,8 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
             }
           }
         }
-      }
-      // the project MMA of the previous slice must have read sH2 before it is rewritten
-      wait_projects(p_issued);
-      if (sp < NRUN) {
-        const float4 s2 = *reinterpret_cast<const float4*>(tab + 128 + cg * 4);
-        const float4 t2 = *reinterpret_cast<const float4*>(tab + 192 + cg * 4);
+        const float4 s2 = *reinterpret_cast<const float4*>(tb + 128 + cg * 4);
+        const float4 t2 = *reinterpret_cast<const float4*>(tb + 192 + cg * 4);
 #pragma unroll
         for (int j = 0; j < RUN; ++j) {
           float v[4] = {fmaf(s2.x, o2[j][0].x, t2.x), fmaf(s2.y, o2[j][0].y, t2.y),
@@ -335,6 +356,8 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
               make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
         }
       }
+      if (has_next) tab_store(tab + ((gc + 1) & 1) * 832);   // readers: behind S3
+      cp_wait<0>();                   // W3(gc) landed
       fence_proxy_async_smem();
       __syncthreads();                                                     // S3: a2 tile complete
       if (warp == 0) {
@@ -347,8 +370,7 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ad = umma_smem_desc(sH2_u + (uint32_t)(kk * 32), 16, 1024);
-              const uint64_t bd =
-                  umma_smem_desc(wb + (uint32_t)(p.off_w3 + h * nn * 128 + kk * 32), 16, 1024);
+              const uint64_t bd = umma_smem_desc(sW3_u + (uint32_t)(h * nn * 128 + kk * 32), 16, 1024);
               umma_bf16(tmem + (uint32_t)(p.proj_col + h * nn), ad, bd, idesc,
                         (c > 0 || kk > 0) ? 1u : 0u);
             }
@@ -356,16 +378,9 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
         }
         __syncwarp();
       }
-      ++p_issued;
-      tab_store();    // next slice's tables (this slice's readers are behind S3)
-      if (p.nbuf == 1 && c + 1 < NC) {
-        wait_projects(p_issued);        // W3 / W1 of this slice are free
-        load_w(c + 1, 0);
-        cp_commit();
-      }
     }
     // ---- epilogue 2: y = bf16(bn3(h3) (+ x)) ----
-    wait_projects(p_issued);
+    wait_projects(gc);
     tc_fence_after();
     {
       const int q = warp & 3, r = q * 32 + lane;
@@ -403,8 +418,9 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
         }
       }
     }
+    // the next tile's first project MMA (accumulate = 0) is issued behind S2 and S3 of its first
+    // slice: every warp's accumulator reads above are complete by then
     tc_fence_before();
-    __syncthreads();   // accumulators and staging buffers are free for the next tile
   }
   tc_fence_before();
   __syncthreads();
@@ -418,20 +434,18 @@ __global__ void __launch_bounds__(256, 1) block_eval_kernel(const __grid_constan
 // host
 // ------------------------------------------------------------------------------------------------
 template <class G>
-static cudaError_t launch_eval(BlockEvalDev& p, size_t smem_fixed, cudaStream_t st) {
+static cudaError_t launch_eval(BlockEvalDev& p, cudaStream_t st) {
   // shared-memory plan (bytes from the 1024-aligned base)
   p.xpanel_bytes = G::MT * 16384;
   int off = p.KB * p.xpanel_bytes;
   p.off_w = off;
-  p.off_w3 = p.KB * 8192;
+  p.off_w3 = p.KB * 8192;                      // W3 slice behind the W1 slice
   p.wbuf_bytes = ((p.off_w3 + p.Npad * 128) + 1023) & ~1023;
-  const int rest = G::MT * 16384 + 16384 + (int)smem_fixed;
-  p.nbuf = (off + 2 * p.wbuf_bytes + rest <= 227 * 1024 - 1024) ? 2 : 1;
-  if (p.NC == 1) p.nbuf = 1;
-  off += p.nbuf * p.wbuf_bytes;
+  p.nbuf = 1;
+  off += p.wbuf_bytes;
   p.off_h1 = off; off += G::MT * 16384;
   p.off_h2 = off; off += 16384;
-  p.off_tab = off; off += (256 + 576) * 4;
+  p.off_tab = off; off += 2 * 832 * 4;     // two table sets: s1 t1 s2 t2 [64] + taps [9][64]
   p.off_c3 = off; off += 2 * p.Npad * 4;
   p.off_bars = (off + 15) & ~15; off = p.off_bars + 32;
   const int smem = off;
@@ -444,34 +458,33 @@ static cudaError_t launch_eval(BlockEvalDev& p, size_t smem_fixed, cudaStream_t 
   const int tiles_img = p.tiles_h * p.tiles_w;
   const int groups = (p.N + G::TI - 1) / G::TI;
   p.num_tiles = groups * tiles_img;
-  // the dynamic-smem limit is process-wide state: only ever raise it; occupancy cached per size
+  // the dynamic-smem limit is process-wide state: only ever raise it
   static std::mutex mu;
   static int attr = 0;
-  static int occ_smem[8], occ_val[8], n_occ = 0;
-  int per_sm = 0;
   {
     std::lock_guard<std::mutex> lock(mu);
     if (attr < smem) {
       cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
+      // two CTAs of ~100 KB need the largest shared-memory carve-out
+      e = cudaFuncSetAttribute(block_eval_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               (int)cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
       attr = smem;
     }
-    for (int i = 0; i < n_occ; ++i)
-      if (occ_smem[i] == smem) per_sm = occ_val[i];
-    if (per_sm == 0) {
-      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, block_eval_kernel<G>,
-                                                                    256, smem);
-      if (e != cudaSuccess) return e;
-      if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-      if (n_occ < 8) { occ_smem[n_occ] = smem; occ_val[n_occ++] = per_sm; }
-    }
   }
-  // resident CTAs per SM are also bounded by the TMEM columns each one allocates
-  if (per_sm > 512 / cols) per_sm = 512 / cols;
-  if (per_sm > 2) per_sm = 2;
+  // Resident CTAs per SM: 228 KB of shared memory (+1 KB the driver reserves per CTA), 512 TMEM
+  // columns, 64 Ki registers (__launch_bounds__(256, 2): <= 128 per thread).
+  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for the 101 KB configurations that
+  // ncu's launch__occupancy_limit_* and the hardware both place twice: computed here.)
+  int per_sm = (2 * (smem + 1024) <= 228 * 1024 && 2 * cols <= 512) ? 2 : 1;
   long long cap = (long long)max_ctas() * per_sm;
   const int grid = (int)(p.num_tiles < cap ? p.num_tiles : cap);
+  static const bool dbg = getenv("YAMB_EVAL_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "block_eval: tiles %d grid %d per_sm %d smem %d tmem_cols %d Npad %d NC %d KB %d\n",
+            p.num_tiles, grid, per_sm, smem, cols, p.Npad, p.NC, p.KB);
   block_eval_kernel<G><<<grid, 256, smem, st>>>(p);
   return cudaGetLastError();
 }
@@ -533,9 +546,9 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   p.tiles_h = (a->H + cands[best].toh - 1) / cands[best].toh;
   p.tiles_w = (a->W + cands[best].tow - 1) / cands[best].tow;
   cudaError_t e;
-  if (best == 0) e = launch_eval<EvGeom<8, 16, 1>>(p, 8192, st);
-  else if (best == 1) e = launch_eval<EvGeom<7, 14, 1>>(p, 8192, st);
-  else e = launch_eval<EvGeom<7, 7, 2>>(p, 8192, st);
+  if (best == 0) e = launch_eval<EvGeom<8, 16, 1>>(p, st);
+  else if (best == 1) e = launch_eval<EvGeom<7, 14, 1>>(p, st);
+  else e = launch_eval<EvGeom<7, 7, 2>>(p, st);
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
   return 0;
 }
