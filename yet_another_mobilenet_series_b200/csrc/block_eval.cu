@@ -7,11 +7,11 @@
 // under torch.no_grad()).  With the statistics known up front the block is a pure function of an
 // input tile plus a one-pixel halo: SURVEY.md §7.1 step 2 / §7.2, BASELINE.json's "fused block".
 //
-// One persistent CTA per SM (two where shared memory and TMEM allow) walks output tiles of <= 128
-// pixels (8x16, 7x14 or two 7x7 images).  Per tile:
-//   x tile (+halo, <= 256 pixels) --cp.async--> smem, SWIZZLE_128B K-major  (A operand, read once)
+// Persistent CTAs (two per SM where shared memory and TMEM allow) walk output tiles of <= 112
+// pixels (7x16, 7x14 or two 7x7 images).  Per tile:
+//   x tile (+halo, <= 162 pixels) --TMA 4-D box, zero fill outside the image--> smem (A operand)
 //   for every 64-channel slice of the hidden dimension:
-//     W1 slice, W3 slice --cp.async--> smem (double-buffered when it fits)
+//     W1 slice, W3 slice --TMA--> smem
 //     tcgen05.mma  [256 px x Cin] x [Cin x 64]       -> TMEM (fp32)                   expand
 //     tcgen05.ld -> BatchNorm1 + act -> bf16, zero outside the image -> smem          epilogue 1
 //     3x3 stencil on the CUDA cores (FFMA2) -> BatchNorm2 + act -> bf16 -> smem (A operand layout)
@@ -21,9 +21,17 @@
 // input) never leave the SM.  BatchNorm folding (gamma * rsqrt(var + eps), beta - mean * scale) is
 // done by the kernel from the module's own buffers: no preparation launches.
 //
+// Roles: 8 warps; all of them run the two epilogues, warps 0-6 run the stencil (14 runs of 7 or 8
+// outputs x 16 channel groups), and while they do, ONE thread of warp 7 drives the machine: TMA
+// loads of the next operands, tcgen05.mma of the next slice's expand and of this slice's project.
+// Every staging buffer is single and refilled right after its last reader retired:
+//   wait expand(gc) | TMA W1(gc+1) [+ x of the next tile] | epilogue 1 | S2 | TMA W3(gc),
+//   expand(gc+1) || stencil -> a2 | S3 | project(gc) | (last slice of a tile: epilogue 2)
+//
 // Rounding points: a1 = bf16(act(bn1(fp32 accumulator))), a2 = bf16(act(bn2(fp32 stencil))),
 // y = bf16(bn3(fp32 accumulator) + x) — one rounding fewer per stage than the four-launch path
 // (which stores the raw convolution outputs in bf16 first).
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -44,63 +52,62 @@ struct BnEvalDev {
 
 struct BlockEvalDev {
   int N, H, W, Cin, Chid, Cout, act, residual;
-  const __nv_bfloat16 *x, *w1, *w3;
+  const __nv_bfloat16* x;
   const float* wdw;
   BnEvalDev bn1, bn2, bn3;
   __nv_bfloat16* y;
   int tiles_h, tiles_w, num_tiles;
-  int KB;            // 64-channel panels of the x tile
-  int cpr;           // 16-byte chunks per x / W1 row incl. the zero padding to a multiple of 16 channels
+  int KB;            // 64-channel panels of the x tile / the W1 slice
+  int nks;           // K steps (16 channels) of the expand MMA
   int Npad;          // Cout rounded up to a multiple of 16 (UMMA N)
   int NC;            // 64-channel slices of the hidden dimension
-  int nbuf;          // weight staging buffers (1 or 2)
-  int xpanel_bytes;  // MT * 16 KB
-  int off_w, wbuf_bytes, off_w3, off_tab, off_h1, off_h2, off_c3, off_bars;
+  int xpanel_bytes;  // bytes between the 64-channel panels of the x tile
+  int off_w1, off_w3, off_h1, off_h2, off_tab, off_c3, off_bars;
   int tmem_cols, proj_col;
 };
 
+constexpr int kH1Pitch = 144;    // bytes per pixel of the a1 tile: 64 bf16 + 16 (conflict-free, no swizzle)
+constexpr int kTabFloats = 832;  // s1 t1 s2 t2 [64] + taps [9][64]
+
 // Output tile TI images x TOH x TOW pixels (<= 128 = the M of the project MMA); the input tile with
-// its one-pixel halo is the M of the expand MMAs (MT tiles of 128 rows).
+// its one-pixel halo is the M of the expand MMAs (2 tiles of 128 rows, rows >= NPI are don't-care).
 template <int TOH_, int TOW_, int TI_>
 struct EvGeom {
   static constexpr int TOH = TOH_, TOW = TOW_, TI = TI_;
   static constexpr int IH = TOH + 2, IW = TOW + 2;
   static constexpr int NPI = TI * IH * IW;
-  static constexpr int MT = (NPI + 127) / 128;
   static constexpr int NPO = TI * TOH * TOW;
   static constexpr int RUN = (TOW % 8 == 0) ? 8 : 7;   // consecutive outputs of one row per stencil thread
   static constexpr int NRUN = NPO / RUN;
-  static_assert(NPO <= 128 && MT <= 2 && TOW % RUN == 0 && NRUN <= 16, "tile geometry");
+  static_assert(NPO <= 128 && NPI > 128 && NPI <= 256 && TOW % RUN == 0 && NRUN <= 14,
+                "tile geometry (warp 7 must stay free of stencil work)");
 };
 
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool ok) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0)
-               : "memory");
-}
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 template <class G>
-__global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constant__ BlockEvalDev p) {
+__global__ void __launch_bounds__(256, 2)
+block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                  const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ BlockEvalDev p) {
   constexpr int TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
-  constexpr int NPI = G::NPI, MT = G::MT, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN;
+  constexpr int NPI = G::NPI, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint64_t* bar_e = reinterpret_cast<uint64_t*>(smem + p.off_bars);
-  uint64_t* bar_p = bar_e + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_e + 2);
+  uint64_t* bar_e = reinterpret_cast<uint64_t*>(smem + p.off_bars);   // expand MMAs of a slice retired
+  uint64_t* bar_p = bar_e + 1;                                         // project MMAs of a slice retired
+  uint64_t* bar_ld = bar_e + 2;                                        // TMA: W1 slice (+ x tile) landed
+  uint64_t* bar_w3 = bar_e + 3;                                        // TMA: W3 slice landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_e + 4);
   float* c3 = reinterpret_cast<float*>(smem + p.off_c3);     // [scale3 | shift3] x Npad
-  float* tab = reinterpret_cast<float*>(smem + p.off_tab);   // s1 t1 s2 t2 [64] + taps [9][64]
+  float* tab = reinterpret_cast<float*>(smem + p.off_tab);   // two sets of kTabFloats
   uint8_t* sH1 = smem + p.off_h1;
   uint8_t* sH2 = smem + p.off_h2;
-  const uint32_t sX_u = smem_u32(smem), sH2_u = smem_u32(sH2);
+  const uint32_t sX_u = smem_u32(smem), sW1_u = sX_u + (uint32_t)p.off_w1,
+                 sW3_u = sX_u + (uint32_t)p.off_w3, sH2_u = smem_u32(sH2);
 
   if (tid == 0) {
     mbar_init(bar_e, 1);
     mbar_init(bar_p, 1);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_w3, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -119,14 +126,24 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
   }
   // rows of the project A operand beyond the tile's pixels are never written: keep them zero
   for (int i = tid; i < 16384 / 16; i += 256) reinterpret_cast<uint4*>(sH2)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const bool control = warp == 7 && lane == 0;
+  if (control) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW3);
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const ActParam ap = make_act(p.act);
+  const bool lean = ap.kind == 0;   // relu / relu6 / none: clamp the packed bf16 pair
+  const uint32_t lo2 = pack_bf16(ap.lo, ap.lo), hi2 = pack_bf16(ap.hi, ap.hi);
 
   // ---- per-slice coefficient tables (double-buffered), fetched one slice ahead into registers ----
-  // threads 0..127: BatchNorm1 / BatchNorm2 of hidden channel (slice*64 + tid%64); all threads: taps
+  // threads 0..127: BatchNorm1 / BatchNorm2 of hidden channel slice*64 + tid%64;
+  // thread (ch = tid/4, q = tid%4 < 3): taps 3q..3q+2 of that channel
   float pre_s = 0.f, pre_t = 0.f, pre_w[3] = {0.f, 0.f, 0.f};
   auto tab_fetch = [&](int c) {
     if (tid < 128) {
@@ -139,12 +156,11 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
         pre_t = (b.beta ? __ldg(b.beta + hc) : 0.f) - __ldg(b.mean + hc) * pre_s;
       }
     }
+    const int hc = c * 64 + (tid >> 2), q = tid & 3;
+    const bool ok = q < 3 && hc < p.Chid;
+    const float* src = p.wdw + (size_t)hc * 9 + q * 3;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = tid + 256 * k;   // i = ch * 9 + tap: contiguous in global memory
-      const int hc = c * 64 + i / 9;
-      pre_w[k] = (i < 576 && hc < p.Chid) ? __ldg(p.wdw + (size_t)c * 576 + i) : 0.f;
-    }
+    for (int k = 0; k < 3; ++k) pre_w[k] = ok ? __ldg(src + k) : 0.f;
   };
   auto tab_store = [&](float* tb) {
     if (tid < 128) {
@@ -152,71 +168,45 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
       tb[which * 128 + ch] = pre_s;          // s1 at 0, s2 at 128
       tb[which * 128 + 64 + ch] = pre_t;     // t1 at 64, t2 at 192
     }
+    const int q = tid & 3;
+    if (q < 3) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const int i = tid + 256 * k;
-      if (i < 576) tb[256 + (i % 9) * 64 + i / 9] = pre_w[k];
+      for (int k = 0; k < 3; ++k) tb[256 + (q * 3 + k) * 64 + (tid >> 2)] = pre_w[k];
     }
   };
 
-  // ---- operand staging ---------------------------------------------------------------------------
-  auto load_x = [&](int t) {
+  // ---- the control thread: TMA + tcgen05.mma ----------------------------------------------------
+  const uint64_t ad_x = umma_smem_desc(sX_u, 16, 1024), bd_w1 = umma_smem_desc(sW1_u, 16, 1024);
+  const uint64_t ad_h2 = umma_smem_desc(sH2_u, 16, 1024), bd_w3 = umma_smem_desc(sW3_u, 16, 1024);
+  const uint32_t idesc_e = umma_idesc_bf16(128, 64, 0, 0);
+  const int p_halves = p.Npad > 256 ? 2 : 1, p_nn = p.Npad / p_halves;
+  const uint32_t idesc_p = umma_idesc_bf16(128, p_nn, 0, 0);
+  uint32_t ld_par = 0, w3_par = 0;
+  auto tma_x = [&](int t) {            // x tile of tile t: one 4-D box per 64-channel panel
     const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
-    const int total = NPI * p.cpr;
-    for (int i = tid; i < total; i += 256) {
-      const int r = i / p.cpr, j = i - r * p.cpr;
-      const int ti = r / (IH * IW), rem = r % (IH * IW), iy = rem / IW, ix = rem % IW;
-      const int n = g * TI + ti, yy = ty * TOH - 1 + iy, xx = tx * TOW - 1 + ix;
-      const bool ok = n < p.N && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W &&
-                      j * 8 < p.Cin;
-      const __nv_bfloat16* src =
-          ok ? p.x + ((size_t)(n * p.H + yy) * p.W + xx) * p.Cin + j * 8 : p.x;
-      cp_async_16(sX_u + (uint32_t)((j >> 3) * p.xpanel_bytes + r * 128 + (((j & 7) ^ (r & 7)) << 4)),
-                  src, ok);
-    }
+    for (int kb = 0; kb < p.KB; ++kb)
+      tma_load_4d(&tmX, bar_ld, sX_u + (uint32_t)(kb * p.xpanel_bytes), kb * 64, tx * TOW - 1,
+                  ty * TOH - 1, g * TI);
   };
-  const uint32_t sW1_u = sX_u + (uint32_t)p.off_w, sW3_u = sW1_u + (uint32_t)p.off_w3;
-  auto load_w1 = [&](int c) {
-    const int n1 = 64 * p.cpr;
-    for (int i = tid; i < n1; i += 256) {
-      const int hr = i / p.cpr, j = i - hr * p.cpr, hc = c * 64 + hr;
-      const bool ok = hc < p.Chid && j * 8 < p.Cin;
-      const __nv_bfloat16* src = ok ? p.w1 + (size_t)hc * p.Cin + j * 8 : p.w1;
-      cp_async_16(sW1_u + (uint32_t)((j >> 3) * 8192 + hr * 128 + (((j & 7) ^ (hr & 7)) << 4)), src, ok);
-    }
+  auto tma_w1 = [&](int c) {
+    for (int kb = 0; kb < p.KB; ++kb)
+      tma_load_2d(&tmW1, bar_ld, smem + p.off_w1 + kb * 8192, kb * 64, c * 64);
   };
-  auto load_w3 = [&](int c) {
-    const int n3 = p.Npad * 8;
-    for (int i = tid; i < n3; i += 256) {
-      const int n = i >> 3, j = i & 7, kc = c * 64 + j * 8;
-      const bool ok = n < p.Cout && kc < p.Chid;
-      const __nv_bfloat16* src = ok ? p.w3 + (size_t)n * p.Chid + kc : p.w3;
-      cp_async_16(sW3_u + (uint32_t)(n * 128 + ((j ^ (n & 7)) << 4)), src, ok);
-    }
-  };
-  // expand MMAs of one slice: [MT x 128 pixels, Cin] x [Cin, 64] -> TMEM columns [0, MT*64)
-  auto issue_expand = [&]() {
-    if (warp == 0) {
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
-        const int nks = p.cpr >> 1;   // K steps of 16 channels
+  auto issue_expand = [&]() {          // [2 x 128 pixels, Cin] x [Cin, 64] -> TMEM columns [0, 128)
+    tc_fence_after();
 #pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt)
-          for (int ks = 0; ks < nks; ++ks) {
-            const int kb = ks >> 2, kk = ks & 3;
-            const uint64_t ad = umma_smem_desc(
-                sX_u + (uint32_t)(kb * p.xpanel_bytes + mt * 16384 + kk * 32), 16, 1024);
-            const uint64_t bd = umma_smem_desc(sW1_u + (uint32_t)(kb * 8192 + kk * 32), 16, 1024);
-            umma_bf16(tmem + (uint32_t)(mt * 64), ad, bd, idesc, ks > 0 ? 1u : 0u);
-          }
-        umma_commit(bar_e);
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll 1
+      for (int ks = 0; ks < p.nks; ++ks) {
+        const int kb = ks >> 2, kk = ks & 3;
+        umma_bf16(tmem + (uint32_t)(mt * 64),
+                  ad_x + (uint64_t)((kb * p.xpanel_bytes + mt * 16384 + kk * 32) >> 4),
+                  bd_w1 + (uint64_t)((kb * 8192 + kk * 32) >> 4), idesc_e, ks > 0 ? 1u : 0u);
       }
-      __syncwarp();
-    }
+    umma_commit(bar_e);
   };
 
-  uint32_t pe = 0, pp = 0;          // mbarrier phase parities
+  uint32_t pe = 0, pp = 0;          // parities of bar_e / bar_p (every thread follows them)
   int p_waited = 0;                 // project commits waited for (whole kernel)
   auto wait_projects = [&](int upto) {
     while (p_waited < upto) {
@@ -226,97 +216,131 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
     }
   };
 
-  // Software pipeline over the slices gc = 0, 1, ... of all tiles of this CTA.  While slice gc is in
-  // its epilogue / stencil, the tensor core already runs expand(gc+1) and project(gc-1), and the
-  // operands of gc+1 (W1 slice; the x tile when gc+1 starts a new tile) stream in: every staging
-  // buffer is single, each is refilled right after its last reader retired.
-  //   wait expand(gc) | load W1(gc+1) [+ x] | epilogue 1 | load W3(gc) | S2 | issue expand(gc+1)
-  //   | stencil -> sH2 | S3 | issue project(gc) | (last slice of a tile: epilogue 2)
+  // ---- per-thread geometry (the same in every tile) ------------------------------------------------
+  // epilogue 1: this thread's pixel row of the input tile (warps 0-3: rows 0..127, 4-7: 128..255)
+  const int e1_r = (warp >> 2) * 128 + (warp & 3) * 32 + lane;
+  const int e1_ti = e1_r / (IH * IW);
+  const int e1_dy = (e1_r % (IH * IW)) / IW - 1, e1_dx = (e1_r % (IH * IW)) % IW - 1;
+  // stencil: RUN consecutive outputs of one row x 4 channels
+  const int cg = tid & 15, sp = tid >> 4;
+  const int r0 = sp * RUN;
+  const int s_ti = r0 / (TOH * TOW), s_oy = (r0 % (TOH * TOW)) / TOW, s_ox0 = (r0 % (TOH * TOW)) % TOW;
+  const uint8_t* s_hb = sH1 + (s_ti * IH * IW + s_oy * IW + s_ox0) * kH1Pitch + cg * 8;
+  // epilogue 2: this thread's output pixel
+  const int e2_r = (warp & 3) * 32 + lane;
+  const int e2_ti = e2_r / (TOH * TOW);
+  const int e2_oy = (e2_r % (TOH * TOW)) / TOW, e2_ox = (e2_r % (TOH * TOW)) % TOW;
+
   const int NC = p.NC;
   int t = blockIdx.x;
-  if (t < p.num_tiles) {
-    load_x(t);
-    load_w1(0);
-    cp_commit();
-    tab_fetch(0);
-    tab_store(tab);
-    cp_wait<0>();
-    fence_proxy_async_smem();
-    __syncthreads();
+  tab_fetch(0);
+  tab_store(tab);
+  if (control) {
+    mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (NPI * 128 + 8192)));
+    tma_x(t);
+    tma_w1(0);
+    mbar_wait(bar_ld, ld_par);
+    ld_par ^= 1;
     issue_expand();
   }
+  __syncthreads();   // tables of slice 0
   int gc = 0;
   for (; t < p.num_tiles; t += gridDim.x) {
     const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
+    const bool more_tiles = t + (int)gridDim.x < p.num_tiles;
+    bool e1_inside;
+    {
+      const int n = g * TI + e1_ti, yy = ty * TOH + e1_dy, xx = tx * TOW + e1_dx;
+      e1_inside = e1_r < NPI && n < p.N && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+    }
     for (int c = 0; c < NC; ++c, ++gc) {
       const bool last_c = c + 1 == NC;
-      const bool has_next = !last_c || t + (int)gridDim.x < p.num_tiles;
-      float* tb = tab + (gc & 1) * 832;
+      const bool has_next = !last_c || more_tiles;
+      const float* tb = tab + (gc & 1) * kTabFloats;
       mbar_wait(bar_e, pe);           // expand(gc) retired: accumulator ready, sW1 (and sX) free
       pe ^= 1;
       tc_fence_after();
       if (has_next) {
-        if (last_c) load_x(t + gridDim.x);
-        load_w1(last_c ? 0 : c + 1);
-        cp_commit();                                                        // group A
+        if (control) {
+          mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (8192 + (last_c ? NPI * 128 : 0))));
+          if (last_c) tma_x(t + gridDim.x);
+          tma_w1(last_c ? 0 : c + 1);
+        }
         tab_fetch(last_c ? 0 : c + 1);   // registers; stored before S3
       }
+      __syncwarp();                   // warp 7 reconverges before the warp-wide tcgen05.ld
       // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
       {
-        const int q = warp & 3;
-#pragma unroll 1
-        for (int mt = warp >> 2; mt < MT; mt += 2) {
-          const int r = mt * 128 + q * 32 + lane;
-          const int ti = r / (IH * IW), rem = r % (IH * IW), iy = rem / IW, ix = rem % IW;
-          const int n = g * TI + ti, yy = ty * TOH - 1 + iy, xx = tx * TOW - 1 + ix;
-          const bool inside = r < NPI && n < p.N && (unsigned)yy < (unsigned)p.H &&
-                              (unsigned)xx < (unsigned)p.W;
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+        uint8_t* dst = sH1 + e1_r * kH1Pitch;
 #pragma unroll
-          for (int hcol = 0; hcol < 2; ++hcol) {
-            uint32_t acc[32];
-            tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + hcol * 32), acc);
-            tmem_ld_wait();
+        for (int hcol = 0; hcol < 2; ++hcol) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + (uint32_t)(hcol * 32), acc);
+          tmem_ld_wait();
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              const int cb = hcol * 32 + ch * 8;
-              const float4 s0 = *reinterpret_cast<const float4*>(tb + cb);
-              const float4 s1 = *reinterpret_cast<const float4*>(tb + cb + 4);
-              const float4 t0 = *reinterpret_cast<const float4*>(tb + 64 + cb);
-              const float4 t1 = *reinterpret_cast<const float4*>(tb + 64 + cb + 4);
-              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-              const float tt[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          for (int ch = 0; ch < 4; ++ch) {
+            const int cb = hcol * 32 + ch * 8;
+            const float4 s0 = *reinterpret_cast<const float4*>(tb + cb);
+            const float4 s1 = *reinterpret_cast<const float4*>(tb + cb + 4);
+            const float4 t0 = *reinterpret_cast<const float4*>(tb + 64 + cb);
+            const float4 t1 = *reinterpret_cast<const float4*>(tb + 64 + cb + 4);
+            const float2 ss[4] = {make_float2(s0.x, s0.y), make_float2(s0.z, s0.w),
+                                  make_float2(s1.x, s1.y), make_float2(s1.z, s1.w)};
+            const float2 tt[4] = {make_float2(t0.x, t0.y), make_float2(t0.z, t0.w),
+                                  make_float2(t1.x, t1.y), make_float2(t1.z, t1.w)};
+            uint32_t ow[4];
+            if (lean) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 v = ffma2(ss[e], make_float2(__uint_as_float(acc[ch * 8 + 2 * e]),
+                                                          __uint_as_float(acc[ch * 8 + 2 * e + 1])),
+                                       tt[e]);
+                ow[e] = clamp_bf16x2(pack_bf16(v.x, v.y), lo2, hi2);
+              }
+            } else {
               float v[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaf(ss[e], __uint_as_float(acc[ch * 8 + e]), tt[e]);
+              for (int e = 0; e < 4; ++e) {
+                const float2 w = ffma2(ss[e], make_float2(__uint_as_float(acc[ch * 8 + 2 * e]),
+                                                          __uint_as_float(acc[ch * 8 + 2 * e + 1])),
+                                       tt[e]);
+                v[2 * e] = w.x;
+                v[2 * e + 1] = w.y;
+              }
               act_vec<8>(v, ap);
-              uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              if (!inside) o = make_uint4(0u, 0u, 0u, 0u);
-              if (r < NPI)
-                *reinterpret_cast<uint4*>(sH1 + r * 128 + (((cb >> 3) ^ (r & 7)) << 4)) = o;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) ow[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
             }
+            uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            if (!e1_inside) o = make_uint4(0u, 0u, 0u, 0u);
+            if (e1_r < NPI) *reinterpret_cast<uint4*>(dst + cb * 2) = o;
           }
         }
       }
       // project(gc-1) retired long ago (it was issued before this slice's accumulator wait):
       // sW3 and sH2 are free
       wait_projects(gc);
-      load_w3(c);
-      cp_commit();                                                          // group B
-      cp_wait<1>();                   // group A landed (B may still be in flight)
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();                                                     // S2: a1 tile complete
-      if (has_next) issue_expand();   // expand(gc+1) runs under the stencil
-      // ---- 3x3 stencil: RUN consecutive outputs of one row x 4 channels per thread ----
-      const int cg = tid & 15, sp = tid >> 4;
-      const int r0 = sp * RUN;
-      if (sp < NRUN) {
+      if (warp == 7) {
+        // ---- control: W3 slice in, the next slice's expand out (under the stencil) ----
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar_w3, (uint32_t)(p.Npad * 128));
+          for (int h = 0; h < p_halves; ++h)
+            tma_load_2d(&tmW3, bar_w3, smem + p.off_w3 + h * p_nn * 128, c * 64, h * p_nn);
+          if (has_next) {
+            mbar_wait(bar_ld, ld_par);     // landed during epilogue 1
+            ld_par ^= 1;
+            issue_expand();
+          }
+        }
+        __syncwarp();
+      } else if (sp < NRUN) {
+        // ---- 3x3 stencil: RUN consecutive outputs of one row x 4 channels per thread ----
         float2 o2[RUN][2];
 #pragma unroll
         for (int j = 0; j < RUN; ++j) o2[j][0] = o2[j][1] = make_float2(0.f, 0.f);
-        const int ti = r0 / (TOH * TOW), rem = r0 % (TOH * TOW), oy = rem / TOW, ox0 = rem % TOW;
-        const int pbase = ti * IH * IW + oy * IW + ox0;
         float2 w2[9][2];
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp) {
@@ -324,14 +348,11 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
           w2[tp][0] = make_float2(wv.x, wv.y);
           w2[tp][1] = make_float2(wv.z, wv.w);
         }
-        const uint8_t* hb = sH1 + (cg & 1) * 8;
-        const int cgh = cg >> 1;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
           for (int ixx = 0; ixx < RUN + 2; ++ixx) {
-            const int pi = pbase + ky * IW + ixx;
-            const uint2 a = *reinterpret_cast<const uint2*>(hb + pi * 128 + ((cgh ^ (pi & 7)) << 4));
+            const uint2 a = *reinterpret_cast<const uint2*>(s_hb + (ky * IW + ixx) * kH1Pitch);
             const float2 alo = make_float2(bf16lo(a.x), bf16hi(a.x));
             const float2 ahi = make_float2(bf16lo(a.y), bf16hi(a.y));
 #pragma unroll
@@ -346,53 +367,56 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
         }
         const float4 s2 = *reinterpret_cast<const float4*>(tb + 128 + cg * 4);
         const float4 t2 = *reinterpret_cast<const float4*>(tb + 192 + cg * 4);
+        const float2 s2a = make_float2(s2.x, s2.y), s2b = make_float2(s2.z, s2.w);
+        const float2 t2a = make_float2(t2.x, t2.y), t2b = make_float2(t2.z, t2.w);
 #pragma unroll
         for (int j = 0; j < RUN; ++j) {
-          float v[4] = {fmaf(s2.x, o2[j][0].x, t2.x), fmaf(s2.y, o2[j][0].y, t2.y),
-                        fmaf(s2.z, o2[j][1].x, t2.z), fmaf(s2.w, o2[j][1].y, t2.w)};
-          act_vec<4>(v, ap);
+          const float2 va = ffma2(s2a, o2[j][0], t2a), vb = ffma2(s2b, o2[j][1], t2b);
+          uint32_t wa, wb;
+          if (lean) {
+            wa = clamp_bf16x2(pack_bf16(va.x, va.y), lo2, hi2);
+            wb = clamp_bf16x2(pack_bf16(vb.x, vb.y), lo2, hi2);
+          } else {
+            float v[4] = {va.x, va.y, vb.x, vb.y};
+            act_vec<4>(v, ap);
+            wa = pack_bf16(v[0], v[1]);
+            wb = pack_bf16(v[2], v[3]);
+          }
           const int r = r0 + j;
           *reinterpret_cast<uint2*>(sH2 + r * 128 + (((cg >> 1) ^ (r & 7)) << 4) + (cg & 1) * 8) =
-              make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+              make_uint2(wa, wb);
         }
       }
-      if (has_next) tab_store(tab + ((gc + 1) & 1) * 832);   // readers: behind S3
-      cp_wait<0>();                   // W3(gc) landed
+      if (has_next) tab_store(tab + ((gc + 1) & 1) * kTabFloats);   // its readers are behind S3
       fence_proxy_async_smem();
       __syncthreads();                                                     // S3: a2 tile complete
-      if (warp == 0) {
+      if (control) {
+        mbar_wait(bar_w3, w3_par);     // landed during the stencil
+        w3_par ^= 1;
         tc_fence_after();
-        if (lane == 0) {
-          const int halves = p.Npad > 256 ? 2 : 1;
-          const int nn = p.Npad / halves;
-          const uint32_t idesc = umma_idesc_bf16(128, nn, 0, 0);
-          for (int h = 0; h < halves; ++h)
+        for (int h = 0; h < p_halves; ++h)
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = umma_smem_desc(sH2_u + (uint32_t)(kk * 32), 16, 1024);
-              const uint64_t bd = umma_smem_desc(sW3_u + (uint32_t)(h * nn * 128 + kk * 32), 16, 1024);
-              umma_bf16(tmem + (uint32_t)(p.proj_col + h * nn), ad, bd, idesc,
-                        (c > 0 || kk > 0) ? 1u : 0u);
-            }
-          umma_commit(bar_p);
-        }
-        __syncwarp();
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem + (uint32_t)(p.proj_col + h * p_nn), ad_h2 + (uint64_t)(kk * 2),
+                      bd_w3 + (uint64_t)((h * p_nn * 128 + kk * 32) >> 4), idesc_p,
+                      (c > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(bar_p);
       }
     }
     // ---- epilogue 2: y = bf16(bn3(h3) (+ x)) ----
     wait_projects(gc);
     tc_fence_after();
+    __syncwarp();
     {
-      const int q = warp & 3, r = q * 32 + lane;
-      const int ti = r / (TOH * TOW), rem = r % (TOH * TOW), oy = rem / TOW, ox = rem % TOW;
-      const int n = g * TI + ti, yy = ty * TOH + oy, xx = tx * TOW + ox;
-      const bool valid = r < NPO && n < p.N && yy < p.H && xx < p.W;
+      const int n = g * TI + e2_ti, yy = ty * TOH + e2_oy, xx = tx * TOW + e2_ox;
+      const bool valid = e2_r < NPO && n < p.N && yy < p.H && xx < p.W;
       const size_t pix = valid ? ((size_t)(n * p.H + yy) * p.W + xx) : 0;
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)p.proj_col;
       const int units = p.Npad >> 4;
 #pragma unroll 1
       for (int u = warp >> 2; u < units; u += 2) {
         uint32_t acc[16];
-        tmem_ld_32x16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.proj_col + u * 16), acc);
+        tmem_ld_32x16(taddr + (uint32_t)(u * 16), acc);
         tmem_ld_wait();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -433,31 +457,69 @@ __global__ void __launch_bounds__(256, 2) block_eval_kernel(const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
+static int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  static PFN_encodeTiled encode = get_encode_tiled();
+  if (!encode) return set_error(YAMB_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+                      dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(YAMB_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 template <class G>
-static cudaError_t launch_eval(BlockEvalDev& p, cudaStream_t st) {
-  // shared-memory plan (bytes from the 1024-aligned base)
-  p.xpanel_bytes = G::MT * 16384;
+static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t st) {
+  // ---- shared-memory plan (bytes from the 1024-aligned base) ----
+  // x tile: NPI rows of 128 B per 64-channel panel; the second 128-row MMA tile of a panel reads
+  // past them (rows that are never used): those reads stay inside this CTA's allocation
+  p.xpanel_bytes = (G::NPI * 128 + 1023) & ~1023;
   int off = p.KB * p.xpanel_bytes;
-  p.off_w = off;
-  p.off_w3 = p.KB * 8192;                      // W3 slice behind the W1 slice
-  p.wbuf_bytes = ((p.off_w3 + p.Npad * 128) + 1023) & ~1023;
-  p.nbuf = 1;
-  off += p.wbuf_bytes;
-  p.off_h1 = off; off += G::MT * 16384;
-  p.off_h2 = off; off += 16384;
-  p.off_tab = off; off += 2 * 832 * 4;     // two table sets: s1 t1 s2 t2 [64] + taps [9][64]
+  p.off_w1 = off; off += p.KB * 8192;
+  p.off_w3 = off; off += p.Npad * 128;
+  p.off_h2 = (off + 1023) & ~1023; off = p.off_h2 + 16384;
+  p.off_h1 = off; off += ((G::NPI * kH1Pitch) + 15) & ~15;
+  p.off_tab = off; off += 2 * kTabFloats * 4;
   p.off_c3 = off; off += 2 * p.Npad * 4;
-  p.off_bars = (off + 15) & ~15; off = p.off_bars + 32;
-  const int smem = off;
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  p.proj_col = G::MT * 64;
+  p.off_bars = (off + 15) & ~15; off = p.off_bars + 48;
+  int smem = off;
+  const int x_read_end = (p.KB - 1) * p.xpanel_bytes + 32768;   // last byte the expand MMA may touch
+  if (smem < x_read_end) smem = x_read_end;
+  if (smem > 227 * 1024) return set_error(YAMB_EINVAL, "block_eval: tile does not fit shared memory");
+  p.proj_col = 128;
   int need = p.proj_col + p.Npad, cols = 32;
   while (cols < need) cols *= 2;
-  if (cols > 512) return cudaErrorInvalidValue;
+  if (cols > 512) return set_error(YAMB_EINVAL, "block_eval: accumulators exceed TMEM");
   p.tmem_cols = cols;
-  const int tiles_img = p.tiles_h * p.tiles_w;
   const int groups = (p.N + G::TI - 1) / G::TI;
-  p.num_tiles = groups * tiles_img;
+  p.num_tiles = groups * p.tiles_h * p.tiles_w;
+  // ---- tensor maps: x [N][H][W][Cin] (4-D box with halo), W1 [Chid][Cin], W3 [Cout][Chid] ----
+  CUtensorMap tmX, tmW1, tmW3;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    const cuuint64_t str[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.W * p.Cin * 2,
+                               (cuuint64_t)p.H * p.W * p.Cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)G::IW, (cuuint32_t)G::IH, (cuuint32_t)G::TI};
+    int rc = make_map(&tmX, a->x, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Chid};
+    const cuuint64_t str[1] = {(cuuint64_t)p.Cin * 2};
+    const cuuint32_t box[2] = {64, 64};
+    int rc = make_map(&tmW1, a->w_expand, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const int halves = p.Npad > 256 ? 2 : 1;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.Chid, (cuuint64_t)p.Cout};
+    const cuuint64_t str[1] = {(cuuint64_t)p.Chid * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(p.Npad / halves)};
+    int rc = make_map(&tmW3, a->w_project, 2, dims, str, box);
+    if (rc) return rc;
+  }
   // the dynamic-smem limit is process-wide state: only ever raise it
   static std::mutex mu;
   static int attr = 0;
@@ -466,27 +528,28 @@ static cudaError_t launch_eval(BlockEvalDev& p, cudaStream_t st) {
     if (attr < smem) {
       cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      // two CTAs of ~100 KB need the largest shared-memory carve-out
-      e = cudaFuncSetAttribute(block_eval_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               (int)cudaSharedmemCarveoutMaxShared);
-      if (e != cudaSuccess) return e;
+      if (e == cudaSuccess)   // two CTAs of ~90 KB need the largest shared-memory carve-out
+        e = cudaFuncSetAttribute(block_eval_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval attr: %s", cudaGetErrorString(e));
       attr = smem;
     }
   }
   // Resident CTAs per SM: 228 KB of shared memory (+1 KB the driver reserves per CTA), 512 TMEM
   // columns, 64 Ki registers (__launch_bounds__(256, 2): <= 128 per thread).
-  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for the 101 KB configurations that
+  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for the ~100 KB configurations that
   // ncu's launch__occupancy_limit_* and the hardware both place twice: computed here.)
-  int per_sm = (2 * (smem + 1024) <= 228 * 1024 && 2 * cols <= 512) ? 2 : 1;
-  long long cap = (long long)max_ctas() * per_sm;
+  const int per_sm = (2 * (smem + 1024) <= 228 * 1024 && 2 * cols <= 512) ? 2 : 1;
+  const long long cap = (long long)max_ctas() * per_sm;
   const int grid = (int)(p.num_tiles < cap ? p.num_tiles : cap);
   static const bool dbg = getenv("YAMB_EVAL_DEBUG") != nullptr;
   if (dbg)
     fprintf(stderr, "block_eval: tiles %d grid %d per_sm %d smem %d tmem_cols %d Npad %d NC %d KB %d\n",
             p.num_tiles, grid, per_sm, smem, cols, p.Npad, p.NC, p.KB);
-  block_eval_kernel<G><<<grid, 256, smem, st>>>(p);
-  return cudaGetLastError();
+  block_eval_kernel<G><<<grid, 256, smem, st>>>(tmX, tmW1, tmW3, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
@@ -518,7 +581,6 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   p.Cin = a->Cin; p.Chid = a->Chid; p.Cout = a->Cout;
   p.act = a->act; p.residual = a->residual ? 1 : 0;
   p.x = (const __nv_bfloat16*)a->x; p.y = (__nv_bfloat16*)a->y;
-  p.w1 = (const __nv_bfloat16*)a->w_expand; p.w3 = (const __nv_bfloat16*)a->w_project;
   p.wdw = a->w_dw;
   auto cvt = [](const yamb_bn_eval& s) {
     BnEvalDev d;
@@ -527,13 +589,13 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   };
   p.bn1 = cvt(a->bn1); p.bn2 = cvt(a->bn2); p.bn3 = cvt(a->bn3);
   const int kpad = (a->Cin + 15) / 16 * 16;
-  p.cpr = kpad / 8;
+  p.nks = kpad / 16;
   p.KB = (kpad + 63) / 64;
   p.Npad = (a->Cout + 15) / 16 * 16;
   p.NC = (a->Chid + 63) / 64;
-  // tile geometry: the one that wastes the fewest of the 128 rows of a tile
+  // tile geometry: the one that needs the fewest tiles
   struct Cand { int toh, tow, ti; };
-  const Cand cands[3] = {{8, 16, 1}, {7, 14, 1}, {7, 7, 2}};
+  const Cand cands[3] = {{7, 16, 1}, {7, 14, 1}, {7, 7, 2}};
   int best = 0;
   long long best_tiles = -1;
   for (int i = 0; i < 3; ++i) {
@@ -545,12 +607,9 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   if (best_tiles > 0x7fffffffLL) return set_error(YAMB_EINVAL, "block_eval: too many tiles");
   p.tiles_h = (a->H + cands[best].toh - 1) / cands[best].toh;
   p.tiles_w = (a->W + cands[best].tow - 1) / cands[best].tow;
-  cudaError_t e;
-  if (best == 0) e = launch_eval<EvGeom<8, 16, 1>>(p, st);
-  else if (best == 1) e = launch_eval<EvGeom<7, 14, 1>>(p, st);
-  else e = launch_eval<EvGeom<7, 7, 2>>(p, st);
-  if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
-  return 0;
+  if (best == 0) return launch_eval<EvGeom<7, 16, 1>>(p, a, st);
+  if (best == 1) return launch_eval<EvGeom<7, 14, 1>>(p, a, st);
+  return launch_eval<EvGeom<7, 7, 2>>(p, a, st);
 }
 
 }  // namespace yamb
