@@ -352,13 +352,14 @@ int yamb_colsum_bf16(const void* X, int64_t M, int32_t C, int64_t ld, float* out
 
 /* ---- eval-mode inverted-residual block, ONE launch, no intermediate in HBM -----------------------
  * Replaces the forward of InvertedResidualChannels (reference models/mobilenet_base.py:446-451;
- * single branch, expand=True, 3x3 depthwise, stride 1) when every BatchNorm uses its running
- * statistics (model.eval(): validation / forward_loss under no_grad, common.py:67-80,
- * train.py:273-309): x tile -> tcgen05 expand -> BN1+act -> 3x3 stencil -> BN2+act -> tcgen05
- * project (accumulated over 64-channel slices of the hidden dimension) -> BN3 (+x) -> y.
- * The BatchNorm folding scale = gamma*rsqrt(var+eps), shift = beta - mean*scale is done inside
- * the kernel from the module's buffers (csrc/block_eval.cu).  Shapes it does not cover return
- * YAMB_EINVAL; the caller then runs the four-launch sequence with folded coefficients. */
+ * single branch, 3x3 depthwise, stride 1 or 2, with the 1x1 expansion or without it (:397-404,
+ * hidden == input)) when every BatchNorm uses its running statistics (model.eval(): validation /
+ * forward_loss under no_grad, common.py:67-80, train.py:273-309): x tile (TMA, halo zero-filled)
+ * -> tcgen05 expand -> BN1+act -> 3x3 stencil -> BN2+act -> tcgen05 project (accumulated over
+ * 64-channel slices of the hidden dimension) -> BN3 (+x) -> y.  The BatchNorm folding
+ * scale = gamma*rsqrt(var+eps), shift = beta - mean*scale is done inside the kernel from the
+ * module's buffers (csrc/block_eval.cu).  Shapes it does not cover return YAMB_EINVAL; the caller
+ * then runs the four-launch sequence with folded coefficients. */
 typedef struct yamb_bn_eval {
   const float* gamma;         /* [C] or NULL (=1) */
   const float* beta;          /* [C] or NULL (=0) */
@@ -368,17 +369,17 @@ typedef struct yamb_bn_eval {
 } yamb_bn_eval;
 
 typedef struct yamb_block_eval {
-  int32_t N, H, W;            /* input pixels (NHWC); stride 1: the output has the same H, W */
+  int32_t N, H, W;            /* input pixels (NHWC); output (H-1)/stride+1 x (W-1)/stride+1 */
   int32_t Cin, Chid, Cout;    /* multiples of 8; Cin <= 256, Cout <= 320 */
-  int32_t kernel, stride;     /* 3, 1 */
+  int32_t kernel, stride;     /* 3; 1 or 2 */
   int32_t act;                /* YAMB_ACT_* of the two inner activations */
-  int32_t residual;           /* y += x (needs Cin == Cout) */
+  int32_t residual;           /* y += x (needs Cin == Cout, stride 1) */
   const void* x;              /* bf16 [N,H,W,Cin] */
-  const void* w_expand;       /* bf16 [Chid][Cin] */
+  const void* w_expand;       /* bf16 [Chid][Cin], or NULL: no expansion (Chid == Cin, bn1 unused) */
   const float* w_dw;          /* fp32 [Chid][3][3] */
   const void* w_project;      /* bf16 [Cout][Chid] */
   yamb_bn_eval bn1, bn2, bn3; /* over Chid, Chid, Cout channels */
-  void* y;                    /* bf16 [N,H,W,Cout] */
+  void* y;                    /* bf16 [N,Ho,Wo,Cout] */
 } yamb_block_eval;
 
 int yamb_block_eval_fwd(const yamb_block_eval* args, yamb_stream_t stream);

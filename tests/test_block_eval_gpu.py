@@ -12,7 +12,8 @@ common.py:67-80 under torch.no_grad()).  Checked against
 
 Edge cases: images that do not divide into tiles, odd image counts on the two-images-per-tile
 geometry, channel counts that need K / N padding (24), a partial last 64-channel slice (144),
-the 320-column project accumulator, single-buffered weight staging (Cin = 160).
+the 320-column project accumulator, three K panels (Cin = 160), stride 2 (incl. odd sizes and a
+single output pixel), blocks without the expansion (one and two channel panels, with stride 2).
 """
 import copy
 import os
@@ -30,10 +31,10 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _make_block(cin, chid, cout, act, seed):
+def _make_block(cin, chid, cout, act, seed, stride=1, expand=True):
     from yet_another_mobilenet_series_b200 import mobilenet_base as mb
     torch.manual_seed(seed)
-    blk = mb.InvertedResidualChannels(cin, cout, 1, [chid], [3], True,
+    blk = mb.InvertedResidualChannels(cin, cout, stride, [chid], [3], expand,
                                       active_fn=mb.get_active_fn({"relu": "nn.ReLU", "relu6": "nn.ReLU6",
                                                                 "swish": "nn.Swish"}[act]),
                                       batch_norm_kwargs={"momentum": 0.01, "eps": 1e-3})
@@ -62,6 +63,17 @@ CASES = [
     (40, 120, 40, 3, 9, 13, "swish"),      # odd sizes, swish
     (8, 8, 8, 1, 3, 3, "relu"),            # smallest legal block
     (32, 192, 32, 2, 112, 112, "relu"),    # many tiles per CTA
+    # stride 2 (7x7 outputs from a 15x15 input tile, 2 channels per stencil thread)
+    (16, 96, 24, 2, 112, 112, "relu", 2, True),     # MobileNetV2 block 2
+    (24, 144, 32, 3, 56, 56, "relu6", 2, True),     # block 4
+    (32, 192, 64, 5, 28, 28, "relu", 2, True),      # block 7
+    (96, 576, 160, 3, 14, 14, "relu", 2, True),     # block 14
+    (16, 48, 24, 2, 17, 23, "swish", 2, True),      # odd sizes: Ho = 9, Wo = 12
+    (8, 16, 8, 1, 2, 2, "relu", 2, True),           # one output pixel
+    # no expansion (hidden == input): the stencil reads the x tile itself
+    (32, 32, 16, 2, 112, 112, "relu", 1, False),    # MobileNetV2 block 1
+    (96, 96, 96, 3, 14, 14, "relu6", 1, False),     # two 64-channel panels, skip connection
+    (24, 24, 40, 2, 30, 30, "relu", 2, False),      # no expansion + stride 2
 ]
 
 
@@ -72,9 +84,10 @@ def test_fused_eval_block(built_lib, case):
     from yet_another_mobilenet_series_b200 import engine
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    cin, chid, cout, N, H, W, act = case
+    cin, chid, cout, N, H, W, act = case[:7]
+    stride, expand = (case[7], case[8]) if len(case) > 7 else (1, True)
     dev = torch.device("cuda")
-    blk = _make_block(cin, chid, cout, act, seed=sum(case[:6]))
+    blk = _make_block(cin, chid, cout, act, sum(case[:6]), stride, expand)
     g = torch.Generator().manual_seed(7)
     x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
     # ---- oracle with the kernel's rounding points (CPU) ----
@@ -100,7 +113,7 @@ def test_fused_eval_block(built_lib, case):
         torch.cuda.synchronize()
     finally:
         engine.EVAL_FUSED = True
-    assert engine.LAUNCHES - launches0 >= 5
+    assert engine.LAUNCHES - launches0 >= (5 if expand else 4)
     # ---- stock torch fp32 (truth) and autocast-bf16 (yardstick) on the same GPU ----
     ref = tm.as_reference(copy.deepcopy(blk)).to(dev).eval()
     with torch.no_grad():
@@ -154,7 +167,7 @@ def test_fused_eval_abi_rejects_what_it_does_not_cover(built_lib):
     st = torch.cuda.current_stream().cuda_stream
     assert lib.yamb_block_eval_fwd(C.byref(a), st) == 0
     torch.cuda.synchronize()
-    for field, bad in (("stride", 2), ("kernel", 5), ("Cin", 12), ("Cout", 328), ("Cin", 264)):
+    for field, bad in (("stride", 3), ("kernel", 5), ("Cin", 12), ("Cout", 328), ("Cin", 264)):
         b = nat.BlockEval.from_buffer_copy(a)
         setattr(b, field, bad)
         assert lib.yamb_block_eval_fwd(C.byref(b), st) == -1, field
@@ -165,10 +178,16 @@ def test_fused_eval_abi_rejects_what_it_does_not_cover(built_lib):
     b = nat.BlockEval.from_buffer_copy(a)
     b.bn2.running_var = None
     assert lib.yamb_block_eval_fwd(C.byref(b), st) == -1
+    b = nat.BlockEval.from_buffer_copy(a)
+    b.w_expand = None                # no expansion needs Chid == Cin
+    assert lib.yamb_block_eval_fwd(C.byref(b), st) == -1
+    b = nat.BlockEval.from_buffer_copy(a)
+    b.stride = 2                     # a skip connection needs stride 1
+    assert lib.yamb_block_eval_fwd(C.byref(b), st) == -1
 
 
 def test_mobilenet_v2_eval_uses_the_one_launch_blocks(built_lib):
-    """Whole network, model.eval() under no_grad: 12 of the 17 blocks go through the one-launch
+    """Whole network, model.eval() under no_grad: all 17 blocks go through the one-launch
     kernel; logits against the reference graph in fp32 with the autocast yardstick."""
     import bench
     from oracle import torch_model as tm
@@ -188,7 +207,7 @@ def test_mobilenet_v2_eval_uses_the_one_launch_blocks(built_lib):
     with torch.no_grad():
         y = model(x).float()
     torch.cuda.synchronize()
-    assert engine.EVAL_FUSED_CALLS - c0 == 12
+    assert engine.EVAL_FUSED_CALLS - c0 == 17
     ref = tm.as_reference(copy.deepcopy(model)).eval()
     with torch.no_grad():
         yt = ref(x)

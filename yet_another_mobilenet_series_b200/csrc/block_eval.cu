@@ -51,7 +51,7 @@ struct BnEvalDev {
 };
 
 struct BlockEvalDev {
-  int N, H, W, Cin, Chid, Cout, act, residual;
+  int N, H, W, Ho, Wo, Cin, Chid, Cout, act, residual;
   const __nv_bfloat16* x;
   const float* wdw;
   BnEvalDev bn1, bn2, bn3;
@@ -71,24 +71,27 @@ constexpr int kTabFloats = 832;  // s1 t1 s2 t2 [64] + taps [9][64]
 
 // Output tile TI images x TOH x TOW pixels (<= 128 = the M of the project MMA); the input tile with
 // its one-pixel halo is the M of the expand MMAs (2 tiles of 128 rows, rows >= NPI are don't-care).
-template <int TOH_, int TOW_, int TI_>
+// Stencil threads (warps 0-6 = 224 threads): a thread owns CPT channels (64 / CPT channel groups)
+// and RUN consecutive outputs of one output row.
+template <int S_, int TOH_, int TOW_, int TI_, int CPT_>
 struct EvGeom {
-  static constexpr int TOH = TOH_, TOW = TOW_, TI = TI_;
-  static constexpr int IH = TOH + 2, IW = TOW + 2;
+  static constexpr int S = S_, TOH = TOH_, TOW = TOW_, TI = TI_, CPT = CPT_;
+  static constexpr int IH = (TOH - 1) * S + 3, IW = (TOW - 1) * S + 3;
   static constexpr int NPI = TI * IH * IW;
   static constexpr int NPO = TI * TOH * TOW;
   static constexpr int RUN = (TOW % 8 == 0) ? 8 : 7;   // consecutive outputs of one row per stencil thread
   static constexpr int NRUN = NPO / RUN;
-  static_assert(NPO <= 128 && NPI > 128 && NPI <= 256 && TOW % RUN == 0 && NRUN <= 14,
+  static constexpr int NCG = 64 / CPT;                  // channel groups
+  static_assert(NPO <= 128 && NPI > 128 && NPI <= 256 && TOW % RUN == 0 && NRUN * NCG <= 224,
                 "tile geometry (warp 7 must stay free of stencil work)");
 };
 
-template <class G>
+template <class G, bool EXPAND>
 __global__ void __launch_bounds__(256, 2)
 block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ BlockEvalDev p) {
-  constexpr int TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
-  constexpr int NPI = G::NPI, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN;
+  constexpr int S = G::S, TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
+  constexpr int NPI = G::NPI, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN, CPT = G::CPT, NCG = G::NCG;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bar_e = reinterpret_cast<uint64_t*>(smem + p.off_bars);   // expand MMAs of a slice retired
@@ -150,7 +153,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const BnEvalDev& b = tid < 64 ? p.bn1 : p.bn2;
       const int hc = c * 64 + (tid & 63);
       pre_s = pre_t = 0.f;
-      if (hc < p.Chid) {
+      if (hc < p.Chid && (EXPAND || tid >= 64)) {   // no expansion: there is no BatchNorm1
         const float r = rsqrtf(__ldg(b.var + hc) + b.eps);
         pre_s = (b.gamma ? __ldg(b.gamma + hc) : 1.f) * r;
         pre_t = (b.beta ? __ldg(b.beta + hc) : 0.f) - __ldg(b.mean + hc) * pre_s;
@@ -185,8 +188,8 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto tma_x = [&](int t) {            // x tile of tile t: one 4-D box per 64-channel panel
     const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
     for (int kb = 0; kb < p.KB; ++kb)
-      tma_load_4d(&tmX, bar_ld, sX_u + (uint32_t)(kb * p.xpanel_bytes), kb * 64, tx * TOW - 1,
-                  ty * TOH - 1, g * TI);
+      tma_load_4d(&tmX, bar_ld, sX_u + (uint32_t)(kb * p.xpanel_bytes), kb * 64, tx * TOW * S - 1,
+                  ty * TOH * S - 1, g * TI);
   };
   auto tma_w1 = [&](int c) {
     for (int kb = 0; kb < p.KB; ++kb)
@@ -222,10 +225,10 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int e1_ti = e1_r / (IH * IW);
   const int e1_dy = (e1_r % (IH * IW)) / IW - 1, e1_dx = (e1_r % (IH * IW)) % IW - 1;
   // stencil: RUN consecutive outputs of one row x 4 channels
-  const int cg = tid & 15, sp = tid >> 4;
+  const int cg = tid % NCG, sp = tid / NCG;
   const int r0 = sp * RUN;
   const int s_ti = r0 / (TOH * TOW), s_oy = (r0 % (TOH * TOW)) / TOW, s_ox0 = (r0 % (TOH * TOW)) % TOW;
-  const uint8_t* s_hb = sH1 + (s_ti * IH * IW + s_oy * IW + s_ox0) * kH1Pitch + cg * 8;
+  const uint8_t* s_hb = sH1 + (s_ti * IH * IW + s_oy * S * IW + s_ox0 * S) * kH1Pitch + cg * CPT * 2;
   // epilogue 2: this thread's output pixel
   const int e2_r = (warp & 3) * 32 + lane;
   const int e2_ti = e2_r / (TOH * TOW);
@@ -236,12 +239,14 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tab_fetch(0);
   tab_store(tab);
   if (control) {
-    mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (NPI * 128 + 8192)));
+    mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (NPI * 128 + (EXPAND ? 8192 : 0))));
     tma_x(t);
-    tma_w1(0);
-    mbar_wait(bar_ld, ld_par);
-    ld_par ^= 1;
-    issue_expand();
+    if (EXPAND) {
+      tma_w1(0);
+      mbar_wait(bar_ld, ld_par);
+      ld_par ^= 1;
+      issue_expand();
+    }
   }
   __syncthreads();   // tables of slice 0
   int gc = 0;
@@ -250,27 +255,27 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const bool more_tiles = t + (int)gridDim.x < p.num_tiles;
     bool e1_inside;
     {
-      const int n = g * TI + e1_ti, yy = ty * TOH + e1_dy, xx = tx * TOW + e1_dx;
+      const int n = g * TI + e1_ti, yy = ty * TOH * S + e1_dy, xx = tx * TOW * S + e1_dx;
       e1_inside = e1_r < NPI && n < p.N && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
     }
     for (int c = 0; c < NC; ++c, ++gc) {
       const bool last_c = c + 1 == NC;
       const bool has_next = !last_c || more_tiles;
       const float* tb = tab + (gc & 1) * kTabFloats;
-      mbar_wait(bar_e, pe);           // expand(gc) retired: accumulator ready, sW1 (and sX) free
-      pe ^= 1;
-      tc_fence_after();
-      if (has_next) {
-        if (control) {
-          mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (8192 + (last_c ? NPI * 128 : 0))));
-          if (last_c) tma_x(t + gridDim.x);
-          tma_w1(last_c ? 0 : c + 1);
+      if (EXPAND) {
+        mbar_wait(bar_e, pe);           // expand(gc) retired: accumulator ready, sW1 (and sX) free
+        pe ^= 1;
+        tc_fence_after();
+        if (has_next) {
+          if (control) {
+            mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (8192 + (last_c ? NPI * 128 : 0))));
+            if (last_c) tma_x(t + gridDim.x);
+            tma_w1(last_c ? 0 : c + 1);
+          }
+          tab_fetch(last_c ? 0 : c + 1);   // registers; stored before S3
         }
-        tab_fetch(last_c ? 0 : c + 1);   // registers; stored before S3
-      }
-      __syncwarp();                   // warp 7 reconverges before the warp-wide tcgen05.ld
-      // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
-      {
+        __syncwarp();                   // warp 7 reconverges before the warp-wide tcgen05.ld
+        // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
         const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
         uint8_t* dst = sH1 + e1_r * kH1Pitch;
 #pragma unroll
@@ -317,6 +322,23 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (e1_r < NPI) *reinterpret_cast<uint4*>(dst + cb * 2) = o;
           }
         }
+      } else {
+        // ---- no expansion (hidden == input, reference mobilenet_base.py:397-404): the stencil input
+        //      IS the x tile (already activated by its producer; TMA zero-filled the padding):
+        //      panel c of the x tile -> sH1, un-swizzled ----
+        if (c == 0) {
+          mbar_wait(bar_ld, ld_par);    // every thread follows this barrier in the no-expand variant
+          ld_par ^= 1;
+        }
+        if (has_next) tab_fetch(last_c ? 0 : c + 1);
+        if (tid < NPI) {
+          const uint8_t* src = smem + c * p.xpanel_bytes + tid * 128;
+          uint8_t* dst = sH1 + tid * kH1Pitch;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(dst + j * 16) =
+                *reinterpret_cast<const uint4*>(src + ((j ^ (tid & 7)) << 4));
+        }
       }
       // project(gc-1) retired long ago (it was issued before this slice's accumulator wait):
       // sW3 and sH2 are free
@@ -329,62 +351,88 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           mbar_arrive_expect_tx(bar_w3, (uint32_t)(p.Npad * 128));
           for (int h = 0; h < p_halves; ++h)
             tma_load_2d(&tmW3, bar_w3, smem + p.off_w3 + h * p_nn * 128, c * 64, h * p_nn);
-          if (has_next) {
-            mbar_wait(bar_ld, ld_par);     // landed during epilogue 1
-            ld_par ^= 1;
-            issue_expand();
+          if (EXPAND) {
+            if (has_next) {
+              mbar_wait(bar_ld, ld_par);     // landed during epilogue 1
+              ld_par ^= 1;
+              issue_expand();
+            }
+          } else if (last_c && more_tiles) {
+            // every panel of this tile has been copied out: the next tile's x may land
+            mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * NPI * 128));
+            tma_x(t + gridDim.x);
           }
         }
         __syncwarp();
       } else if (sp < NRUN) {
-        // ---- 3x3 stencil: RUN consecutive outputs of one row x 4 channels per thread ----
-        float2 o2[RUN][2];
+        // ---- 3x3 stencil: RUN consecutive outputs of one row x CPT channels per thread ----
+        constexpr int NV = CPT / 2;          // packed fp32 pairs per pixel
+        float2 o2[RUN][NV];
 #pragma unroll
-        for (int j = 0; j < RUN; ++j) o2[j][0] = o2[j][1] = make_float2(0.f, 0.f);
-        float2 w2[9][2];
+        for (int j = 0; j < RUN; ++j)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) o2[j][v] = make_float2(0.f, 0.f);
+        float2 w2[9][NV];
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp) {
-          const float4 wv = *reinterpret_cast<const float4*>(tb + 256 + tp * 64 + cg * 4);
-          w2[tp][0] = make_float2(wv.x, wv.y);
-          w2[tp][1] = make_float2(wv.z, wv.w);
+          if (CPT == 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(tb + 256 + tp * 64 + cg * 4);
+            w2[tp][0] = make_float2(wv.x, wv.y);
+            w2[tp][NV - 1] = make_float2(wv.z, wv.w);
+          } else {
+            w2[tp][0] = *reinterpret_cast<const float2*>(tb + 256 + tp * 64 + cg * 2);
+          }
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-          for (int ixx = 0; ixx < RUN + 2; ++ixx) {
-            const uint2 a = *reinterpret_cast<const uint2*>(s_hb + (ky * IW + ixx) * kH1Pitch);
-            const float2 alo = make_float2(bf16lo(a.x), bf16hi(a.x));
-            const float2 ahi = make_float2(bf16lo(a.y), bf16hi(a.y));
+          for (int ixx = 0; ixx < (RUN - 1) * S + 3; ++ixx) {
+            float2 av[NV];
+            if (CPT == 4) {
+              const uint2 a = *reinterpret_cast<const uint2*>(s_hb + (ky * IW + ixx) * kH1Pitch);
+              av[0] = make_float2(bf16lo(a.x), bf16hi(a.x));
+              av[NV - 1] = make_float2(bf16lo(a.y), bf16hi(a.y));
+            } else {
+              const uint32_t a = *reinterpret_cast<const uint32_t*>(s_hb + (ky * IW + ixx) * kH1Pitch);
+              av[0] = make_float2(bf16lo(a), bf16hi(a));
+            }
 #pragma unroll
             for (int j = 0; j < RUN; ++j) {
-              const int kx = ixx - j;   // compile-time after unrolling
+              const int kx = ixx - j * S;   // compile-time after unrolling
               if (kx >= 0 && kx < 3) {
-                o2[j][0] = ffma2(w2[ky * 3 + kx][0], alo, o2[j][0]);
-                o2[j][1] = ffma2(w2[ky * 3 + kx][1], ahi, o2[j][1]);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) o2[j][v] = ffma2(w2[ky * 3 + kx][v], av[v], o2[j][v]);
               }
             }
           }
         }
-        const float4 s2 = *reinterpret_cast<const float4*>(tb + 128 + cg * 4);
-        const float4 t2 = *reinterpret_cast<const float4*>(tb + 192 + cg * 4);
-        const float2 s2a = make_float2(s2.x, s2.y), s2b = make_float2(s2.z, s2.w);
-        const float2 t2a = make_float2(t2.x, t2.y), t2b = make_float2(t2.z, t2.w);
+        float2 s2v[NV], t2v[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          s2v[v] = *reinterpret_cast<const float2*>(tb + 128 + cg * CPT + 2 * v);
+          t2v[v] = *reinterpret_cast<const float2*>(tb + 192 + cg * CPT + 2 * v);
+        }
+        constexpr int kBoff = 0;
+        (void)kBoff;
+        const int boff = cg * CPT * 2;       // byte offset of this thread's channels inside a row
 #pragma unroll
         for (int j = 0; j < RUN; ++j) {
-          const float2 va = ffma2(s2a, o2[j][0], t2a), vb = ffma2(s2b, o2[j][1], t2b);
-          uint32_t wa, wb;
-          if (lean) {
-            wa = clamp_bf16x2(pack_bf16(va.x, va.y), lo2, hi2);
-            wb = clamp_bf16x2(pack_bf16(vb.x, vb.y), lo2, hi2);
-          } else {
-            float v[4] = {va.x, va.y, vb.x, vb.y};
-            act_vec<4>(v, ap);
-            wa = pack_bf16(v[0], v[1]);
-            wb = pack_bf16(v[2], v[3]);
+          uint32_t wv[NV];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const float2 z = ffma2(s2v[v], o2[j][v], t2v[v]);
+            if (lean) {
+              wv[v] = clamp_bf16x2(pack_bf16(z.x, z.y), lo2, hi2);
+            } else {
+              float q[2] = {z.x, z.y};
+              act_vec<2>(q, ap);
+              wv[v] = pack_bf16(q[0], q[1]);
+            }
           }
           const int r = r0 + j;
-          *reinterpret_cast<uint2*>(sH2 + r * 128 + (((cg >> 1) ^ (r & 7)) << 4) + (cg & 1) * 8) =
-              make_uint2(wa, wb);
+          uint8_t* dst = sH2 + r * 128 + (((boff >> 4) ^ (r & 7)) << 4) + (boff & 15);
+          if (CPT == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(wv[0], wv[NV - 1]);
+          else *reinterpret_cast<uint32_t*>(dst) = wv[0];
         }
       }
       if (has_next) tab_store(tab + ((gc + 1) & 1) * kTabFloats);   // its readers are behind S3
@@ -409,8 +457,8 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     __syncwarp();
     {
       const int n = g * TI + e2_ti, yy = ty * TOH + e2_oy, xx = tx * TOW + e2_ox;
-      const bool valid = e2_r < NPO && n < p.N && yy < p.H && xx < p.W;
-      const size_t pix = valid ? ((size_t)(n * p.H + yy) * p.W + xx) : 0;
+      const bool valid = e2_r < NPO && n < p.N && yy < p.Ho && xx < p.Wo;
+      const size_t pix = valid ? ((size_t)(n * p.Ho + yy) * p.Wo + xx) : 0;
       const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)p.proj_col;
       const int units = p.Npad >> 4;
 #pragma unroll 1
@@ -470,14 +518,14 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_
   return 0;
 }
 
-template <class G>
+template <class G, bool EXPAND>
 static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t st) {
   // ---- shared-memory plan (bytes from the 1024-aligned base) ----
   // x tile: NPI rows of 128 B per 64-channel panel; the second 128-row MMA tile of a panel reads
   // past them (rows that are never used): those reads stay inside this CTA's allocation
   p.xpanel_bytes = (G::NPI * 128 + 1023) & ~1023;
   int off = p.KB * p.xpanel_bytes;
-  p.off_w1 = off; off += p.KB * 8192;
+  p.off_w1 = off; off += EXPAND ? p.KB * 8192 : 0;
   p.off_w3 = off; off += p.Npad * 128;
   p.off_h2 = (off + 1023) & ~1023; off = p.off_h2 + 16384;
   p.off_h1 = off; off += ((G::NPI * kH1Pitch) + 15) & ~15;
@@ -494,6 +542,10 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
   if (cols > 512) return set_error(YAMB_EINVAL, "block_eval: accumulators exceed TMEM");
   p.tmem_cols = cols;
   const int groups = (p.N + G::TI - 1) / G::TI;
+  p.tiles_h = (p.Ho + G::TOH - 1) / G::TOH;
+  p.tiles_w = (p.Wo + G::TOW - 1) / G::TOW;
+  if ((long long)groups * p.tiles_h * p.tiles_w > 0x7fffffffLL)
+    return set_error(YAMB_EINVAL, "block_eval: too many tiles");
   p.num_tiles = groups * p.tiles_h * p.tiles_w;
   // ---- tensor maps: x [N][H][W][Cin] (4-D box with halo), W1 [Chid][Cin], W3 [Cout][Chid] ----
   CUtensorMap tmX, tmW1, tmW3;
@@ -505,7 +557,8 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
     int rc = make_map(&tmX, a->x, 4, dims, str, box);
     if (rc) return rc;
   }
-  {
+  memset(&tmW1, 0, sizeof(tmW1));
+  if (EXPAND) {
     const cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Chid};
     const cuuint64_t str[1] = {(cuuint64_t)p.Cin * 2};
     const cuuint32_t box[2] = {64, 64};
@@ -526,10 +579,10 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
   {
     std::lock_guard<std::mutex> lock(mu);
     if (attr < smem) {
-      cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G>,
+      cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e == cudaSuccess)   // two CTAs of ~90 KB need the largest shared-memory carve-out
-        e = cudaFuncSetAttribute(block_eval_kernel<G>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval attr: %s", cudaGetErrorString(e));
       attr = smem;
@@ -546,7 +599,7 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
   if (dbg)
     fprintf(stderr, "block_eval: tiles %d grid %d per_sm %d smem %d tmem_cols %d Npad %d NC %d KB %d\n",
             p.num_tiles, grid, per_sm, smem, cols, p.Npad, p.NC, p.KB);
-  block_eval_kernel<G><<<grid, 256, smem, st>>>(tmX, tmW1, tmW3, p);
+  block_eval_kernel<G, EXPAND><<<grid, 256, smem, st>>>(tmX, tmW1, tmW3, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
   return 0;
@@ -560,15 +613,19 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
     return set_error(YAMB_EINVAL, "block_eval: channel counts must be positive multiples of 8");
   if (a->Cin > 256 || a->Cout > 320)
     return set_error(YAMB_EINVAL, "block_eval: Cin <= 256, Cout <= 320 (got %d, %d)", a->Cin, a->Cout);
-  if (a->kernel != 3 || a->stride != 1)
-    return set_error(YAMB_EINVAL, "block_eval: only 3x3 stride-1 depthwise (got k=%d s=%d)",
+  if (a->kernel != 3 || (a->stride != 1 && a->stride != 2))
+    return set_error(YAMB_EINVAL, "block_eval: only 3x3 depthwise with stride 1 or 2 (got k=%d s=%d)",
                      a->kernel, a->stride);
+  if (!a->w_expand && a->Chid != a->Cin)
+    return set_error(YAMB_EINVAL, "block_eval: no expand weights needs Chid == Cin");
+  if (a->residual && a->stride != 1)
+    return set_error(YAMB_EINVAL, "block_eval: residual needs stride 1");
   if (a->residual && a->Cin != a->Cout)
     return set_error(YAMB_EINVAL, "block_eval: residual needs Cin == Cout");
-  if (!a->x || !a->y || !a->w_expand || !a->w_dw || !a->w_project)
+  if (!a->x || !a->y || !a->w_dw || !a->w_project)
     return set_error(YAMB_EINVAL, "block_eval: null pointer");
   const yamb_bn_eval* bns[3] = {&a->bn1, &a->bn2, &a->bn3};
-  for (int i = 0; i < 3; ++i)
+  for (int i = a->w_expand ? 0 : 1; i < 3; ++i)
     if (!bns[i]->running_mean || !bns[i]->running_var)
       return set_error(YAMB_EINVAL, "block_eval: BatchNorm %d has no running statistics", i + 1);
   if ((((uintptr_t)a->x) | ((uintptr_t)a->y) | ((uintptr_t)a->w_expand) | ((uintptr_t)a->w_project)) & 15)
@@ -578,6 +635,8 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   BlockEvalDev p;
   memset(&p, 0, sizeof(p));
   p.N = a->N; p.H = a->H; p.W = a->W;
+  p.Ho = (a->H - 1) / a->stride + 1;      // pad 1, k 3
+  p.Wo = (a->W - 1) / a->stride + 1;
   p.Cin = a->Cin; p.Chid = a->Chid; p.Cout = a->Cout;
   p.act = a->act; p.residual = a->residual ? 1 : 0;
   p.x = (const __nv_bfloat16*)a->x; p.y = (__nv_bfloat16*)a->y;
@@ -593,23 +652,31 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   p.KB = (kpad + 63) / 64;
   p.Npad = (a->Cout + 15) / 16 * 16;
   p.NC = (a->Chid + 63) / 64;
-  // tile geometry: the one that needs the fewest tiles
+  const bool ex = a->w_expand != nullptr;
+  if (a->stride == 2) {
+    // 7x7 outputs from a 15x15 input tile (225 of the 256 expand rows), 2 channels per thread
+    return ex ? launch_eval<EvGeom<2, 7, 7, 1, 2>, true>(p, a, st)
+              : launch_eval<EvGeom<2, 7, 7, 1, 2>, false>(p, a, st);
+  }
+  // stride 1: the tile geometry that needs the fewest tiles
   struct Cand { int toh, tow, ti; };
   const Cand cands[3] = {{7, 16, 1}, {7, 14, 1}, {7, 7, 2}};
   int best = 0;
   long long best_tiles = -1;
   for (int i = 0; i < 3; ++i) {
-    const long long th = (a->H + cands[i].toh - 1) / cands[i].toh;
-    const long long tw = (a->W + cands[i].tow - 1) / cands[i].tow;
+    const long long th = (p.Ho + cands[i].toh - 1) / cands[i].toh;
+    const long long tw = (p.Wo + cands[i].tow - 1) / cands[i].tow;
     const long long tiles = th * tw * ((a->N + cands[i].ti - 1) / cands[i].ti);
     if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best = i; }
   }
-  if (best_tiles > 0x7fffffffLL) return set_error(YAMB_EINVAL, "block_eval: too many tiles");
-  p.tiles_h = (a->H + cands[best].toh - 1) / cands[best].toh;
-  p.tiles_w = (a->W + cands[best].tow - 1) / cands[best].tow;
-  if (best == 0) return launch_eval<EvGeom<7, 16, 1>>(p, a, st);
-  if (best == 1) return launch_eval<EvGeom<7, 14, 1>>(p, a, st);
-  return launch_eval<EvGeom<7, 7, 2>>(p, a, st);
+  if (best == 0)
+    return ex ? launch_eval<EvGeom<1, 7, 16, 1, 4>, true>(p, a, st)
+              : launch_eval<EvGeom<1, 7, 16, 1, 4>, false>(p, a, st);
+  if (best == 1)
+    return ex ? launch_eval<EvGeom<1, 7, 14, 1, 4>, true>(p, a, st)
+              : launch_eval<EvGeom<1, 7, 14, 1, 4>, false>(p, a, st);
+  return ex ? launch_eval<EvGeom<1, 7, 7, 2, 4>, true>(p, a, st)
+            : launch_eval<EvGeom<1, 7, 7, 2, 4>, false>(p, a, st);
 }
 
 }  // namespace yamb

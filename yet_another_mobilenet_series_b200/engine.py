@@ -1336,22 +1336,25 @@ EVAL_FUSED_CALLS = 0     # blocks that went through yamb_block_eval_fwd (tests /
 
 def fused_eval_supported(block, x):
     """True when yamb_block_eval_fwd covers this block for this call: no gradient wanted, every
-    BatchNorm normalising with running statistics, unfused single-branch block with expansion,
-    3x3 stride-1 depthwise (reference models/mobilenet_base.py:380-421; the 12 such blocks of
-    MobileNetV2-1.0), channel counts the kernel's tiles hold."""
+    BatchNorm normalising with running statistics, unfused single-branch block with a 3x3
+    depthwise, stride 1 or 2, with or without expansion (reference models/mobilenet_base.py:380-421;
+    all 17 blocks of MobileNetV2-1.0), channel counts the kernel's tiles hold."""
     if not EVAL_FUSED or torch.is_grad_enabled() or hasattr(block, "expand_conv"):
         return False
-    if not getattr(block, "expand", False) or block.stride != 1:
+    if block.stride not in (1, 2) or not hasattr(block, "ops"):
         return False
     if list(block.kernel_sizes) != [3] or len(block.channels) != 1:
         return False
     cin, chid, cout = block.input_dim, block.channels[0], block.output_dim
     if cin % 8 or chid % 8 or cout % 8 or cin > 256 or cout > 320:
         return False
+    if not block.expand and chid != cin:
+        return False
     if x.dim() != 4 or x.shape[0] * x.shape[2] * x.shape[3] >= 2 ** 30:
         return False
     op = block.ops[0]
-    for bn in (op[0][1], op[1][1], block.pw_bn):
+    bns = (op[0][1], op[1][1], block.pw_bn) if block.expand else (op[0][1], block.pw_bn)
+    for bn in bns:
         if not isinstance(bn, torch.nn.BatchNorm2d) or bn.training or \
                 not bn.track_running_stats or bn.running_mean is None:
             return False
@@ -1368,42 +1371,47 @@ def fused_eval_forward(block, x):
     dev = x.device
     N, Cin, H, W = x.shape
     op = block.ops[0]
-    conv_e, bn1, conv_d, bn2, conv_p, bn3 = op[0][0], op[0][1], op[1][0], op[1][1], op[2], \
-        block.pw_bn
-    Chid, Cout = block.channels[0], block.output_dim
+    if block.expand:
+        conv_e, bn1, conv_d, bn2, conv_p = op[0][0], op[0][1], op[1][0], op[1][1], op[2]
+    else:
+        conv_e, bn1, conv_d, bn2, conv_p = None, None, op[0][0], op[0][1], op[1]
+    bn3 = block.pw_bn
+    Chid, Cout, stride = block.channels[0], block.output_dim, block.stride
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     st = block.__dict__.get("_yamb_eval")
     if st is None:
         st = block.__dict__["_yamb_eval"] = _ScratchDict()
     key = dev.index
     own = st.get(key)
     if own is None:
-        own = (torch.empty(Chid, Cin, device=dev, dtype=torch.bfloat16),
+        own = (torch.empty(Chid, Cin, device=dev, dtype=torch.bfloat16) if block.expand else None,
                torch.empty(Cout, Chid, device=dev, dtype=torch.bfloat16))
         st[key] = own
     with torch.no_grad():
-        w1 = _bf16_operand(conv_e.weight, own[0], (Chid, Cin))
+        w1 = _bf16_operand(conv_e.weight, own[0], (Chid, Cin)) if block.expand else None
         w3 = _bf16_operand(conv_p.weight, own[1], (Cout, Chid))
-    y = torch.empty((N, Cout, H, W), device=dev, dtype=torch.bfloat16,
+    y = torch.empty((N, Cout, Ho, Wo), device=dev, dtype=torch.bfloat16,
                     memory_format=torch.channels_last)
     a = nat.BlockEval()
     a.N, a.H, a.W = N, H, W
     a.Cin, a.Chid, a.Cout = Cin, Chid, Cout
-    a.kernel, a.stride = 3, 1
+    a.kernel, a.stride = 3, stride
     a.act = act_code_of(block.active_fn)
     a.residual = 1 if block.use_res_connect else 0
     a.x, a.y = x.data_ptr(), y.data_ptr()
-    a.w_expand, a.w_project = w1.data_ptr(), w3.data_ptr()
+    a.w_expand, a.w_project = nat.ptr(w1), w3.data_ptr()
     a.w_dw = conv_d.weight.data_ptr()
     for dst, bn in ((a.bn1, bn1), (a.bn2, bn2), (a.bn3, bn3)):
+        if bn is None:
+            continue
         dst.gamma = nat.ptr(bn.weight)
         dst.beta = nat.ptr(bn.bias)
         dst.running_mean = bn.running_mean.data_ptr()
         dst.running_var = bn.running_var.data_ptr()
         dst.eps = bn.eps
-    M = N * H * W
     launch(lib_fn("yamb_block_eval_fwd"), a, "block_eval",
-           2 * M * (Cin * (2 if block.use_res_connect else 1) + Cout),
-           2 * M * Chid * (Cin + Cout + 9))
+           2 * (N * H * W * Cin * (2 if block.use_res_connect else 1) + N * Ho * Wo * Cout),
+           2 * Chid * (N * H * W * (Cin if block.expand else 0) + N * Ho * Wo * (Cout + 9)))
     EVAL_FUSED_CALLS += 1
     return y
 
