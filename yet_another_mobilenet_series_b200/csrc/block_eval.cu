@@ -86,7 +86,7 @@ struct EvGeom {
                 "tile geometry (warp 7 must stay free of stencil work)");
 };
 
-template <class G, bool EXPAND>
+template <class G, bool EXPAND, bool LEAN>
 __global__ void __launch_bounds__(256, 2)
 block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ BlockEvalDev p) {
@@ -141,7 +141,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const ActParam ap = make_act(p.act);
-  const bool lean = ap.kind == 0;   // relu / relu6 / none: clamp the packed bf16 pair
+  constexpr bool lean = LEAN;       // relu / relu6 / none: clamp the packed bf16 pair
   const uint32_t lo2 = pack_bf16(ap.lo, ap.lo), hi2 = pack_bf16(ap.hi, ap.hi);
 
   // ---- per-slice coefficient tables (double-buffered), fetched one slice ahead into registers ----
@@ -257,6 +257,13 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     {
       const int n = g * TI + e1_ti, yy = ty * TOH * S + e1_dy, xx = tx * TOW * S + e1_dx;
       e1_inside = e1_r < NPI && n < p.N && (unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W;
+      // zero padding of the depthwise input: this thread's row of the a1 tile, once per tile (the
+      // previous tile's stencil reads are behind its last S3, this tile's first are behind S2)
+      if (EXPAND && !e1_inside && e1_r < NPI) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(sH1 + e1_r * kH1Pitch + j * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
     for (int c = 0; c < NC; ++c, ++gc) {
       const bool last_c = c + 1 == NC;
@@ -317,9 +324,8 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
               for (int e = 0; e < 4; ++e) ow[e] = pack_bf16(v[2 * e], v[2 * e + 1]);
             }
-            uint4 o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            if (!e1_inside) o = make_uint4(0u, 0u, 0u, 0u);
-            if (e1_r < NPI) *reinterpret_cast<uint4*>(dst + cb * 2) = o;
+            // rows outside the image were zeroed at the start of the tile and stay zero
+            if (e1_inside) *reinterpret_cast<uint4*>(dst + cb * 2) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
           }
         }
       } else {
@@ -518,8 +524,8 @@ static int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_
   return 0;
 }
 
-template <class G, bool EXPAND>
-static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t st) {
+template <class G, bool EXPAND, bool LEAN>
+static int launch_eval_act(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t st) {
   // ---- shared-memory plan (bytes from the 1024-aligned base) ----
   // x tile: NPI rows of 128 B per 64-channel panel; the second 128-row MMA tile of a panel reads
   // past them (rows that are never used): those reads stay inside this CTA's allocation
@@ -579,10 +585,10 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
   {
     std::lock_guard<std::mutex> lock(mu);
     if (attr < smem) {
-      cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND>,
+      cudaError_t e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND, LEAN>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e == cudaSuccess)   // two CTAs of ~90 KB need the largest shared-memory carve-out
-        e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(block_eval_kernel<G, EXPAND, LEAN>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  (int)cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval attr: %s", cudaGetErrorString(e));
       attr = smem;
@@ -599,10 +605,17 @@ static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t s
   if (dbg)
     fprintf(stderr, "block_eval: tiles %d grid %d per_sm %d smem %d tmem_cols %d Npad %d NC %d KB %d\n",
             p.num_tiles, grid, per_sm, smem, cols, p.Npad, p.NC, p.KB);
-  block_eval_kernel<G, EXPAND><<<grid, 256, smem, st>>>(tmX, tmW1, tmW3, p);
+  block_eval_kernel<G, EXPAND, LEAN><<<grid, 256, smem, st>>>(tmX, tmW1, tmW3, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(YAMB_ECUDA, "block_eval launch: %s", cudaGetErrorString(e));
   return 0;
+}
+
+template <class G, bool EXPAND>
+static int launch_eval(BlockEvalDev& p, const yamb_block_eval* a, cudaStream_t st) {
+  // relu / relu6 / none are clamps of the packed bf16 pair; swish / h-swish take the generic path
+  const bool lean = a->act == YAMB_ACT_NONE || a->act == YAMB_ACT_RELU || a->act == YAMB_ACT_RELU6;
+  return lean ? launch_eval_act<G, EXPAND, true>(p, a, st) : launch_eval_act<G, EXPAND, false>(p, a, st);
 }
 
 int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
