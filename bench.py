@@ -224,6 +224,43 @@ def torch_gpu_context(batch=256, steps=5, warmup=3, device=None, config="mobilen
     return out
 
 
+def eval_forward_context(batch, device, config="mobilenet_v2", iters=10):
+    """Supplementary (not the headline metric): model.eval() forward under no_grad on this GPU —
+    the validation path of the reference (common.py:67-80).  Blocks that yamb_block_eval_fwd covers
+    run in ONE launch with no intermediate in HBM (csrc/block_eval.cu); `four_launch_ms` is the same
+    forward with YAMB_EVAL_FUSED off (expand GEMM, depthwise, project GEMM, BN apply per block)."""
+    from yet_another_mobilenet_series_b200 import engine
+    model = build_model(config=config).to(device).eval()
+    x = torch.randn(batch, 3, 224, 224, device=device).to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+
+    def timed():
+        with torch.no_grad():
+            for _ in range(3):
+                model(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                model(x)
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    c0 = engine.EVAL_FUSED_CALLS
+    ms = timed()
+    n_one = (engine.EVAL_FUSED_CALLS - c0) // (iters + 3)
+    prev = engine.EVAL_FUSED
+    engine.EVAL_FUSED = False
+    try:
+        ms4 = timed()
+    finally:
+        engine.EVAL_FUSED = prev
+    return {"ms": round(ms, 3), "img_per_s": round(batch / ms * 1e3), "batch": batch,
+            "one_launch_blocks": n_one, "four_launch_ms": round(ms4, 3),
+            "note": "eager launches, activations of consecutive iterations exceed L2"}
+
+
 def run_torch_gpu(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -443,6 +480,7 @@ def run_ours(args):
         }
     base = None
     gpu_ctx = None
+    eval_ctx = None
     if world == 1 and not args.no_cpu_baseline:
         base, _ = cpu_baseline()
         base["host_cpu"] = host_cpu()
@@ -450,6 +488,10 @@ def run_ours(args):
         del ts
         torch.cuda.empty_cache()
         gpu_ctx = torch_gpu_context(B, device=dev, config=args.config)
+        try:
+            eval_ctx = eval_forward_context(B, dev, config=args.config)
+        except Exception as e:                      # supplementary: never takes the line down
+            eval_ctx = {"error": repr(e)[:200]}
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
     e2e_val = B * world * args.steps / (e2e_ms * 1e-3)
@@ -477,6 +519,7 @@ def run_ours(args):
         "eager_profiled_step_ms": round(eager_ms, 3),
         "cpu_baseline": base,
         "gpu_context": gpu_ctx,
+        "eval_forward": eval_ctx,
         "loss_first_last": [loss0, loss_end],
     }
     print(json.dumps(line))

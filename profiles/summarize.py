@@ -149,6 +149,57 @@ def block(rnd, name="b3"):
     print("block summary written")
 
 
+def eval_blocks(rnd, names=("b1", "b2", "b3", "b8", "b15")):
+    """ncu --set full of the one-launch eval-mode block kernel (csrc/block_eval.cu) on several
+    MobileNetV2 blocks at N = 256 (tests/gpu_profile_block.py with YAMB_PROFILE_EVAL=1)."""
+    path = os.path.join(SRC, "%s_ncu_eval_raw.csv" % rnd)
+    if not os.path.exists(path):
+        return
+    hdr, body = read_ncu_csv(path)
+    units = read_ncu_csv.units or [""] * len(hdr)
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def num(r, key):
+        v, u = r[col[key]], units[col[key]]
+        x = float(v.replace(",", ""))
+        scale = {"Gbyte": 1e3, "Mbyte": 1.0, "Kbyte": 1e-3, "byte": 1e-6, "us": 1, "ns": 1e-3, "ms": 1e3}
+        return x * scale.get(u, 1.0)
+    want = [("gpu__time_duration.sum", "time us"), ("dram__bytes_read.sum", "dram rd MB"),
+            ("dram__bytes_write.sum", "dram wr MB"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+            ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+            ("sm__warps_active.avg.per_cycle_active", "warps/cycle"),
+            ("smsp__inst_executed.sum", "warp instr"),
+            ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+            ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
+            ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_sb"),
+            ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_sb"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid"),
+            ("launch__shared_mem_per_block_dynamic", "smem KB"),
+            ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+    rows = [r for r in body if len(r) >= len(hdr) and "block_eval_kernel" in r[col["Kernel Name"]]]
+    with open(os.path.join(OUT, "%s_ncu_eval_summary.md" % rnd), "w") as f:
+        f.write("# %s — ncu --set full, eval-mode block in ONE launch (`yamb::block_eval_kernel`), "
+                "N=256\n\n" % rnd)
+        f.write("`YAMB_PROFILE_EVAL=1 ncu --set full --clock-control none -k regex:block_eval python "
+                "tests/gpu_profile_block.py %s` (one profiled launch per block after two warm-up "
+                "iterations; serialised, cold caches).  Algorithmic bytes of a block: x read once "
+                "(twice with the skip connection), y written once — the hidden tensors never reach "
+                "HBM, so `dram rd + wr` here IS the block's whole traffic.\n\n" % " ".join(names))
+        f.write("| block | " + " | ".join(w[1] for w in want) + " |\n|---|" + "---|" * len(want) + "\n")
+        for name, r in zip(names, rows):
+            cells = []
+            for key, _ in want:
+                if key not in col:
+                    cells.append("-")
+                    continue
+                x = num(r, key)
+                cells.append("%.0f" % x if x >= 1000 else "%.2f" % x if x < 10 else "%.1f" % x)
+            f.write("| %s | " % BLOCK_DESC.get(name, name) + " | ".join(cells) + " |\n")
+    print("eval block summary written:", len(rows), "kernels")
+
+
 def bench_launches(rnd):
     """ncu launch list of `python bench.py --steps 2 --warmup 1` itself
     (`ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv`): trimmed CSV +
@@ -200,3 +251,4 @@ if __name__ == "__main__":
     for b in ("b1", "b2", "b3", "b8", "b15"):
         block(rnd, b)
     bench_launches(rnd)
+    eval_blocks(rnd)
