@@ -229,6 +229,7 @@ def eval_forward_context(batch, device, config="mobilenet_v2", iters=10):
     the validation path of the reference (common.py:67-80).  Blocks that yamb_block_eval_fwd covers
     run in ONE launch with no intermediate in HBM (csrc/block_eval.cu); `four_launch_ms` is the same
     forward with YAMB_EVAL_FUSED off (expand GEMM, depthwise, project GEMM, BN apply per block)."""
+    import torch
     from yet_another_mobilenet_series_b200 import engine
     model = build_model(config=config).to(device).eval()
     x = torch.randn(batch, 3, 224, 224, device=device).to(torch.bfloat16).contiguous(
