@@ -676,25 +676,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.has_bnf) {
               if (rmax == 32) {
                 // full sub-tile: 4 independent accumulator sets (a 32-deep dependent chain of
-                // LDS -> FADD/FFMA was ~1500 cycles on the epilogue's critical path per sub-tile)
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-                auto rowf = [&](int r, float& S0, float& S1, float& Q0, float& Q1) {
+                // LDS -> FADD/FFMA was ~1500 cycles on the epilogue's critical path per sub-tile);
+                // packed fp32x2: one FFMA2 adds the column pair, one squares-and-adds it
+                float2 sA = make_float2(0.f, 0.f), sB = sA, sC = sA, sD = sA;
+                float2 qA = sA, qB = sA, qC = sA, qD = sA;
+                const float2 one2 = make_float2(1.f, 1.f);
+                auto rowf = [&](int r, float2& S, float2& Q) {
                   const uint32_t u = *reinterpret_cast<const uint32_t*>(
                       sO + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-                  const float a = bf16lo(u), b = bf16hi(u);
-                  S0 += a; S1 += b;
-                  Q0 = fmaf(a, a, Q0); Q1 = fmaf(b, b, Q1);
+                  const float2 v = make_float2(bf16lo(u), bf16hi(u));
+                  S = ffma2(one2, v, S);
+                  Q = ffma2(v, v, Q);
                 };
 #pragma unroll
                 for (int r = 0; r < 32; r += 4) {
-                  rowf(r, a0, b0, c0, d0);
-                  rowf(r + 1, a1, b1, c1, d1);
-                  rowf(r + 2, a2, b2, c2, d2);
-                  rowf(r + 3, a3, b3, c3, d3);
+                  rowf(r, sA, qA);
+                  rowf(r + 1, sB, qB);
+                  rowf(r + 2, sC, qC);
+                  rowf(r + 3, sD, qD);
                 }
-                s0 = (a0 + a1) + (a2 + a3); s1 = (b0 + b1) + (b2 + b3);
-                q0 = (c0 + c1) + (c2 + c3); q1 = (d0 + d1) + (d2 + d3);
+                s0 = (sA.x + sB.x) + (sC.x + sD.x); s1 = (sA.y + sB.y) + (sC.y + sD.y);
+                q0 = (qA.x + qB.x) + (qC.x + qD.x); q1 = (qA.y + qB.y) + (qC.y + qD.y);
               } else {
                 for (int r = 0; r < rmax; ++r) {
                   const uint32_t u = *reinterpret_cast<const uint32_t*>(
@@ -705,29 +707,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             } else {
-              const float m0 = cz_m[c], m1 = cz_m[c + 1], r0 = cz_r[c], r1 = cz_r[c + 1];
-              float sa = 0.f, sb = 0.f, sc2 = 0.f, sd = 0.f, ta = 0.f, tb = 0.f, tc = 0.f, td = 0.f;
-              float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f, ra = 0.f, rb2 = 0.f, rc = 0.f, rd = 0.f;
-              auto rowacc = [&](int r, float& S0, float& S1, float& Q0, float& Q1) {
+              // sum(dz), sum(dz * xhat) with xhat = h * r - m * r: three packed FFMA2 per row
+              const float2 r2 = make_float2(cz_r[c], cz_r[c + 1]);
+              const float2 nmr2 = make_float2(-cz_m[c] * r2.x, -cz_m[c + 1] * r2.y);
+              const float2 one2 = make_float2(1.f, 1.f), zero2 = make_float2(0.f, 0.f);
+              float2 sA = zero2, sB = zero2, sC = zero2, sD = zero2;
+              float2 qA = zero2, qB = zero2, qC = zero2, qD = zero2;
+              auto rowacc = [&](int r, float2& S, float2& Q) {
                 const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
                 const uint32_t u = *reinterpret_cast<const uint32_t*>(sO + off);
                 const uint32_t hh = *reinterpret_cast<const uint32_t*>(s_h + off);
-                const float a = bf16lo(u), b = bf16hi(u);
-                S0 += a; S1 += b;
-                Q0 = fmaf(a, (bf16lo(hh) - m0) * r0, Q0);
-                Q1 = fmaf(b, (bf16hi(hh) - m1) * r1, Q1);
+                const float2 a = make_float2(bf16lo(u), bf16hi(u));
+                const float2 xh = ffma2(make_float2(bf16lo(hh), bf16hi(hh)), r2, nmr2);
+                S = ffma2(one2, a, S);
+                Q = ffma2(a, xh, Q);
               };
               int r = 0;
 #pragma unroll 2
               for (; r + 3 < rmax; r += 4) {   // four independent accumulator sets
-                rowacc(r, sa, ta, qa, ra);
-                rowacc(r + 1, sb, tb, qb, rb2);
-                rowacc(r + 2, sc2, tc, qc, rc);
-                rowacc(r + 3, sd, td, qd, rd);
+                rowacc(r, sA, qA);
+                rowacc(r + 1, sB, qB);
+                rowacc(r + 2, sC, qC);
+                rowacc(r + 3, sD, qD);
               }
-              for (; r < rmax; ++r) rowacc(r, sa, ta, qa, ra);
-              s0 = (sa + sb) + (sc2 + sd); s1 = (ta + tb) + (tc + td);
-              q0 = (qa + qb) + (qc + qd); q1 = (ra + rb2) + (rc + rd);
+              for (; r < rmax; ++r) rowacc(r, sA, qA);
+              s0 = (sA.x + sB.x) + (sC.x + sD.x); s1 = (sA.y + sB.y) + (sC.y + sD.y);
+              q0 = (qA.x + qB.x) + (qC.x + qD.x); q1 = (qA.y + qB.y) + (qC.y + qD.y);
             }
             if (reg_stats) {
               switch (sub) {  // constant register indices in every case
