@@ -371,12 +371,12 @@ typedef struct yamb_bn_eval {
 typedef struct yamb_block_eval {
   int32_t N, H, W;            /* input pixels (NHWC); output (H-1)/stride+1 x (W-1)/stride+1 */
   int32_t Cin, Chid, Cout;    /* multiples of 8; Cin <= 256, Cout <= 320 */
-  int32_t kernel, stride;     /* 3; 1 or 2 */
+  int32_t kernel, stride;     /* 3, 5 or 7 (5 / 7: with expansion, relu / relu6); 1 or 2 */
   int32_t act;                /* YAMB_ACT_* of the two inner activations */
   int32_t residual;           /* y += x (needs Cin == Cout, stride 1) */
   const void* x;              /* bf16 [N,H,W,Cin] */
   const void* w_expand;       /* bf16 [Chid][Cin], or NULL: no expansion (Chid == Cin, bn1 unused) */
-  const float* w_dw;          /* fp32 [Chid][3][3] */
+  const float* w_dw;          /* fp32 [Chid][k][k] */
   const void* w_project;      /* bf16 [Cout][Chid] */
   yamb_bn_eval bn1, bn2, bn3; /* over Chid, Chid, Cout channels */
   void* y;                    /* bf16 [N,Ho,Wo,Cout] */

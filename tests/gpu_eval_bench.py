@@ -60,8 +60,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=20)
-    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "eval_bench.json"))
+    ap.add_argument("--config", default="mobilenet_v2",
+                    help="mobilenet_v2 | proxyless_mobile | atomnas_c+ | autonl_l (bench.py --config)")
+    ap.add_argument("--out", default=None)
     args = ap.parse_args()
+    if args.out is None:
+        args.out = os.path.join(ROOT, "gpurun_out", "eval_bench%s.json" % (
+            "" if args.config == "mobilenet_v2" else "_" + args.config.replace("+", "plus")))
     import __graft_entry__ as g
     g.build()
     import bench
@@ -69,23 +74,23 @@ def main():
     from yet_another_mobilenet_series_b200 import engine
     dev = torch.device("cuda")
     torch.backends.cudnn.benchmark = True
-    model = bench.build_model().to(dev).eval()
+    model = bench.build_model(config=args.config).to(dev).eval()
     N = args.batch
     flush = torch.zeros(64 << 20, device=dev)
     x = torch.randn(N, 3, 224, 224, device=dev).to(torch.bfloat16).contiguous(
         memory_format=torch.channels_last)
-    res = {"batch": N, "blocks": []}
+    res = {"config": args.config, "batch": N, "blocks": []}
     # ---- per block ----
     feats = list(model.features)
     h = x
     with torch.no_grad():
         for i, m in enumerate(feats):
-            if hasattr(m, "pw_bn"):
+            if hasattr(m, "use_res_connect") and hasattr(m, "channels"):
                 inp = h
-                rec = {"block": sum(hasattr(q, "pw_bn") for q in feats[:i + 1]),
-                       "shape": "%dx%dx%d -> %d (hidden %d, stride %d)" % (
+                rec = {"block": sum(hasattr(q, "use_res_connect") for q in feats[:i + 1]),
+                       "shape": "%dx%dx%d -> %d (hidden %d, k %s, stride %d)" % (
                            inp.shape[1], inp.shape[2], inp.shape[3], m.output_dim,
-                           sum(m.channels), m.stride),
+                           sum(m.channels), list(m.kernel_sizes), m.stride),
                        "one_launch": bool(engine.fused_eval_supported(m, inp))}
                 M_in = inp.shape[0] * inp.shape[2] * inp.shape[3]
                 ho = (inp.shape[2] - 1) // m.stride + 1
@@ -95,7 +100,7 @@ def main():
                 rec["alg_MB"] = round(alg / 1e6, 1)
                 if rec["one_launch"]:
                     t1, n1 = kernel_time(lambda: m(inp), args.iters, flush)
-                    assert n1 == 1
+                    assert n1 == 1, n1
                     rec["one_launch_us"] = round(t1 * 1e3, 1)
                     rec["one_launch_GBps"] = round(alg / t1 / 1e6, 1)
                 engine.EVAL_FUSED = False

@@ -31,10 +31,10 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def _make_block(cin, chid, cout, act, seed, stride=1, expand=True):
+def _make_block(cin, chid, cout, act, seed, stride=1, expand=True, k=3):
     from yet_another_mobilenet_series_b200 import mobilenet_base as mb
     torch.manual_seed(seed)
-    blk = mb.InvertedResidualChannels(cin, cout, stride, [chid], [3], expand,
+    blk = mb.InvertedResidualChannels(cin, cout, stride, [chid], [k], expand,
                                       active_fn=mb.get_active_fn({"relu": "nn.ReLU", "relu6": "nn.ReLU6",
                                                                 "swish": "nn.Swish"}[act]),
                                       batch_norm_kwargs={"momentum": 0.01, "eps": 1e-3})
@@ -74,6 +74,17 @@ CASES = [
     (32, 32, 16, 2, 112, 112, "relu", 1, False),    # MobileNetV2 block 1
     (96, 96, 96, 3, 14, 14, "relu6", 1, False),     # two 64-channel panels, skip connection
     (24, 24, 40, 2, 30, 30, "relu", 2, False),      # no expansion + stride 2
+    # 5x5 / 7x7 depthwise (Proxyless-mobile, apps/mobilenet/proxyless_mobile_mnas.yml)
+    (16, 48, 32, 2, 112, 112, "relu6", 2, True, 5),   # 112 -> 56, k5 s2: 6x7 outputs per tile
+    (40, 120, 40, 3, 28, 28, "relu6", 1, True, 5),    # k5 s1, 7x14 tiles
+    (80, 240, 80, 3, 14, 14, "relu6", 1, True, 5),
+    (96, 288, 96, 5, 7, 7, "relu", 1, True, 5),       # two images per tile, 5x5
+    (32, 96, 40, 2, 56, 56, "relu6", 2, True, 7),     # k7 s2: 4x7 outputs from a 13x19 tile
+    (96, 576, 192, 3, 14, 14, "relu6", 2, True, 7),
+    (192, 576, 192, 3, 7, 7, "relu6", 1, True, 7),    # k7 s1: one 7x7 image per tile, 3 K panels
+    (192, 1152, 320, 2, 7, 7, "relu6", 1, True, 7),   # 18 slices, 320-column accumulator
+    (24, 72, 24, 2, 19, 11, "relu", 1, True, 7),      # odd sizes, 7x7
+    (24, 72, 24, 2, 19, 11, "relu", 2, True, 5),      # odd sizes, 5x5 stride 2
 ]
 
 
@@ -86,8 +97,9 @@ def test_fused_eval_block(built_lib, case):
     torch.backends.cuda.matmul.allow_tf32 = False
     cin, chid, cout, N, H, W, act = case[:7]
     stride, expand = (case[7], case[8]) if len(case) > 7 else (1, True)
+    k = case[9] if len(case) > 9 else 3
     dev = torch.device("cuda")
-    blk = _make_block(cin, chid, cout, act, sum(case[:6]), stride, expand)
+    blk = _make_block(cin, chid, cout, act, sum(case[:6]), stride, expand, k)
     g = torch.Generator().manual_seed(7)
     x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
     # ---- oracle with the kernel's rounding points (CPU) ----
@@ -131,6 +143,37 @@ def test_fused_eval_block(built_lib, case):
     assert _rel(y, y4) < 1e-2
 
 
+def test_proxyless_eval_uses_the_one_launch_blocks(built_lib):
+    """Proxyless-mobile (k in {3,5,7}, reference apps/mobilenet/proxyless_mobile_mnas.yml): all 20
+    blocks in one launch each; logits vs the reference graph in fp32 with the autocast yardstick."""
+    from _cfg import build_from_cfg
+    from oracle import torch_model as tm
+    from yet_another_mobilenet_series_b200 import engine
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda")
+    model, _ = build_from_cfg("proxyless_mobile")
+    g = torch.Generator().manual_seed(5)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1, generator=g)
+            m.running_var.uniform_(0.8, 1.25, generator=g)
+    model = model.to(dev).eval()
+    x = torch.randn(8, 3, 224, 224, generator=g).to(dev)
+    c0 = engine.EVAL_FUSED_CALLS
+    with torch.no_grad():
+        y = model(x).float()
+    torch.cuda.synchronize()
+    assert engine.EVAL_FUSED_CALLS - c0 == 20
+    ref = tm.as_reference(copy.deepcopy(model)).eval()
+    with torch.no_grad():
+        yt = ref(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ya = ref(x.contiguous(memory_format=torch.channels_last)).float()
+    eo, ea = _rel(y, yt), _rel(ya, yt)
+    assert eo <= SLACK * ea + FLOOR, (eo, ea)
+
+
 def test_fused_eval_needs_no_grad_and_eval_mode(built_lib):
     """Gradient wanted or a BatchNorm in training mode -> the four-launch autograd path."""
     from yet_another_mobilenet_series_b200 import engine
@@ -167,7 +210,7 @@ def test_fused_eval_abi_rejects_what_it_does_not_cover(built_lib):
     st = torch.cuda.current_stream().cuda_stream
     assert lib.yamb_block_eval_fwd(C.byref(a), st) == 0
     torch.cuda.synchronize()
-    for field, bad in (("stride", 3), ("kernel", 5), ("Cin", 12), ("Cout", 328), ("Cin", 264)):
+    for field, bad in (("stride", 3), ("kernel", 4), ("Cin", 12), ("Cout", 328), ("Cin", 264)):
         b = nat.BlockEval.from_buffer_copy(a)
         setattr(b, field, bad)
         assert lib.yamb_block_eval_fwd(C.byref(b), st) == -1, field

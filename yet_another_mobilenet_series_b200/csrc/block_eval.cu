@@ -67,16 +67,18 @@ struct BlockEvalDev {
 };
 
 constexpr int kH1Pitch = 144;    // bytes per pixel of the a1 tile: 64 bf16 + 16 (conflict-free, no swizzle)
-constexpr int kTabFloats = 832;  // s1 t1 s2 t2 [64] + taps [9][64]
+// one set of per-slice tables: s1 t1 s2 t2 [64] + taps [K*K][64]
+__host__ __device__ constexpr int tab_floats(int k) { return 256 + k * k * 64; }
 
 // Output tile TI images x TOH x TOW pixels (<= 128 = the M of the project MMA); the input tile with
 // its one-pixel halo is the M of the expand MMAs (2 tiles of 128 rows, rows >= NPI are don't-care).
 // Stencil threads (warps 0-6 = 224 threads): a thread owns CPT channels (64 / CPT channel groups)
 // and RUN consecutive outputs of one output row.
-template <int S_, int TOH_, int TOW_, int TI_, int CPT_>
+template <int K_, int S_, int TOH_, int TOW_, int TI_, int CPT_>
 struct EvGeom {
-  static constexpr int S = S_, TOH = TOH_, TOW = TOW_, TI = TI_, CPT = CPT_;
-  static constexpr int IH = (TOH - 1) * S + 3, IW = (TOW - 1) * S + 3;
+  static constexpr int K = K_, S = S_, TOH = TOH_, TOW = TOW_, TI = TI_, CPT = CPT_;
+  static constexpr int P = (K - 1) / 2;
+  static constexpr int IH = (TOH - 1) * S + K, IW = (TOW - 1) * S + K;
   static constexpr int NPI = TI * IH * IW;
   static constexpr int NPO = TI * TOH * TOW;
   static constexpr int RUN = (TOW % 8 == 0) ? 8 : 7;   // consecutive outputs of one row per stencil thread
@@ -90,6 +92,7 @@ template <class G, bool EXPAND, bool LEAN>
 __global__ void __launch_bounds__(256, 2)
 block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ BlockEvalDev p) {
+  constexpr int K = G::K, P = G::P, kTabFloats = tab_floats(G::K);
   constexpr int S = G::S, TOH = G::TOH, TOW = G::TOW, TI = G::TI, IH = G::IH, IW = G::IW;
   constexpr int NPI = G::NPI, NPO = G::NPO, RUN = G::RUN, NRUN = G::NRUN, CPT = G::CPT, NCG = G::NCG;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -147,8 +150,11 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // ---- per-slice coefficient tables (double-buffered), fetched one slice ahead into registers ----
   // threads 0..127: BatchNorm1 / BatchNorm2 of hidden channel slice*64 + tid%64;
   // thread (ch = tid/4, q = tid%4 < 3): taps 3q..3q+2 of that channel
-  float pre_s = 0.f, pre_t = 0.f, pre_w[3] = {0.f, 0.f, 0.f};
-  auto tab_fetch = [&](int c) {
+  float pre_s = 0.f, pre_t = 0.f;
+  // tab_fetch(c, tb): BatchNorm coefficients of slice c into registers (tab_store publishes them);
+  // the K*K taps of its 64 channels go global -> tb by 4-byte cp.async (tid -> channel tid/4,
+  // taps tid%4, tid%4 + 4, ...), complete before the S3 that precedes their first reader
+  auto tab_fetch = [&](int c, float* tb) {
     if (tid < 128) {
       const BnEvalDev& b = tid < 64 ? p.bn1 : p.bn2;
       const int hc = c * 64 + (tid & 63);
@@ -159,11 +165,15 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         pre_t = (b.beta ? __ldg(b.beta + hc) : 0.f) - __ldg(b.mean + hc) * pre_s;
       }
     }
-    const int hc = c * 64 + (tid >> 2), q = tid & 3;
-    const bool ok = q < 3 && hc < p.Chid;
-    const float* src = p.wdw + (size_t)hc * 9 + q * 3;
+    const int ch = tid >> 2, hc = c * 64 + ch;
+    const bool ok = hc < p.Chid;
+    const float* src = p.wdw + (size_t)(ok ? hc : 0) * (K * K);
+    const uint32_t dst = smem_u32(tb + 256 + ch);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pre_w[k] = ok ? __ldg(src + k) : 0.f;
+    for (int tp = (tid & 3); tp < K * K; tp += 4)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (uint32_t)(tp * 256)),
+                   "l"(src + tp), "r"(ok ? 4 : 0) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto tab_store = [&](float* tb) {
     if (tid < 128) {
@@ -171,11 +181,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       tb[which * 128 + ch] = pre_s;          // s1 at 0, s2 at 128
       tb[which * 128 + 64 + ch] = pre_t;     // t1 at 64, t2 at 192
     }
-    const int q = tid & 3;
-    if (q < 3) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) tb[256 + (q * 3 + k) * 64 + (tid >> 2)] = pre_w[k];
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // this thread's taps have landed
   };
 
   // ---- the control thread: TMA + tcgen05.mma ----------------------------------------------------
@@ -188,8 +194,8 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto tma_x = [&](int t) {            // x tile of tile t: one 4-D box per 64-channel panel
     const int tx = t % p.tiles_w, ty = (t / p.tiles_w) % p.tiles_h, g = t / (p.tiles_w * p.tiles_h);
     for (int kb = 0; kb < p.KB; ++kb)
-      tma_load_4d(&tmX, bar_ld, sX_u + (uint32_t)(kb * p.xpanel_bytes), kb * 64, tx * TOW * S - 1,
-                  ty * TOH * S - 1, g * TI);
+      tma_load_4d(&tmX, bar_ld, sX_u + (uint32_t)(kb * p.xpanel_bytes), kb * 64, tx * TOW * S - P,
+                  ty * TOH * S - P, g * TI);
   };
   auto tma_w1 = [&](int c) {
     for (int kb = 0; kb < p.KB; ++kb)
@@ -223,7 +229,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   // epilogue 1: this thread's pixel row of the input tile (warps 0-3: rows 0..127, 4-7: 128..255)
   const int e1_r = (warp >> 2) * 128 + (warp & 3) * 32 + lane;
   const int e1_ti = e1_r / (IH * IW);
-  const int e1_dy = (e1_r % (IH * IW)) / IW - 1, e1_dx = (e1_r % (IH * IW)) % IW - 1;
+  const int e1_dy = (e1_r % (IH * IW)) / IW - P, e1_dx = (e1_r % (IH * IW)) % IW - P;
   // stencil: RUN consecutive outputs of one row x 4 channels
   const int cg = tid % NCG, sp = tid / NCG;
   const int r0 = sp * RUN;
@@ -236,7 +242,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int NC = p.NC;
   int t = blockIdx.x;
-  tab_fetch(0);
+  tab_fetch(0, tab);
   tab_store(tab);
   if (control) {
     mbar_arrive_expect_tx(bar_ld, (uint32_t)(p.KB * (NPI * 128 + (EXPAND ? 8192 : 0))));
@@ -279,7 +285,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (last_c) tma_x(t + gridDim.x);
             tma_w1(last_c ? 0 : c + 1);
           }
-          tab_fetch(last_c ? 0 : c + 1);   // registers; stored before S3
+          tab_fetch(last_c ? 0 : c + 1, tab + ((gc + 1) & 1) * kTabFloats);   // published before S3
         }
         __syncwarp();                   // warp 7 reconverges before the warp-wide tcgen05.ld
         // ---- epilogue 1: a1 = bf16(act(bn1(h1))), zero outside the image, -> sH1[pixel][64] ----
@@ -336,7 +342,7 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           mbar_wait(bar_ld, ld_par);    // every thread follows this barrier in the no-expand variant
           ld_par ^= 1;
         }
-        if (has_next) tab_fetch(last_c ? 0 : c + 1);
+        if (has_next) tab_fetch(last_c ? 0 : c + 1, tab + ((gc + 1) & 1) * kTabFloats);
         if (tid < NPI) {
           const uint8_t* src = smem + c * p.xpanel_bytes + tid * 128;
           uint8_t* dst = sH1 + tid * kH1Pitch;
@@ -371,28 +377,30 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         __syncwarp();
       } else if (sp < NRUN) {
-        // ---- 3x3 stencil: RUN consecutive outputs of one row x CPT channels per thread ----
+        // ---- KxK stencil: RUN consecutive outputs of one row x CPT channels per thread; the taps
+        //      of one kernel row at a time in registers ----
         constexpr int NV = CPT / 2;          // packed fp32 pairs per pixel
         float2 o2[RUN][NV];
 #pragma unroll
         for (int j = 0; j < RUN; ++j)
 #pragma unroll
           for (int v = 0; v < NV; ++v) o2[j][v] = make_float2(0.f, 0.f);
-        float2 w2[9][NV];
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp) {
-          if (CPT == 4) {
-            const float4 wv = *reinterpret_cast<const float4*>(tb + 256 + tp * 64 + cg * 4);
-            w2[tp][0] = make_float2(wv.x, wv.y);
-            w2[tp][NV - 1] = make_float2(wv.z, wv.w);
-          } else {
-            w2[tp][0] = *reinterpret_cast<const float2*>(tb + 256 + tp * 64 + cg * 2);
+        for (int ky = 0; ky < K; ++ky) {
+          float2 w2[K][NV];
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float* wp = tb + 256 + (ky * K + kx) * 64 + cg * CPT;
+            if (CPT == 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wp);
+              w2[kx][0] = make_float2(wv.x, wv.y);
+              w2[kx][NV - 1] = make_float2(wv.z, wv.w);
+            } else {
+              w2[kx][0] = *reinterpret_cast<const float2*>(wp);
+            }
           }
-        }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-          for (int ixx = 0; ixx < (RUN - 1) * S + 3; ++ixx) {
+          for (int ixx = 0; ixx < (RUN - 1) * S + K; ++ixx) {
             float2 av[NV];
             if (CPT == 4) {
               const uint2 a = *reinterpret_cast<const uint2*>(s_hb + (ky * IW + ixx) * kH1Pitch);
@@ -405,9 +413,9 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
             for (int j = 0; j < RUN; ++j) {
               const int kx = ixx - j * S;   // compile-time after unrolling
-              if (kx >= 0 && kx < 3) {
+              if (kx >= 0 && kx < K) {
 #pragma unroll
-                for (int v = 0; v < NV; ++v) o2[j][v] = ffma2(w2[ky * 3 + kx][v], av[v], o2[j][v]);
+                for (int v = 0; v < NV; ++v) o2[j][v] = ffma2(w2[kx][v], av[v], o2[j][v]);
               }
             }
           }
@@ -535,7 +543,7 @@ static int launch_eval_act(BlockEvalDev& p, const yamb_block_eval* a, cudaStream
   p.off_w3 = off; off += p.Npad * 128;
   p.off_h2 = (off + 1023) & ~1023; off = p.off_h2 + 16384;
   p.off_h1 = off; off += ((G::NPI * kH1Pitch) + 15) & ~15;
-  p.off_tab = off; off += 2 * kTabFloats * 4;
+  p.off_tab = off; off += 2 * tab_floats(G::K) * 4;
   p.off_c3 = off; off += 2 * p.Npad * 4;
   p.off_bars = (off + 15) & ~15; off = p.off_bars + 48;
   int smem = off;
@@ -626,9 +634,13 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
     return set_error(YAMB_EINVAL, "block_eval: channel counts must be positive multiples of 8");
   if (a->Cin > 256 || a->Cout > 320)
     return set_error(YAMB_EINVAL, "block_eval: Cin <= 256, Cout <= 320 (got %d, %d)", a->Cin, a->Cout);
-  if (a->kernel != 3 || (a->stride != 1 && a->stride != 2))
-    return set_error(YAMB_EINVAL, "block_eval: only 3x3 depthwise with stride 1 or 2 (got k=%d s=%d)",
+  if ((a->kernel != 3 && a->kernel != 5 && a->kernel != 7) || (a->stride != 1 && a->stride != 2))
+    return set_error(YAMB_EINVAL, "block_eval: depthwise k in {3,5,7}, stride 1 or 2 (got k=%d s=%d)",
                      a->kernel, a->stride);
+  if (a->kernel != 3 && (!a->w_expand || (a->act != YAMB_ACT_NONE && a->act != YAMB_ACT_RELU &&
+                                          a->act != YAMB_ACT_RELU6)))
+    return set_error(YAMB_EINVAL, "block_eval: k = 5 / 7 is built with expansion and a clamp "
+                                  "activation (relu / relu6) only");
   if (!a->w_expand && a->Chid != a->Cin)
     return set_error(YAMB_EINVAL, "block_eval: no expand weights needs Chid == Cin");
   if (a->residual && a->stride != 1)
@@ -666,30 +678,33 @@ int block_eval_launch(const yamb_block_eval* a, cudaStream_t st) {
   p.Npad = (a->Cout + 15) / 16 * 16;
   p.NC = (a->Chid + 63) / 64;
   const bool ex = a->w_expand != nullptr;
-  if (a->stride == 2) {
-    // 7x7 outputs from a 15x15 input tile (225 of the 256 expand rows), 2 channels per thread
-    return ex ? launch_eval<EvGeom<2, 7, 7, 1, 2>, true>(p, a, st)
-              : launch_eval<EvGeom<2, 7, 7, 1, 2>, false>(p, a, st);
+  // fewest tiles among the geometries of (k, stride); each holds its input tile in <= 256 rows
+  auto tiles_of = [&](int toh, int tow, int ti) {
+    return (long long)((p.Ho + toh - 1) / toh) * ((p.Wo + tow - 1) / tow) * ((a->N + ti - 1) / ti);
+  };
+  if (a->kernel == 3) {
+    if (a->stride == 2)   // 7x7 outputs from a 15x15 input tile, 2 channels per stencil thread
+      return ex ? launch_eval<EvGeom<3, 2, 7, 7, 1, 2>, true>(p, a, st)
+                : launch_eval<EvGeom<3, 2, 7, 7, 1, 2>, false>(p, a, st);
+    const long long t0 = tiles_of(7, 16, 1), t1 = tiles_of(7, 14, 1), t2 = tiles_of(7, 7, 2);
+    if (t0 <= t1 && t0 <= t2)
+      return ex ? launch_eval<EvGeom<3, 1, 7, 16, 1, 4>, true>(p, a, st)
+                : launch_eval<EvGeom<3, 1, 7, 16, 1, 4>, false>(p, a, st);
+    if (t1 <= t2)
+      return ex ? launch_eval<EvGeom<3, 1, 7, 14, 1, 4>, true>(p, a, st)
+                : launch_eval<EvGeom<3, 1, 7, 14, 1, 4>, false>(p, a, st);
+    return ex ? launch_eval<EvGeom<3, 1, 7, 7, 2, 4>, true>(p, a, st)
+              : launch_eval<EvGeom<3, 1, 7, 7, 2, 4>, false>(p, a, st);
   }
-  // stride 1: the tile geometry that needs the fewest tiles
-  struct Cand { int toh, tow, ti; };
-  const Cand cands[3] = {{7, 16, 1}, {7, 14, 1}, {7, 7, 2}};
-  int best = 0;
-  long long best_tiles = -1;
-  for (int i = 0; i < 3; ++i) {
-    const long long th = (p.Ho + cands[i].toh - 1) / cands[i].toh;
-    const long long tw = (p.Wo + cands[i].tow - 1) / cands[i].tow;
-    const long long tiles = th * tw * ((a->N + cands[i].ti - 1) / cands[i].ti);
-    if (best_tiles < 0 || tiles < best_tiles) { best_tiles = tiles; best = i; }
+  if (a->kernel == 5) {
+    if (a->stride == 2) return launch_eval_act<EvGeom<5, 2, 6, 7, 1, 2>, true, true>(p, a, st);
+    const long long t0 = tiles_of(7, 16, 1), t1 = tiles_of(7, 14, 1), t2 = tiles_of(7, 7, 2);
+    if (t0 <= t1 && t0 <= t2) return launch_eval_act<EvGeom<5, 1, 7, 16, 1, 4>, true, true>(p, a, st);
+    if (t1 <= t2) return launch_eval_act<EvGeom<5, 1, 7, 14, 1, 4>, true, true>(p, a, st);
+    return launch_eval_act<EvGeom<5, 1, 7, 7, 2, 4>, true, true>(p, a, st);
   }
-  if (best == 0)
-    return ex ? launch_eval<EvGeom<1, 7, 16, 1, 4>, true>(p, a, st)
-              : launch_eval<EvGeom<1, 7, 16, 1, 4>, false>(p, a, st);
-  if (best == 1)
-    return ex ? launch_eval<EvGeom<1, 7, 14, 1, 4>, true>(p, a, st)
-              : launch_eval<EvGeom<1, 7, 14, 1, 4>, false>(p, a, st);
-  return ex ? launch_eval<EvGeom<1, 7, 7, 2, 4>, true>(p, a, st)
-            : launch_eval<EvGeom<1, 7, 7, 2, 4>, false>(p, a, st);
+  if (a->stride == 2) return launch_eval_act<EvGeom<7, 2, 4, 7, 1, 2>, true, true>(p, a, st);
+  return launch_eval_act<EvGeom<7, 1, 7, 7, 1, 2>, true, true>(p, a, st);
 }
 
 }  // namespace yamb

@@ -1336,14 +1336,15 @@ EVAL_FUSED_CALLS = 0     # blocks that went through yamb_block_eval_fwd (tests /
 
 def fused_eval_supported(block, x):
     """True when yamb_block_eval_fwd covers this block for this call: no gradient wanted, every
-    BatchNorm normalising with running statistics, unfused single-branch block with a 3x3
-    depthwise, stride 1 or 2, with or without expansion (reference models/mobilenet_base.py:380-421;
-    all 17 blocks of MobileNetV2-1.0), channel counts the kernel's tiles hold."""
+    BatchNorm normalising with running statistics, unfused single-branch block with a 3x3 / 5x5 /
+    7x7 depthwise, stride 1 or 2, with or without expansion (reference
+    models/mobilenet_base.py:380-421; every block of MobileNetV2-1.0 and of Proxyless-mobile),
+    channel counts the kernel's tiles hold."""
     if not EVAL_FUSED or torch.is_grad_enabled() or hasattr(block, "expand_conv"):
         return False
     if block.stride not in (1, 2) or not hasattr(block, "ops"):
         return False
-    if list(block.kernel_sizes) != [3] or len(block.channels) != 1:
+    if len(block.channels) != 1 or list(block.kernel_sizes)[0] not in (3, 5, 7):
         return False
     cin, chid, cout = block.input_dim, block.channels[0], block.output_dim
     if cin % 8 or chid % 8 or cout % 8 or cin > 256 or cout > 320:
@@ -1359,9 +1360,11 @@ def fused_eval_supported(block, x):
                 not bn.track_running_stats or bn.running_mean is None:
             return False
     try:
-        act_code_of(block.active_fn)
+        act = act_code_of(block.active_fn)
     except ValueError:
         return False
+    if block.kernel_sizes[0] != 3 and (not block.expand or act not in (0, 1, 2)):
+        return False        # k = 5 / 7: built with expansion and relu / relu6 only
     return True
 
 
@@ -1395,7 +1398,7 @@ def fused_eval_forward(block, x):
     a = nat.BlockEval()
     a.N, a.H, a.W = N, H, W
     a.Cin, a.Chid, a.Cout = Cin, Chid, Cout
-    a.kernel, a.stride = 3, stride
+    a.kernel, a.stride = block.kernel_sizes[0], stride
     a.act = act_code_of(block.active_fn)
     a.residual = 1 if block.use_res_connect else 0
     a.x, a.y = x.data_ptr(), y.data_ptr()
@@ -1411,7 +1414,8 @@ def fused_eval_forward(block, x):
         dst.eps = bn.eps
     launch(lib_fn("yamb_block_eval_fwd"), a, "block_eval",
            2 * (N * H * W * Cin * (2 if block.use_res_connect else 1) + N * Ho * Wo * Cout),
-           2 * Chid * (N * H * W * (Cin if block.expand else 0) + N * Ho * Wo * (Cout + 9)))
+           2 * Chid * (N * H * W * (Cin if block.expand else 0) +
+                       N * Ho * Wo * (Cout + block.kernel_sizes[0] ** 2)))
     EVAL_FUSED_CALLS += 1
     return y
 
