@@ -8,21 +8,24 @@
 // input tile plus a one-pixel halo: SURVEY.md §7.1 step 2 / §7.2, BASELINE.json's "fused block".
 //
 // Persistent CTAs (two per SM where shared memory and TMEM allow) walk output tiles of <= 112
-// pixels (7x16, 7x14 or two 7x7 images).  Per tile:
-//   x tile (+halo, <= 162 pixels) --TMA 4-D box, zero fill outside the image--> smem (A operand)
+// pixels (k = 3, stride 1: 7x16, 7x14 or two 7x7 images; stride 2 and k = 5 / 7: smaller tiles whose
+// input tile with its halo still fits the 256 rows of two MMA tiles).  Per tile:
+//   x tile (+halo, <= 256 pixels) --TMA 4-D box, zero fill outside the image--> smem (A operand)
 //   for every 64-channel slice of the hidden dimension:
 //     W1 slice, W3 slice --TMA--> smem
 //     tcgen05.mma  [256 px x Cin] x [Cin x 64]       -> TMEM (fp32)                   expand
 //     tcgen05.ld -> BatchNorm1 + act -> bf16, zero outside the image -> smem          epilogue 1
-//     3x3 stencil on the CUDA cores (FFMA2) -> BatchNorm2 + act -> bf16 -> smem (A operand layout)
+//     kxk stencil on the CUDA cores (FFMA2) -> BatchNorm2 + act -> bf16 -> smem (A operand layout)
 //     tcgen05.mma  [128 px x 64] x [64 x Cout]  accumulated over the slices -> TMEM   project
 //   tcgen05.ld -> BatchNorm3 (+ x) -> bf16 -> global                                  epilogue 2
+// Blocks without the 1x1 expansion (hidden == input) skip the first MMA: the x panel itself is the
+// stencil input.
 // HBM traffic: x once (+ halo re-reads from L2), y once; the hidden tensors (6 x the block's
 // input) never leave the SM.  BatchNorm folding (gamma * rsqrt(var + eps), beta - mean * scale) is
 // done by the kernel from the module's own buffers: no preparation launches.
 //
-// Roles: 8 warps; all of them run the two epilogues, warps 0-6 run the stencil (14 runs of 7 or 8
-// outputs x 16 channel groups), and while they do, ONE thread of warp 7 drives the machine: TMA
+// Roles: 8 warps; all of them run the two epilogues, warps 0-6 run the stencil (runs of 7 or 8
+// consecutive outputs of a row x 16 or 32 channel groups), and while they do, ONE thread of warp 7 drives the machine: TMA
 // loads of the next operands, tcgen05.mma of the next slice's expand and of this slice's project.
 // Every staging buffer is single and refilled right after its last reader retired:
 //   wait expand(gc) | TMA W1(gc+1) [+ x of the next tile] | epilogue 1 | S2 | TMA W3(gc),
@@ -426,8 +429,6 @@ block_eval_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           s2v[v] = *reinterpret_cast<const float2*>(tb + 128 + cg * CPT + 2 * v);
           t2v[v] = *reinterpret_cast<const float2*>(tb + 192 + cg * CPT + 2 * v);
         }
-        constexpr int kBoff = 0;
-        (void)kBoff;
         const int boff = cg * CPT * 2;       // byte offset of this thread's channels inside a row
 #pragma unroll
         for (int j = 0; j < RUN; ++j) {
