@@ -29,6 +29,15 @@ CASES = [
     (2, 9, 9, 32, 0, 32, 3, 1, 0, False),
     (1, 7, 7, 960, 0, 960, 3, 1, 1, True),
     (2, 16, 16, 48, 8, 40, 5, 2, 4, True),
+    # narrow branches of searched networks: 8- / 16-channel tiles (csrc/depthwise_narrow.cu) are
+    # selected for C <= 8 with >= 28 rows and C <= 16 with >= 14 rows
+    (2, 56, 56, 40, 24, 8, 3, 1, 3, True),       # AtomNAS block 3: 24 | 8 | 8 channels at 56 x 56
+    (2, 56, 56, 40, 32, 8, 7, 1, 3, True),
+    (2, 57, 59, 24, 0, 8, 5, 2, 1, True),        # odd sizes, stride 2
+    (3, 30, 29, 56, 16, 16, 3, 2, 2, True),      # 16-channel tiles
+    (2, 28, 28, 56, 40, 16, 5, 1, 3, True),
+    (2, 33, 31, 16, 0, 16, 7, 2, 3, True),
+    (2, 64, 64, 8, 0, 8, 3, 1, 0, False),        # no prologue
 ]
 
 
