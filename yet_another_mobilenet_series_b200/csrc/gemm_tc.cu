@@ -177,6 +177,7 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
   // ~0.1 IPC and the loaders bounded the GEMM).  `lean`: clamp-type activation, no SE gate.
   const bool lean = ap.kind == 0 && gate == nullptr;
   const uint32_t swz = (uint32_t)(lc << 4);
+  const float inv_rps = pixbase < (1u << 24) - 1024u ? 1.0f / (float)rps : 0.f;   // 0: divide
 #pragma unroll 1
   for (int rb = rbeg + (ln >> cs); rb < rows; rb += RS * NB) {
     uint4 v[NB], w[MODE == 2 ? NB : 1];
@@ -235,7 +236,18 @@ __device__ __forceinline__ void gxform_panel(uint32_t panel, uint32_t panel2, co
         act_vec<8>(x, ap);
         if (gate != nullptr && cok && r < rlimit) {
           // SE: the gate multiplies the bf16-rounded activation (oracle rounding points)
-          const float* gr = gate + (size_t)((pixbase + (unsigned)r) / rps) * C + c0;
+          // sample index = pixel / pixels-per-sample without an integer division: float reciprocal
+          // (pixel indices < 2^24 are exact in fp32) and a one-step correction either way
+          const unsigned pix = pixbase + (unsigned)r;
+          unsigned smp;
+          if (inv_rps != 0.f) {
+            smp = (unsigned)__fmul_rz((float)pix, inv_rps);
+            if (smp * rps > pix) --smp;
+            else if ((smp + 1u) * rps <= pix) ++smp;
+          } else {
+            smp = pix / rps;
+          }
+          const float* gr = gate + (size_t)smp * C + c0;
           const float4 q0 = __ldg(reinterpret_cast<const float4*>(gr));
           const float4 q1 = __ldg(reinterpret_cast<const float4*>(gr + 4));
           const float gq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
