@@ -272,11 +272,15 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n, int a
 // ----------------------------------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SWISH = 3, ACT_HSWISH = 4 };
 
+// swish = z * sigmoid(z): MUFU.EX2 + MUFU.RCP (`__fdividef`, 2 ulp) instead of the IEEE division's
+// ~8-instruction sequence — the values are rounded to bf16 (2^-9) right after; exp(-z) = inf gives
+// z / inf = -0, the limit.  The operand transforms of the Swish networks are bound by exactly these
+// instructions.
 __device__ __forceinline__ float act_fwd(float z, int act) {
   switch (act) {
     case ACT_RELU: return fmaxf(z, 0.f);
     case ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
-    case ACT_SWISH: return z / (1.f + __expf(-z));
+    case ACT_SWISH: return __fdividef(z, 1.f + __expf(-z));
     case ACT_HSWISH: return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
     default: return z;
   }
@@ -287,7 +291,7 @@ __device__ __forceinline__ float act_bwd(float z, int act) {
     case ACT_RELU: return z > 0.f ? 1.f : 0.f;
     case ACT_RELU6: return (z > 0.f && z < 6.f) ? 1.f : 0.f;
     case ACT_SWISH: {
-      float s = 1.f / (1.f + __expf(-z));
+      float s = __fdividef(1.f, 1.f + __expf(-z));
       return s * (1.f + z * (1.f - s));
     }
     case ACT_HSWISH: return z <= -3.f ? 0.f : (z >= 3.f ? 1.f : (2.f * z + 3.f) * (1.f / 6.f));
@@ -309,7 +313,7 @@ __device__ __forceinline__ ActParam make_act(int act) {
 }
 __device__ __forceinline__ float act_rt(float z, const ActParam& a) {
   if (a.kind == 0) return fminf(fmaxf(z, a.lo), a.hi);
-  if (a.kind == ACT_SWISH) return z / (1.f + __expf(-z));
+  if (a.kind == ACT_SWISH) return __fdividef(z, 1.f + __expf(-z));
   return z * fminf(fmaxf(z + 3.f, 0.f), 6.f) * (1.f / 6.f);
 }
 // d act / dz for the clamp family: 1 strictly inside (lo, hi), else 0
@@ -338,7 +342,7 @@ __device__ __forceinline__ void act_vec(float (&x)[N], const ActParam& a) {
     for (int i = 0; i < N; ++i) x[i] = fminf(fmaxf(x[i], a.lo), a.hi);
   } else if (a.kind == ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] = x[i] / (1.f + __expf(-x[i]));
+    for (int i = 0; i < N; ++i) x[i] = __fdividef(x[i], 1.f + __expf(-x[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = x[i] * fminf(fmaxf(x[i] + 3.f, 0.f), 6.f) * (1.f / 6.f);
