@@ -231,3 +231,43 @@ def test_kernel_scratch_does_not_travel_with_a_deepcopy():
         assert torch.equal(a, b), k
     r = pickle.loads(pickle.dumps(seq[1]))
     assert r.__dict__["_yamb_lin"] is None
+
+
+def test_one_launch_eval_dispatch_rules():
+    """engine.fused_eval_supported decides from module structure only (no GPU needed): eval +
+    no_grad + unfused single-branch k in {3,5,7}; everything else keeps the four-launch path."""
+    from yet_another_mobilenet_series_b200 import engine
+    bn = {"momentum": 0.01, "eps": 1e-3}
+    relu, swish = mb.get_active_fn("nn.ReLU6"), mb.get_active_fn("nn.Swish")
+    x = torch.zeros(2, 32, 14, 14)
+
+    def blk(*a, **k):
+        return mb.InvertedResidualChannels(*a, **k).eval()
+
+    plain = blk(32, 32, 1, [192], [3], True, active_fn=relu, batch_norm_kwargs=bn)
+    assert not engine.fused_eval_supported(plain, x)              # gradient mode is on
+    with torch.no_grad():
+        assert engine.fused_eval_supported(plain, x)
+        assert engine.fused_eval_supported(blk(32, 64, 2, [192], [7], True, active_fn=relu,
+                                               batch_norm_kwargs=bn), x)
+        assert engine.fused_eval_supported(blk(32, 16, 1, [32], [3], False, active_fn=relu,
+                                               batch_norm_kwargs=bn), x)
+        assert engine.fused_eval_supported(blk(32, 32, 1, [96], [3], True, active_fn=swish,
+                                               batch_norm_kwargs=bn), x)
+        # not covered: Swish with k = 5, several branches, odd widths, the fused class, train mode
+        assert not engine.fused_eval_supported(blk(32, 32, 1, [96], [5], True, active_fn=swish,
+                                                   batch_norm_kwargs=bn), x)
+        assert not engine.fused_eval_supported(blk(32, 32, 1, [48, 48], [3, 5], True, active_fn=relu,
+                                                   batch_norm_kwargs=bn), x)
+        assert not engine.fused_eval_supported(blk(32, 32, 1, [90], [3], True, active_fn=relu,
+                                                   batch_norm_kwargs=bn), x)
+        fused = mb.InvertedResidualChannelsFused(32, 32, 1, [96], [3], True, active_fn=relu,
+                                                 batch_norm_kwargs=bn).eval()
+        assert not engine.fused_eval_supported(fused, x)
+        assert not engine.fused_eval_supported(plain.train(), x)
+        plain.eval()
+        prev, engine.EVAL_FUSED = engine.EVAL_FUSED, False
+        try:
+            assert not engine.fused_eval_supported(plain, x)      # YAMB_EVAL_FUSED=0
+        finally:
+            engine.EVAL_FUSED = prev
